@@ -1,0 +1,592 @@
+// C ABI of the engine (include/aesgcm_b200.h).  Host-side glue only: argument
+// checks, kernel parameter blocks, scratch buffers, and the chunked
+// host<->device pipeline.  All arithmetic happens in kernels.cu; there is no
+// CPU implementation of the datapath in this library.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/aesgcm_b200.h"
+#include "kernels.h"
+
+namespace {
+
+constexpr int kSlots = 3;
+constexpr size_t kChunkBytes = 32u << 20;  // host pipeline granule
+constexpr size_t kMaxChunks = 8192;
+constexpr uint64_t kAadInlineMax = 4096;   // bytes of AAD folded inside k_stream_finish
+constexpr uint64_t kMaxBlocks = 0xFFFFFFFEull;
+
+// scratch layout (bytes) inside ctx->d_scratch
+constexpr size_t SC_PART_CT = 0;     // 16
+constexpr size_t SC_TAGCALC = 32;    // 16
+constexpr size_t SC_OK = 48;         // 1
+constexpr size_t SC_TAG = 64;        // 16 (host API)
+constexpr size_t SC_KEY = 96;        // 32 raw key upload
+constexpr size_t SC_PARTS = 256;     // list of 16 B partials for finish (user parts + AAD part)
+constexpr size_t SC_PARTS_MAX = 1024;
+constexpr size_t SC_BYTES = SC_PARTS + 16 * (SC_PARTS_MAX + 1);
+
+}  // namespace
+
+struct agcm_ctx {
+    int device = 0, sm_count = 0, ncta = 0, nt = 0;
+    uint32_t* d_te0 = nullptr;
+    KeyDev* d_key = nullptr;
+    uint32_t* d_parts = nullptr;  // 2 x AG_MAX_CTA x 4 words: [0] CT partials, [1] AAD partials
+    uint8_t* d_scratch = nullptr;
+    uint32_t h_rk[60];
+    uint8_t h_H[16];
+    int nr = 0;
+    bool key_set = false;
+    cudaError_t last_err = cudaSuccess;
+    uint64_t launches = 0;
+    // host pipeline (lazy)
+    cudaStream_t hs[kSlots] = {nullptr, nullptr, nullptr};
+    uint8_t* d_stage[kSlots] = {nullptr, nullptr, nullptr};
+    uint8_t* d_stage_aux[kSlots] = {nullptr, nullptr, nullptr};  // iv / aad / tag / ok for batch chunks
+    uint32_t* d_stage_parts[kSlots] = {nullptr, nullptr, nullptr};
+    uint8_t* d_chunk_partials = nullptr;
+    uint8_t* d_aad_stage = nullptr;
+    size_t aad_stage_cap = 0;
+    bool pipeline_ready = false;
+};
+
+namespace {
+
+int cuda_fail(agcm_ctx* c, cudaError_t e)
+{
+    if (c) c->last_err = e;
+    return AGCM_E_CUDA;
+}
+
+#define AG_CUDA(ctx, call)                              \
+    do {                                                \
+        cudaError_t _e = (call);                        \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e); \
+    } while (0)
+
+int mode_to_nr(int mode)
+{
+    switch (mode) {
+        case 128: return 10;
+        case 192: return 12;
+        case 256: return 14;
+    }
+    return 0;
+}
+
+void iv_words(const uint8_t iv[12], uint32_t w[3])
+{
+    for (int i = 0; i < 3; ++i)
+        w[i] = (uint32_t)iv[4 * i] | ((uint32_t)iv[4 * i + 1] << 8) | ((uint32_t)iv[4 * i + 2] << 16) |
+               ((uint32_t)iv[4 * i + 3] << 24);
+}
+
+// GHASH partial of `n_bytes` at d_in (optionally also CTR) -> 16 B at d_partial16,
+// scaled by H^blocks_after.  parts_raw: per-CTA scratch (AG_MAX_CTA x 4 words).
+int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
+               uint64_t n_bytes, uint64_t blocks_after, uint32_t* parts_raw, uint8_t* d_partial16, cudaStream_t st)
+{
+    if (n_bytes == 0) {
+        if (d_partial16) AG_CUDA(c, cudaMemsetAsync(d_partial16, 0, 16, st));
+        return AGCM_OK;
+    }
+    StreamParams p;
+    memcpy(p.rk, c->h_rk, sizeof(p.rk));
+    iv_words(iv, p.iv);
+    p.ctr0 = (uint32_t)(2 + first_block);
+    p.n_bytes = n_bytes;
+    p.in = d_in;
+    p.out = d_out;
+    p.key = c->d_key;
+    p.te0 = c->d_te0;
+    p.partials = parts_raw;
+    AG_CUDA(c, ag_launch_stream(p, c->nr, mode, c->ncta, c->nt, st));
+    c->launches++;
+    if (mode != AG_MODE_CTR_ONLY && d_partial16) {
+        AG_CUDA(c, ag_launch_reduce_scale(c->d_key, parts_raw, (uint32_t)c->ncta, blocks_after, d_partial16, st));
+        c->launches++;
+    }
+    return AGCM_OK;
+}
+
+// parts16: device list of n_parts partials (natural byte order), may live anywhere.
+int run_finish(agcm_ctx* c, int decrypt, const uint8_t iv[12], const uint8_t* d_parts16, int n_parts, const uint8_t* d_aad,
+               uint64_t aad_len, uint64_t ct_len, uint8_t* d_tag, uint8_t* d_ok, cudaStream_t st)
+{
+    if (n_parts < 0 || (size_t)n_parts > SC_PARTS_MAX) return AGCM_E_BAD_ARG;
+    if (decrypt && (!d_tag || !d_ok)) return AGCM_E_BAD_ARG;
+    if (!decrypt && !d_tag) return AGCM_E_BAD_ARG;
+    const uint64_t n_ct_blocks = (ct_len + 15) >> 4;
+    if (n_ct_blocks > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
+    const uint8_t* parts = d_parts16;
+    int np = n_parts;
+    const uint8_t* aad_inline = (aad_len && d_aad) ? d_aad : nullptr;
+    if (aad_len && !d_aad) return AGCM_E_BAD_ARG;
+    if (aad_len > kAadInlineMax) {
+        // bulk AAD: same grid-wide Horner in GHASH-only mode, weighted by H^(n_ct_blocks)
+        uint8_t* list = c->d_scratch + SC_PARTS;
+        if (n_parts) AG_CUDA(c, cudaMemcpyAsync(list, d_parts16, 16 * (size_t)n_parts, cudaMemcpyDeviceToDevice, st));
+        int rc = run_stream(c, AG_MODE_GHASH_ONLY, iv, 0, d_aad, nullptr, aad_len, n_ct_blocks,
+                            c->d_parts + 4 * AG_MAX_CTA, list + 16 * (size_t)n_parts, st);
+        if (rc) return rc;
+        parts = list;
+        np = n_parts + 1;
+        aad_inline = nullptr;
+    }
+    FinishParams f;
+    memcpy(f.rk, c->h_rk, sizeof(f.rk));
+    f.nr = (uint32_t)c->nr;
+    iv_words(iv, f.iv);
+    f.key = c->d_key;
+    f.te0 = c->d_te0;
+    f.parts = parts;
+    f.n_parts = (uint32_t)np;
+    f.aad = aad_inline;
+    f.aad_len = aad_len;
+    f.ct_len = ct_len;
+    f.tag_calc = decrypt ? c->d_scratch + SC_TAGCALC : d_tag;
+    f.tag_expected = decrypt ? d_tag : nullptr;
+    f.ok = decrypt ? d_ok : nullptr;
+    AG_CUDA(c, ag_launch_finish(f, st));
+    c->launches++;
+    return AGCM_OK;
+}
+
+int ensure_pipeline(agcm_ctx* c)
+{
+    if (c->pipeline_ready) return AGCM_OK;
+    for (int s = 0; s < kSlots; ++s) {
+        AG_CUDA(c, cudaStreamCreateWithFlags(&c->hs[s], cudaStreamNonBlocking));
+        AG_CUDA(c, cudaMalloc(&c->d_stage[s], kChunkBytes));
+        AG_CUDA(c, cudaMalloc(&c->d_stage_aux[s], kChunkBytes / 8));
+        AG_CUDA(c, cudaMalloc(&c->d_stage_parts[s], sizeof(uint32_t) * 4 * AG_MAX_CTA));
+    }
+    AG_CUDA(c, cudaMalloc(&c->d_chunk_partials, 16 * kMaxChunks));
+    c->pipeline_ready = true;
+    return AGCM_OK;
+}
+
+int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len)
+{
+    if (lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32) return lanes;
+    if (lanes != 0) return -1;
+    // enough groups to occupy every lane of the persistent grid, but never more
+    // lanes than blocks in a message
+    const uint64_t total_lanes = (uint64_t)c->ncta * c->nt;
+    uint64_t g = 1;
+    while (g < 32 && n_msgs * g * 2 <= total_lanes) g <<= 1;
+    const uint64_t blocks = (avg_len + 15) / 16 + 1;
+    while (g > 1 && g > blocks) g >>= 1;
+    return (int)g;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* agcm_strerror(int rc)
+{
+    switch (rc) {
+        case AGCM_OK: return "ok";
+        case AGCM_E_BAD_MODE: return "bad mode / key length (expected 128, 192 or 256 bits)";
+        case AGCM_E_BAD_LEN: return "bad length";
+        case AGCM_E_COUNTER_OVERFLOW: return "more than 2^32-2 blocks under one IV";
+        case AGCM_E_CUDA: return "CUDA error";
+        case AGCM_E_NO_KEY: return "no key set";
+        case AGCM_E_BAD_ARG: return "bad argument";
+        case AGCM_E_NO_DEVICE: return "no sm_100 CUDA device (the engine has no CPU path)";
+    }
+    return "unknown error";
+}
+
+int agcm_ctx_create_ex(agcm_ctx** out, int device, int n_cta, int threads)
+{
+    if (!out) return AGCM_E_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return AGCM_E_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AGCM_E_NO_DEVICE;
+    if (prop.major != 10) return AGCM_E_NO_DEVICE;
+    agcm_ctx* c = new (std::nothrow) agcm_ctx();
+    if (!c) return AGCM_E_BAD_ARG;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->ncta = n_cta > 0 ? n_cta : c->sm_count;
+    c->nt = threads > 0 ? threads : AG_STREAM_NT_MAX;
+    if (c->ncta > AG_MAX_CTA || c->nt > AG_STREAM_NT_MAX || c->nt < 32 || (c->nt & (c->nt - 1))) {
+        delete c;
+        return AGCM_E_BAD_ARG;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_te0, 256 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_key, sizeof(KeyDev));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_parts, sizeof(uint32_t) * 4 * AG_MAX_CTA * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_scratch, SC_BYTES);
+    if (e == cudaSuccess) e = cudaMemset(c->d_scratch, 0, SC_BYTES);
+    if (e == cudaSuccess) {
+        uint8_t sbox[256];
+        uint32_t te0[256];
+        ag_build_sbox_te0(sbox, te0);
+        e = cudaMemcpy(c->d_te0, te0, sizeof(te0), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        agcm_ctx_destroy(c);
+        return AGCM_E_CUDA;
+    }
+    *out = c;
+    return AGCM_OK;
+}
+
+int agcm_ctx_create(agcm_ctx** out, int device) { return agcm_ctx_create_ex(out, device, 0, 0); }
+
+void agcm_ctx_destroy(agcm_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int s = 0; s < kSlots; ++s) {
+        if (c->hs[s]) cudaStreamDestroy(c->hs[s]);
+        cudaFree(c->d_stage[s]);
+        cudaFree(c->d_stage_aux[s]);
+        cudaFree(c->d_stage_parts[s]);
+    }
+    cudaFree(c->d_chunk_partials);
+    cudaFree(c->d_aad_stage);
+    cudaFree(c->d_te0);
+    cudaFree(c->d_key);
+    cudaFree(c->d_parts);
+    cudaFree(c->d_scratch);
+    delete c;
+}
+
+int agcm_last_cuda_error(const agcm_ctx* c) { return c ? (int)c->last_err : 0; }
+const char* agcm_last_cuda_error_string(const agcm_ctx* c) { return cudaGetErrorString(c ? c->last_err : cudaSuccess); }
+uint64_t agcm_launch_count(const agcm_ctx* c) { return c ? c->launches : 0; }
+
+int agcm_get_info(const agcm_ctx* c, int* n_cta, int* threads, int* sm_count)
+{
+    if (!c) return AGCM_E_BAD_ARG;
+    if (n_cta) *n_cta = c->ncta;
+    if (threads) *threads = c->nt;
+    if (sm_count) *sm_count = c->sm_count;
+    return AGCM_OK;
+}
+
+int agcm_key_expand(agcm_ctx* c, int mode, const uint8_t* d_keys, size_t n_keys, uint8_t* d_round_keys, void* stream)
+{
+    if (!c || (n_keys && (!d_keys || !d_round_keys))) return AGCM_E_BAD_ARG;
+    if (!mode_to_nr(mode)) return AGCM_E_BAD_MODE;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    AG_CUDA(c, ag_launch_key_expand(d_keys, n_keys, mode / 8, c->d_te0, d_round_keys, (cudaStream_t)stream));
+    if (n_keys) c->launches++;
+    return AGCM_OK;
+}
+
+int agcm_key_expand_host(agcm_ctx* c, int mode, const uint8_t* h_key, uint8_t* h_round_keys)
+{
+    if (!c || !h_key || !h_round_keys) return AGCM_E_BAD_ARG;
+    const int nr = mode_to_nr(mode);
+    if (!nr) return AGCM_E_BAD_MODE;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    uint8_t* d_key = c->d_scratch + SC_KEY;
+    uint8_t* d_rk = c->d_scratch + SC_PARTS;  // 240 B of the parts list area, idle outside finish
+    AG_CUDA(c, cudaMemcpy(d_key, h_key, (size_t)mode / 8, cudaMemcpyHostToDevice));
+    AG_CUDA(c, ag_launch_key_expand(d_key, 1, mode / 8, c->d_te0, d_rk, nullptr));
+    c->launches++;
+    AG_CUDA(c, cudaMemcpy(h_round_keys, d_rk, (size_t)16 * (nr + 1), cudaMemcpyDeviceToHost));
+    return AGCM_OK;
+}
+
+int agcm_set_key(agcm_ctx* c, int mode, int pre_expanded, const uint8_t* h_key, size_t key_len)
+{
+    if (!c || !h_key) return AGCM_E_BAD_ARG;
+    const int nr = mode_to_nr(mode);
+    if (!nr) return AGCM_E_BAD_MODE;
+    const size_t want = pre_expanded ? (size_t)16 * (nr + 1) : (size_t)mode / 8;
+    if (key_len != want) return AGCM_E_BAD_MODE;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    c->key_set = false;
+    uint8_t* d_rk = reinterpret_cast<uint8_t*>(c->d_key) + offsetof(KeyDev, rk);
+    if (pre_expanded) {
+        // config/config_aes_kprexp.py:66-95: Nr+1 user-loaded stages, used as they are
+        AG_CUDA(c, cudaMemcpy(d_rk, h_key, key_len, cudaMemcpyHostToDevice));
+    } else {
+        uint8_t* d_raw = c->d_scratch + SC_KEY;
+        AG_CUDA(c, cudaMemcpy(d_raw, h_key, key_len, cudaMemcpyHostToDevice));
+        AG_CUDA(c, ag_launch_key_expand(d_raw, 1, mode / 8, c->d_te0, d_rk, nullptr));
+        c->launches++;
+    }
+    const uint32_t nr_u = (uint32_t)nr;
+    AG_CUDA(c, cudaMemcpy(reinterpret_cast<uint8_t*>(c->d_key) + offsetof(KeyDev, nr), &nr_u, 4, cudaMemcpyHostToDevice));
+    AG_CUDA(c, ag_launch_key_setup(c->d_key, c->d_te0, c->nt, c->ncta, nullptr));
+    c->launches++;
+    AG_CUDA(c, cudaDeviceSynchronize());
+    memset(c->h_rk, 0, sizeof(c->h_rk));
+    AG_CUDA(c, cudaMemcpy(c->h_rk, d_rk, (size_t)16 * (nr + 1), cudaMemcpyDeviceToHost));
+    uint32_t hw[4];
+    AG_CUDA(c, cudaMemcpy(hw, reinterpret_cast<uint8_t*>(c->d_key) + offsetof(KeyDev, H), 16, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 4; ++i) {
+        c->h_H[4 * i + 0] = (uint8_t)(hw[i] >> 24);
+        c->h_H[4 * i + 1] = (uint8_t)(hw[i] >> 16);
+        c->h_H[4 * i + 2] = (uint8_t)(hw[i] >> 8);
+        c->h_H[4 * i + 3] = (uint8_t)hw[i];
+    }
+    c->nr = nr;
+    c->key_set = true;
+    return AGCM_OK;
+}
+
+int agcm_get_round_keys(const agcm_ctx* c, uint8_t* h_round_keys, size_t cap)
+{
+    if (!c || !h_round_keys) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    const size_t n = (size_t)16 * (c->nr + 1);
+    if (cap < n) return AGCM_E_BAD_LEN;
+    memcpy(h_round_keys, c->h_rk, n);
+    return (int)n;
+}
+
+int agcm_get_h(const agcm_ctx* c, uint8_t h_h16[16])
+{
+    if (!c || !h_h16) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    memcpy(h_h16, c->h_H, 16);
+    return AGCM_OK;
+}
+
+int agcm_stream_part(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in,
+                     uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, uint8_t* d_partial16, void* stream)
+{
+    if (!c || !h_iv12 || !d_partial16 || (n_bytes && (!d_in || !d_out))) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    const uint64_t nb = (n_bytes + 15) >> 4;
+    if (first_block > kMaxBlocks || nb > kMaxBlocks - first_block || blocks_after > kMaxBlocks - first_block - nb)
+        return AGCM_E_COUNTER_OVERFLOW;
+    if (blocks_after && (n_bytes & 15)) return AGCM_E_BAD_LEN;  // only the last shard may be ragged
+    AG_CUDA(c, cudaSetDevice(c->device));
+    return run_stream(c, decrypt ? AG_MODE_DEC : AG_MODE_ENC, h_iv12, first_block, d_in, d_out, n_bytes, blocks_after,
+                      c->d_parts, d_partial16, (cudaStream_t)stream);
+}
+
+int agcm_stream_finish(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const uint8_t* d_partials16, int n_parts,
+                       const uint8_t* d_aad, uint64_t aad_len, uint64_t ct_len, uint8_t* d_tag, uint8_t* d_ok, void* stream)
+{
+    if (!c || !h_iv12 || (n_parts && !d_partials16)) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    return run_finish(c, decrypt, h_iv12, d_partials16, n_parts, d_aad, aad_len, ct_len, d_tag, d_ok, (cudaStream_t)stream);
+}
+
+int agcm_stream_crypt(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const uint8_t* d_aad, uint64_t aad_len,
+                      const uint8_t* d_in, uint8_t* d_out, uint64_t n_bytes, uint8_t* d_tag, uint8_t* d_ok, void* stream)
+{
+    if (!c || !h_iv12) return AGCM_E_BAD_ARG;
+    uint8_t* part = c->d_scratch + SC_PART_CT;
+    int rc = agcm_stream_part(c, decrypt, h_iv12, 0, d_in, d_out, n_bytes, 0, part, stream);
+    if (rc) return rc;
+    return agcm_stream_finish(c, decrypt, h_iv12, part, 1, d_aad, aad_len, n_bytes, d_tag, d_ok, stream);
+}
+
+int agcm_stream_probe(agcm_ctx* c, int what, const uint8_t h_iv12[12], const uint8_t* d_in, uint8_t* d_out,
+                      uint64_t n_bytes, void* stream)
+{
+    if (!c || !h_iv12 || !d_in) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (what != AG_MODE_GHASH_ONLY && what != AG_MODE_CTR_ONLY) return AGCM_E_BAD_ARG;
+    if (what == AG_MODE_CTR_ONLY && !d_out) return AGCM_E_BAD_ARG;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    return run_stream(c, what, h_iv12, 0, d_in, d_out, n_bytes, 0, c->d_parts, c->d_scratch + SC_PART_CT,
+                      (cudaStream_t)stream);
+}
+
+static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, BatchParams& p, size_t n_msgs, void* stream)
+{
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (n_msgs == 0) return AGCM_OK;
+    if (!p.iv || !p.tag || (decrypt && !p.ok)) return AGCM_E_BAD_ARG;
+    const int g = pick_lanes(c, lanes, n_msgs, avg_len);
+    if (g < 0) return AGCM_E_BAD_ARG;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    memcpy(p.rk, c->h_rk, sizeof(p.rk));
+    p.key = c->d_key;
+    p.te0 = c->d_te0;
+    p.n_msgs = n_msgs;
+    // no more CTAs than there is work for
+    const uint64_t groups_per_cta = (uint64_t)c->nt / g;
+    uint64_t need = (n_msgs + groups_per_cta - 1) / groups_per_cta;
+    int ncta = (int)(need < (uint64_t)c->ncta ? need : (uint64_t)c->ncta);
+    AG_CUDA(c, ag_launch_batch(p, c->nr, decrypt, g, ncta, c->nt, (cudaStream_t)stream));
+    c->launches++;
+    return AGCM_OK;
+}
+
+int agcm_batch_crypt(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len_hint, const uint8_t* d_iv12,
+                     const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
+                     uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
+{
+    if (!c) return AGCM_E_BAD_ARG;
+    if (n_msgs && (!d_in_off || !d_in || !d_out)) return AGCM_E_BAD_ARG;
+    if ((d_aad == nullptr) != (d_aad_off == nullptr)) return AGCM_E_BAD_ARG;
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.iv = d_iv12;
+    p.aad = d_aad;
+    p.aad_off = d_aad_off;
+    p.in = d_in;
+    p.in_off = d_in_off;
+    p.out = d_out;
+    p.tag = d_tag;
+    p.ok = d_ok;
+    return batch_common(c, decrypt, lanes, avg_len_hint, p, n_msgs, stream);
+}
+
+int agcm_batch_crypt_uniform(agcm_ctx* c, int decrypt, int lanes, const uint8_t* d_iv12, const uint8_t* d_aad,
+                             uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out, uint64_t len,
+                             uint64_t stride, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
+{
+    if (!c) return AGCM_E_BAD_ARG;
+    if (n_msgs && len && (!d_in || !d_out)) return AGCM_E_BAD_ARG;
+    if (stride < len || (aad_len && (!d_aad || aad_stride < aad_len))) return AGCM_E_BAD_LEN;
+    if (((len + 15) >> 4) > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.iv = d_iv12;
+    p.aad = aad_len ? d_aad : nullptr;
+    p.in = d_in;
+    p.out = d_out;
+    p.tag = d_tag;
+    p.ok = d_ok;
+    p.len = len;
+    p.stride = stride;
+    p.aad_len = aad_len;
+    p.aad_stride = aad_stride;
+    return batch_common(c, decrypt, lanes, len, p, n_msgs, stream);
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------
+int agcm_host_alloc(void** out, size_t bytes)
+{
+    if (!out) return AGCM_E_BAD_ARG;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? AGCM_OK : AGCM_E_CUDA;
+}
+
+void agcm_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int agcm_stream_crypt_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const uint8_t* h_aad, uint64_t aad_len,
+                           const uint8_t* h_in, uint8_t* h_out, uint64_t n_bytes, uint8_t h_tag[16], int* h_ok)
+{
+    if (!c || !h_iv12 || !h_tag || (n_bytes && (!h_in || !h_out)) || (aad_len && !h_aad) || (decrypt && !h_ok))
+        return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    const uint64_t total_blocks = (n_bytes + 15) >> 4;
+    if (total_blocks > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
+    const uint64_t n_chunks = (n_bytes + kChunkBytes - 1) / kChunkBytes;
+    if (n_chunks > kMaxChunks || n_chunks > SC_PARTS_MAX) return AGCM_E_BAD_LEN;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc) return rc;
+    if (aad_len > c->aad_stage_cap) {
+        cudaFree(c->d_aad_stage);
+        c->d_aad_stage = nullptr;
+        c->aad_stage_cap = 0;
+        AG_CUDA(c, cudaMalloc(&c->d_aad_stage, aad_len));
+        c->aad_stage_cap = aad_len;
+    }
+    if (aad_len) AG_CUDA(c, cudaMemcpyAsync(c->d_aad_stage, h_aad, aad_len, cudaMemcpyHostToDevice, c->hs[0]));
+    const int mode = decrypt ? AG_MODE_DEC : AG_MODE_ENC;
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        const int s = (int)(k % kSlots);
+        cudaStream_t st = c->hs[s];
+        const uint64_t off = k * kChunkBytes;
+        const uint64_t nb = (n_bytes - off) < kChunkBytes ? (n_bytes - off) : kChunkBytes;
+        const uint64_t first_block = off >> 4;
+        const uint64_t after = total_blocks - first_block - ((nb + 15) >> 4);
+        AG_CUDA(c, cudaMemcpyAsync(c->d_stage[s], h_in + off, nb, cudaMemcpyHostToDevice, st));
+        rc = run_stream(c, mode, h_iv12, first_block, c->d_stage[s], c->d_stage[s], nb, after, c->d_stage_parts[s],
+                        c->d_chunk_partials + 16 * k, st);
+        if (rc) return rc;
+        AG_CUDA(c, cudaMemcpyAsync(h_out + off, c->d_stage[s], nb, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 1; s < kSlots; ++s) AG_CUDA(c, cudaStreamSynchronize(c->hs[s]));
+    uint8_t* d_tag = c->d_scratch + SC_TAG;
+    uint8_t* d_ok = c->d_scratch + SC_OK;
+    if (decrypt) AG_CUDA(c, cudaMemcpyAsync(d_tag, h_tag, 16, cudaMemcpyHostToDevice, c->hs[0]));
+    rc = run_finish(c, decrypt, h_iv12, c->d_chunk_partials, (int)n_chunks, c->d_aad_stage, aad_len, n_bytes, d_tag, d_ok,
+                    c->hs[0]);
+    if (rc) return rc;
+    uint8_t okb = 1;
+    if (decrypt) AG_CUDA(c, cudaMemcpyAsync(&okb, d_ok, 1, cudaMemcpyDeviceToHost, c->hs[0]));
+    else AG_CUDA(c, cudaMemcpyAsync(h_tag, d_tag, 16, cudaMemcpyDeviceToHost, c->hs[0]));
+    AG_CUDA(c, cudaStreamSynchronize(c->hs[0]));
+    if (h_ok) *h_ok = okb ? 1 : 0;
+    return AGCM_OK;
+}
+
+int agcm_batch_crypt_uniform_host(agcm_ctx* c, int decrypt, int lanes, const uint8_t* h_iv12, const uint8_t* h_aad,
+                                  uint64_t aad_len, uint64_t aad_stride, const uint8_t* h_in, uint8_t* h_out,
+                                  uint64_t len, uint64_t stride, uint8_t* h_tag, uint8_t* h_ok, size_t n_msgs)
+{
+    if (!c || !h_iv12 || !h_tag || (len && (!h_in || !h_out)) || (aad_len && !h_aad) || (decrypt && !h_ok))
+        return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (stride < len || (aad_len && aad_stride < aad_len)) return AGCM_E_BAD_LEN;
+    if (n_msgs == 0) return AGCM_OK;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc) return rc;
+    // messages per chunk: payload fits the stage buffer, side data fits the aux buffer
+    const uint64_t per_msg_aux = 12 + 16 + 1 + aad_stride + 16;
+    uint64_t m_chunk = stride ? kChunkBytes / stride : n_msgs;
+    const uint64_t m_aux = (kChunkBytes / 8) / per_msg_aux;
+    if (m_chunk > m_aux) m_chunk = m_aux;
+    if (m_chunk == 0) return AGCM_E_BAD_LEN;  // one record larger than the staging granule: use the stream API
+    // fix the lane count once so every chunk runs the same kernel
+    const int g = pick_lanes(c, lanes, n_msgs < m_chunk ? n_msgs : m_chunk, len);
+    if (g < 0) return AGCM_E_BAD_ARG;
+    uint64_t k = 0;
+    for (uint64_t m0 = 0; m0 < n_msgs; m0 += m_chunk, ++k) {
+        const int s = (int)(k % kSlots);
+        cudaStream_t st = c->hs[s];
+        const uint64_t nm = (n_msgs - m0) < m_chunk ? (n_msgs - m0) : m_chunk;
+        uint8_t* d_data = c->d_stage[s];
+        uint8_t* aux = c->d_stage_aux[s];
+        uint8_t* d_iv = aux;                          // nm x 12
+        uint8_t* d_tag = aux + ((12 * m_chunk + 15) & ~15ull);  // nm x 16
+        uint8_t* d_ok = d_tag + 16 * m_chunk;         // nm
+        uint8_t* d_aad = d_ok + ((m_chunk + 15) & ~15ull);
+        const uint64_t span = (nm - 1) * stride + len;
+        if (len) AG_CUDA(c, cudaMemcpyAsync(d_data, h_in + m0 * stride, span, cudaMemcpyHostToDevice, st));
+        AG_CUDA(c, cudaMemcpyAsync(d_iv, h_iv12 + 12 * m0, 12 * nm, cudaMemcpyHostToDevice, st));
+        if (aad_len)
+            AG_CUDA(c, cudaMemcpyAsync(d_aad, h_aad + m0 * aad_stride, (nm - 1) * aad_stride + aad_len, cudaMemcpyHostToDevice, st));
+        if (decrypt) AG_CUDA(c, cudaMemcpyAsync(d_tag, h_tag + 16 * m0, 16 * nm, cudaMemcpyHostToDevice, st));
+        rc = agcm_batch_crypt_uniform(c, decrypt, g, d_iv, d_aad, aad_len, aad_stride, d_data, d_data, len, stride, d_tag,
+                                      d_ok, nm, st);
+        if (rc) return rc;
+        if (len) {
+            if (stride == len) {
+                AG_CUDA(c, cudaMemcpyAsync(h_out + m0 * stride, d_data, span, cudaMemcpyDeviceToHost, st));
+            } else {
+                // keep the caller's inter-record padding untouched
+                AG_CUDA(c, cudaMemcpy2DAsync(h_out + m0 * stride, stride, d_data, stride, len, nm, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        if (decrypt) AG_CUDA(c, cudaMemcpyAsync(h_ok + m0, d_ok, nm, cudaMemcpyDeviceToHost, st));
+        else AG_CUDA(c, cudaMemcpyAsync(h_tag + 16 * m0, d_tag, 16 * nm, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < kSlots; ++s) AG_CUDA(c, cudaStreamSynchronize(c->hs[s]));
+    return AGCM_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

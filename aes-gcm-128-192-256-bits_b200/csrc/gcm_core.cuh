@@ -1,0 +1,265 @@
+// Per-thread AES-GCM work items, written once as host+device code.
+//
+// The CUDA kernels in kernels.cu call these with shared-memory lookup functors;
+// tests/host_emul.cu calls the SAME functions on the CPU with plain-array
+// functors and loops over "threads" to check the index arithmetic (front
+// padding, strided Horner weights, partial last block) against the oracle
+// before any GPU time is spent.  This is test scaffolding: the product library
+// exports no CPU path.
+//
+// GHASH decomposition (replaces the serial recurrence Y <- (Y xor X)*H of
+// src/gcm_ghash.vhd:269-272 by the equivalent polynomial, using the linearity the
+// reference itself relies on at gcm_ghash.vhd:317-344):
+//
+//   a group of G lanes shares one block sequence S_0..S_{m-1}; it is front-padded
+//   with `pad` virtual zero blocks to rows*G; lane t owns virtual blocks
+//   t, t+G, t+2G, ... and runs  Y_t <- Y_t * H^G  xor  S   per row.
+//   Then  sum_i S_i H^(m-i) = sum_t Y_t * H^(G-t).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include "aes_core.cuh"
+#include "gf128.cuh"
+
+enum : int {
+    AG_MODE_ENC = 0,         // out = in ^ KS ; GHASH over out   (src/aes_gcm.vhd:207-211, enc)
+    AG_MODE_DEC = 1,         // out = in ^ KS ; GHASH over in    (src/aes_gcm.vhd:207-211, dec)
+    AG_MODE_GHASH_ONLY = 2,  // GHASH over in (bulk AAD)
+    AG_MODE_CTR_ONLY = 3     // out = in ^ KS ; no GHASH (profiling aid)
+};
+
+constexpr int AG_MAX_CTA = 256;       // upper bound on persistent-grid size
+constexpr int AG_STREAM_NT_MAX = 1024;
+
+// Per-key derived material, resident in HBM (about 53 KB).  Written by
+// k_key_setup, read by every other kernel.
+struct KeyDev {
+    uint32_t rk[60];                        // stage keys as LE words (stage r = words 4r..4r+3)
+    uint32_t nr;                            // 10 / 12 / 14
+    uint32_t nt_stream;                     // threads per CTA the stream tables were built for
+    uint32_t ncta;                          // persistent grid size the stream tables were built for
+    uint32_t _pad;
+    gf128 H;                                // E_K(0^128)            (src/gcm_gctr.vhd:141-144)
+    gf128 pow2[64];                         // H^(2^k)
+    gf128 hpow_thread[AG_STREAM_NT_MAX + 1];// H^k, k = 0..NT
+    gf128 hpow_cta[AG_MAX_CTA + 1];         // (H^NT)^k, k = 0..ncta
+    uint4 tab[8][256];                      // Shoup tables: [j]=H^(2^j), j=0..5; [6]=H^NT; [7]=H^(NT*ncta)
+};
+
+// ---- 16-byte block I/O ------------------------------------------------------
+// nvalid in 1..16; bytes past nvalid read as zero.  Vector path when aligned.
+AG_HD void ag_load_block(const uint8_t* p, uint32_t nvalid, uint32_t x[4])
+{
+    if (nvalid == 16) {
+#if defined(__CUDA_ARCH__)
+        const uintptr_t a = (uintptr_t)p;
+        if ((a & 15) == 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(p);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+            return;
+        }
+        if ((a & 3) == 0) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+            x[0] = q[0]; x[1] = q[1]; x[2] = q[2]; x[3] = q[3];
+            return;
+        }
+#endif
+    }
+    x[0] = x[1] = x[2] = x[3] = 0;
+    for (uint32_t j = 0; j < nvalid; ++j) x[j >> 2] |= (uint32_t)p[j] << (8 * (j & 3));
+}
+
+AG_HD void ag_store_block(uint8_t* p, uint32_t nvalid, const uint32_t x[4])
+{
+    if (nvalid == 16) {
+#if defined(__CUDA_ARCH__)
+        const uintptr_t a = (uintptr_t)p;
+        if ((a & 15) == 0) {
+            *reinterpret_cast<uint4*>(p) = make_uint4(x[0], x[1], x[2], x[3]);
+            return;
+        }
+        if ((a & 3) == 0) {
+            uint32_t* q = reinterpret_cast<uint32_t*>(p);
+            q[0] = x[0]; q[1] = x[1]; q[2] = x[2]; q[3] = x[3];
+            return;
+        }
+#endif
+    }
+    for (uint32_t j = 0; j < nvalid; ++j) p[j] = (uint8_t)(x[j >> 2] >> (8 * (j & 3)));
+}
+
+// zero bytes nvalid..15 of a block held as LE words (gcm_ghash.vhd:228-246 mask)
+AG_HD void ag_mask_block(uint32_t x[4], uint32_t nvalid)
+{
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const int lo = 4 * w;
+        if ((int)nvalid <= lo) x[w] = 0;
+        else if ((int)nvalid < lo + 4) x[w] &= (1u << (8 * (nvalid - lo))) - 1u;
+    }
+}
+
+// ---- single stream: one lane of the grid-wide strided Horner ----------------
+struct StreamParams {
+    uint32_t rk[60];
+    uint32_t iv[3];       // the 12 IV bytes as LE words
+    uint32_t ctr0;        // counter of this shard's block 0 = 2 + first_block (mod 2^32; aes_icb.vhd:100)
+    uint64_t n_bytes;     // bytes in this shard
+    const uint8_t* in;
+    uint8_t* out;
+    const KeyDev* key;
+    const uint32_t* te0;  // 256-entry Te0 in HBM (per context)
+    uint32_t* partials;   // gridDim.x x 4 BE words: per-CTA GHASH partial, last block weighted H^1
+};
+
+// Returns Y_g for global lane g of Gt lanes; the caller multiplies by H^(Gt-g).
+template <int NR, int MODE, class TE, class GH>
+AG_HD gf128 ag_stream_lane(const StreamParams& p, uint64_t g, uint64_t Gt, TE&& te, GH&& gh)
+{
+    const uint64_t n_blocks = (p.n_bytes + 15) >> 4;
+    const uint64_t rows = (n_blocks + Gt - 1) / Gt;
+    const uint64_t pad = rows * Gt - n_blocks;
+    const uint32_t tail = (uint32_t)(p.n_bytes & 15);  // bytes in a short last block, 0 = full
+
+    AesCtrConst cc;
+    if (MODE != AG_MODE_GHASH_ONLY) cc = aes_ctr_precompute(p.rk, p.iv[0], p.iv[1], p.iv[2], te);
+
+    gf128 y = gf_zero();
+    uint32_t xn[4] = {0, 0, 0, 0};
+    // software prefetch: row u+1's block is requested before row u is processed
+    {
+        const uint64_t v = g;
+        if (rows && v >= pad) {
+            const uint64_t i = v - pad;
+            const uint32_t nv = (i == n_blocks - 1 && tail) ? tail : 16u;
+            ag_load_block(p.in + 16 * i, nv, xn);
+        }
+    }
+    for (uint64_t u = 0; u < rows; ++u) {
+        const uint64_t v = u * Gt + g;
+        uint32_t x[4] = {xn[0], xn[1], xn[2], xn[3]};
+        if (u + 1 < rows) {
+            const uint64_t i1 = v + Gt - pad;  // row >= 1 is never padding
+            const uint32_t nv1 = (i1 == n_blocks - 1 && tail) ? tail : 16u;
+            ag_load_block(p.in + 16 * i1, nv1, xn);
+        }
+        if (MODE != AG_MODE_CTR_ONLY && u) y = gf_mul_table(y, gh);
+        if (v >= pad) {
+            const uint64_t i = v - pad;
+            const uint32_t nv = (i == n_blocks - 1 && tail) ? tail : 16u;
+            uint32_t s[4];
+            if (MODE == AG_MODE_GHASH_ONLY) {
+                s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = x[3];
+            } else {
+                uint32_t ks[4];
+                aes_ctr_block<NR>(p.rk, cc, p.ctr0 + (uint32_t)i, te, ks);
+                uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
+                ag_store_block(p.out + 16 * i, nv, o);
+                if (MODE == AG_MODE_ENC) {
+                    if (nv != 16) ag_mask_block(o, nv);
+                    s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+                } else {
+                    s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = x[3];
+                }
+            }
+            if (MODE != AG_MODE_CTR_ONLY) {
+                y.w[0] ^= ag_bswap32(s[0]);
+                y.w[1] ^= ag_bswap32(s[1]);
+                y.w[2] ^= ag_bswap32(s[2]);
+                y.w[3] ^= ag_bswap32(s[3]);
+            }
+        }
+    }
+    return y;
+}
+
+// ---- batched messages: one lane of a G-lane group ----------------------------
+struct BatchParams {
+    uint32_t rk[60];
+    const KeyDev* key;
+    const uint32_t* te0;
+    const uint8_t* iv;         // n_msgs x 12
+    const uint8_t* aad;        // may be null when there is no AAD
+    const uint64_t* aad_off;   // n_msgs+1 offsets, or null => uniform (aad_stride, aad_len)
+    const uint8_t* in;
+    const uint64_t* in_off;    // n_msgs+1 offsets, or null => uniform (stride, len)
+    uint8_t* out;              // same offsets as `in`
+    uint8_t* tag;              // n_msgs x 16: produced (enc) / expected (dec)
+    uint8_t* ok;               // n_msgs, dec only: 1 = authentic
+    uint64_t n_msgs;
+    uint64_t len, stride, aad_len, aad_stride;  // uniform layout
+};
+
+struct MsgDesc {
+    const uint8_t* in;
+    uint8_t* out;
+    const uint8_t* aad;
+    uint64_t len, aad_len;
+};
+
+AG_HD MsgDesc ag_batch_msg(const BatchParams& p, uint64_t m)
+{
+    MsgDesc d;
+    uint64_t o, l;
+    if (p.in_off) { o = p.in_off[m]; l = p.in_off[m + 1] - o; } else { o = m * p.stride; l = p.len; }
+    d.in = p.in + o;
+    d.out = p.out + o;
+    d.len = l;
+    if (p.aad_off) { o = p.aad_off[m]; l = p.aad_off[m + 1] - o; } else { o = m * p.aad_stride; l = p.aad_len; }
+    d.aad = p.aad ? p.aad + o : nullptr;
+    d.aad_len = p.aad ? l : 0;
+    return d;
+}
+
+// Lane t of G over the unified sequence [AAD blocks | CT blocks | length block]
+// (gcm_ghash.vhd:259-272 order; length block gcm_ghash.vhd:257).  DEC selects the
+// GHASH source (aes_gcm.vhd:207-211).  Returns Y_t (weight H^(G-t) still to apply).
+template <int NR, bool DEC, class TE, class GH>
+AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, const MsgDesc& d, uint32_t t, uint32_t G, TE&& te,
+                          GH&& gh_g)
+{
+    const uint64_t a = (d.aad_len + 15) >> 4, n = (d.len + 15) >> 4;
+    const uint64_t mb = a + n + 1;
+    const uint64_t rows = (mb + G - 1) / G;
+    const uint64_t pad = rows * G - mb;
+    gf128 y = gf_zero();
+    for (uint64_t u = 0; u < rows; ++u) {
+        const uint64_t v = u * G + t;
+        if (u) y = gf_mul_table(y, gh_g);
+        if (v < pad) continue;
+        const uint64_t i = v - pad;
+        uint32_t s[4];
+        if (i < a) {
+            const uint64_t left = d.aad_len - 16 * i;
+            ag_load_block(d.aad + 16 * i, left < 16 ? (uint32_t)left : 16u, s);
+        } else if (i < a + n) {
+            const uint64_t j = i - a;
+            const uint64_t left = d.len - 16 * j;
+            const uint32_t nv = left < 16 ? (uint32_t)left : 16u;
+            uint32_t x[4], ks[4];
+            ag_load_block(d.in + 16 * j, nv, x);
+            aes_ctr_block<NR>(rk, cc, 2u + (uint32_t)j, te, ks);
+            uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
+            ag_store_block(d.out + 16 * j, nv, o);
+            if (DEC) {
+                s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = x[3];
+            } else {
+                if (nv != 16) ag_mask_block(o, nv);
+                s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+            }
+        } else {
+            // [len(A)]64 || [len(C)]64 in bits, big-endian (gcm_ghash.vhd:257)
+            const uint64_t ab = d.aad_len * 8, cb = d.len * 8;
+            y.w[0] ^= (uint32_t)(ab >> 32);
+            y.w[1] ^= (uint32_t)ab;
+            y.w[2] ^= (uint32_t)(cb >> 32);
+            y.w[3] ^= (uint32_t)cb;
+            continue;
+        }
+        y.w[0] ^= ag_bswap32(s[0]);
+        y.w[1] ^= ag_bswap32(s[1]);
+        y.w[2] ^= ag_bswap32(s[2]);
+        y.w[3] ^= ag_bswap32(s[3]);
+    }
+    return y;
+}

@@ -1,0 +1,179 @@
+// GF(2^128) arithmetic in the GCM bit order, shared by device kernels and the
+// host-side kernel emulator used by the CPU tests (tests/host_emul.cu).
+//
+// Behavioural spec: src/ghash_gfmul.vhd:42-63 (SP 800-38D Algorithm 1): bit 127
+// of the VHDL vector is the MSB of byte 0 and is the coefficient of x^0; the
+// multiply-by-x step is "V >> 1, xor 0xE1||0^120 when the dropped bit was 1".
+//
+// Representation: four BIG-ENDIAN 32-bit words; w[0] bits 31..24 hold byte 0, so
+// the whole element reads as one 128-bit string w[0]:w[1]:w[2]:w[3] and
+// "multiply by x" is a funnel shift right across the words.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AG_HD __host__ __device__ __forceinline__
+#define AG_D __device__ __forceinline__
+#else
+#define AG_HD inline
+#endif
+
+struct gf128 {
+    uint32_t w[4];
+};
+
+AG_HD uint32_t ag_bswap32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24);
+#endif
+}
+
+// low 32 bits of (hi:lo) >> sh, 0 <= sh <= 31
+AG_HD uint32_t ag_funnel_r(uint32_t lo, uint32_t hi, int sh)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+#endif
+}
+
+AG_HD gf128 gf_zero()
+{
+    gf128 r;
+    r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0;
+    return r;
+}
+
+// the multiplicative identity: x^0 = MSB of byte 0
+AG_HD gf128 gf_one()
+{
+    gf128 r = gf_zero();
+    r.w[0] = 0x80000000u;
+    return r;
+}
+
+AG_HD gf128 gf_xor(const gf128& a, const gf128& b)
+{
+    gf128 r;
+    r.w[0] = a.w[0] ^ b.w[0];
+    r.w[1] = a.w[1] ^ b.w[1];
+    r.w[2] = a.w[2] ^ b.w[2];
+    r.w[3] = a.w[3] ^ b.w[3];
+    return r;
+}
+
+// V * x  (ghash_gfmul.vhd:50-57)
+AG_HD gf128 gf_mulx(const gf128& v)
+{
+    gf128 r;
+    uint32_t lsb = v.w[3] & 1u;
+    r.w[3] = ag_funnel_r(v.w[3], v.w[2], 1);
+    r.w[2] = ag_funnel_r(v.w[2], v.w[1], 1);
+    r.w[1] = ag_funnel_r(v.w[1], v.w[0], 1);
+    r.w[0] = (v.w[0] >> 1) ^ (0xE1000000u & (0u - lsb));
+    return r;
+}
+
+// Generic bit-serial product X*V (ghash_gfmul.vhd:42-63).  ~128 x 12 integer
+// ops; used only off the per-block path (key setup, per-thread/-CTA weights,
+// tag finish).
+AG_HD gf128 gf_mul(const gf128& x, gf128 v)
+{
+    gf128 z = gf_zero();
+    for (int q = 0; q < 4; ++q) {
+        uint32_t xw = x.w[q];
+        for (int b = 31; b >= 0; --b) {
+            uint32_t m = 0u - ((xw >> b) & 1u);
+            z.w[0] ^= v.w[0] & m;
+            z.w[1] ^= v.w[1] & m;
+            z.w[2] ^= v.w[2] & m;
+            z.w[3] ^= v.w[3] & m;
+            v = gf_mulx(v);
+        }
+    }
+    return z;
+}
+
+// 16 bytes as loaded little-endian (uint4 of LE words, the AES state layout)
+// <-> field element
+AG_HD gf128 gf_from_le_words(uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    gf128 r;
+    r.w[0] = ag_bswap32(a);
+    r.w[1] = ag_bswap32(b);
+    r.w[2] = ag_bswap32(c);
+    r.w[3] = ag_bswap32(d);
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// Multiply by a FIXED element C through an 8-bit Shoup table T[b] = b*C, where
+// the byte b is read as a degree<8 polynomial with its MSB = x^0.
+//
+//   X = sum_j B_j x^(8j)  (B_j = byte j)   =>   X*C = sum_j T[B_j] x^(8j)
+//
+// The 16 table rows are XORed, unreduced, into a 31-byte string at byte offset
+// j, grouped by r = j mod 4 so that each group only needs whole-word offsets;
+// the three groups r=1..3 are then byte-shifted once.  The 120 overflow bits are
+// folded back once per product with x^128 = 1 + x + x^2 + x^7.
+//
+// LOOKUP: functor (uint32_t be_word, int le_byte) -> uint4 {w0,w1,w2,w3} of
+// T[(be_word >> 8*le_byte) & 0xff].  On the device it is one PRMT + one LDS.128.
+template <class LOOKUP>
+AG_HD gf128 gf_mul_table(const gf128& x, LOOKUP&& lookup)
+{
+    uint32_t z[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) z[m] = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        uint32_t a[7];
+#pragma unroll
+        for (int m = 0; m < 7; ++m) a[m] = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 t = lookup(x.w[q], 3 - r);
+            a[q] ^= t.x;
+            a[q + 1] ^= t.y;
+            a[q + 2] ^= t.z;
+            a[q + 3] ^= t.w;
+        }
+        if (r == 0) {
+#pragma unroll
+            for (int m = 0; m < 7; ++m) z[m] ^= a[m];
+        } else {
+            z[0] ^= a[0] >> (8 * r);
+#pragma unroll
+            for (int m = 1; m < 7; ++m) z[m] ^= ag_funnel_r(a[m], a[m - 1], 8 * r);
+            z[7] ^= a[6] << (32 - 8 * r);
+        }
+    }
+    // fold bytes 16..30 (degrees 128..247); the last byte of z[7] is always zero,
+    // so the shifts by 1, 2 and 7 bits lose nothing.
+    gf128 o;
+    o.w[0] = z[0] ^ z[4] ^ (z[4] >> 1) ^ (z[4] >> 2) ^ (z[4] >> 7);
+#pragma unroll
+    for (int m = 1; m < 4; ++m)
+        o.w[m] = z[m] ^ z[4 + m] ^ ag_funnel_r(z[4 + m], z[3 + m], 1) ^ ag_funnel_r(z[4 + m], z[3 + m], 2) ^
+                 ag_funnel_r(z[4 + m], z[3 + m], 7);
+    return o;
+}
+
+// Row b of the compact Shoup table for constant C.  basis[k] = C * x^k, k=0..7.
+AG_HD uint4 gf_table_row(const gf128 basis[8], uint32_t b)
+{
+    uint4 r = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        uint32_t m = 0u - ((b >> (7 - k)) & 1u);
+        r.x ^= basis[k].w[0] & m;
+        r.y ^= basis[k].w[1] & m;
+        r.z ^= basis[k].w[2] & m;
+        r.w ^= basis[k].w[3] & m;
+    }
+    return r;
+}

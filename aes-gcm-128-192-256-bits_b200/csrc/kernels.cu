@@ -1,0 +1,504 @@
+// sm_100a kernels of the AES-GCM engine.
+//
+// Shared-memory plan (one persistent 1024-thread CTA per SM, 194 KB of the 227 KB):
+//
+//   [0      , 64 KB)  AES_A : 256 entries x 256 B; entry x = 32 lane-private copies
+//                     of Te0[x] (128 B) then 32 copies of Te1[x] (128 B)
+//   [64 KB  , 128 KB) AES_B : same for Te2 / Te3
+//   [128 KB , 192 KB) GH    : 256 entries x 256 B; entry b = 8 copies of the 16 B row
+//                     T_a[b] (128 B) then 8 copies of T_b[b] (128 B)
+//   [192 KB , +2 KB)  reduction scratch
+//
+// Every data-dependent lookup is then bank-conflict free BY CONSTRUCTION: lane l
+// reads word l of a 128 B row (32-bit AES lookups), or 16 B slot l%8 of a row
+// (128-bit GHASH lookups, served per quarter-warp).  The 256 B entry stride makes
+// the address a single PRMT: {0, 0, index byte, lane offset}; the table select is
+// an immediate on the LDS.  Per 16 B block that is 16 PRMT + 16 LDS + 8 LOP3 per
+// AES round and 16 PRMT + 16 LDS.128 + ~90 LOP3/SHF per GHASH multiply.
+//
+// Reference blocks replaced: gcm_gctr (aes_icb + aes_ecb + xor, src/gcm_gctr.vhd:150),
+// gcm_ghash + ghash_gfmul (src/gcm_ghash.vhd:225-293, src/ghash_gfmul.vhd:42-63),
+// aes_kexp (config/config_aes_kexp.py:128-159, tb/key_exp.py:79-114).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gcm_core.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr uint32_t SM_AES_A = 0;
+constexpr uint32_t SM_AES_B = 65536;
+constexpr uint32_t SM_GH = 131072;
+constexpr uint32_t SM_MISC = 196608;
+
+extern __shared__ __align__(1024) uint8_t ag_smem[];
+
+// Te_tab[(w >> 8k) & 0xff] from the lane-private replicas
+struct TeSmem {
+    const uint8_t* base;
+    uint32_t lane4;  // (lane & 31) * 4
+    __device__ __forceinline__ uint32_t operator()(int tab, uint32_t w, int k) const
+    {
+        const uint32_t off = __byte_perm(w, lane4, 0x5504 | (k << 4));  // (byte_k << 8) | lane4
+        return *reinterpret_cast<const uint32_t*>(base + off + (tab & 1) * 128 + (tab >> 1) * 65536);
+    }
+};
+
+// row T[(w >> 8k) & 0xff] of the GHASH table from the quarter-warp replicas
+struct GhSmem {
+    const uint8_t* base;  // ag_smem + SM_GH (+128 for T_b)
+    uint32_t lane16;      // (lane & 7) * 16
+    __device__ __forceinline__ uint4 operator()(uint32_t w, int k) const
+    {
+        const uint32_t off = __byte_perm(w, lane16, 0x5504 | (k << 4));
+        return *reinterpret_cast<const uint4*>(base + off);
+    }
+};
+
+// slow-path lookups straight from HBM/L2 (setup and finish kernels only)
+struct TeGlobal {
+    const uint32_t* te0;
+    __device__ __forceinline__ uint32_t operator()(int tab, uint32_t w, int k) const
+    {
+        const uint32_t t = __ldg(te0 + ((w >> (8 * k)) & 0xff));
+        return tab ? ag_rotl32(t, 8 * tab) : t;
+    }
+};
+
+__device__ __forceinline__ void fill_aes_tables(const uint32_t* __restrict__ te0)
+{
+    for (uint32_t idx = threadIdx.x; idx < 256 * 32; idx += blockDim.x) {
+        const uint32_t x = idx >> 5, l = idx & 31;
+        const uint32_t t = __ldg(te0 + x);
+        uint32_t* a = reinterpret_cast<uint32_t*>(ag_smem + SM_AES_A + x * 256 + l * 4);
+        uint32_t* b = reinterpret_cast<uint32_t*>(ag_smem + SM_AES_B + x * 256 + l * 4);
+        a[0] = t;
+        a[32] = ag_rotl32(t, 8);
+        b[0] = ag_rotl32(t, 16);
+        b[32] = ag_rotl32(t, 24);
+    }
+}
+
+__device__ __forceinline__ void fill_gh_tables(const uint4* __restrict__ ta, const uint4* __restrict__ tb)
+{
+    for (uint32_t idx = threadIdx.x; idx < 256 * 8; idx += blockDim.x) {
+        const uint32_t b = idx >> 3, r = idx & 7;
+        uint4* d = reinterpret_cast<uint4*>(ag_smem + SM_GH + b * 256 + r * 16);
+        d[0] = __ldg(ta + b);
+        if (tb) d[8] = __ldg(tb + b);
+    }
+}
+
+__device__ __forceinline__ gf128 warp_xor(gf128 v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v.w[0] ^= __shfl_xor_sync(0xffffffffu, v.w[0], o);
+        v.w[1] ^= __shfl_xor_sync(0xffffffffu, v.w[1], o);
+        v.w[2] ^= __shfl_xor_sync(0xffffffffu, v.w[2], o);
+        v.w[3] ^= __shfl_xor_sync(0xffffffffu, v.w[3], o);
+    }
+    return v;
+}
+
+// H^e for a 64-bit exponent, computed by one full warp: lane k contributes
+// pow2[k]^(bit k) * pow2[k+32]^(bit k+32); the 32 factors are multiplied by a
+// shuffle tree (5 generic products deep).  All lanes return the result.
+__device__ gf128 warp_gf_pow(const KeyDev* kd, uint64_t e)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    gf128 f = ((e >> lane) & 1) ? kd->pow2[lane] : gf_one();
+    if (e >> 32) {  // uniform
+        gf128 f2 = ((e >> (lane + 32)) & 1) ? kd->pow2[lane + 32] : gf_one();
+        f = gf_mul(f, f2);
+    }
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        gf128 g;
+        g.w[0] = __shfl_xor_sync(0xffffffffu, f.w[0], o);
+        g.w[1] = __shfl_xor_sync(0xffffffffu, f.w[1], o);
+        g.w[2] = __shfl_xor_sync(0xffffffffu, f.w[2], o);
+        g.w[3] = __shfl_xor_sync(0xffffffffu, f.w[3], o);
+        f = gf_mul(f, g);
+    }
+    return f;
+}
+
+}  // namespace
+
+// ===========================================================================
+// aes_kexp on the device: one thread per key (tb/key_exp.py:118 semantics;
+// output bytes identical to its list, stage r at bytes 16r..16r+15).
+// ===========================================================================
+__global__ void k_key_expand(const uint8_t* __restrict__ keys, uint64_t n_keys, int key_bytes,
+                             const uint32_t* __restrict__ te0, uint8_t* __restrict__ round_keys)
+{
+    __shared__ uint32_t sbox_s[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sbox_s[i] = (__ldg(te0 + i) >> 8) & 0xff;
+    __syncthreads();
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_keys) return;
+    uint8_t key[32];
+    for (int j = 0; j < key_bytes; ++j) key[j] = keys[i * key_bytes + j];
+    uint32_t rk[60];
+    auto sb = [&](uint32_t b) { return sbox_s[b & 0xff]; };
+    const int nr = aes_key_expand_words(key, key_bytes, sb, rk);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(round_keys + i * (uint64_t)(16 * (nr + 1)));
+    for (int j = 0; j < 4 * (nr + 1); ++j) dst[j] = rk[j];  // LE words == the byte string
+}
+
+// ===========================================================================
+// Per-key setup: H, H^(2^k), per-thread / per-CTA weights, Shoup tables.
+// One CTA of 256 threads; kd->rk / kd->nr must already be filled.
+// ===========================================================================
+__global__ void __launch_bounds__(256) k_key_setup(KeyDev* kd, const uint32_t* __restrict__ te0, uint32_t nt_stream,
+                                                   uint32_t ncta)
+{
+    const uint32_t tid = threadIdx.x;
+    __shared__ gf128 s_pow2[64];
+    if (tid == 0) {
+        TeGlobal te{te0};
+        uint32_t h[4];
+        aes_encrypt_words(kd->rk, (int)kd->nr, 0, 0, 0, 0, te, h);  // H = E_K(0^128), gcm_gctr.vhd:141-144
+        gf128 p = gf_from_le_words(h[0], h[1], h[2], h[3]);
+        kd->H = p;
+        kd->nt_stream = nt_stream;
+        kd->ncta = ncta;
+        for (int k = 0; k < 64; ++k) {
+            s_pow2[k] = p;
+            kd->pow2[k] = p;
+            p = gf_mul(p, p);
+        }
+        kd->hpow_thread[0] = gf_one();
+        kd->hpow_thread[1] = s_pow2[0];
+        kd->hpow_cta[0] = gf_one();
+    }
+    __syncthreads();
+    // H^k for k = 2..nt_stream by doubling: H^(2^s + j) = H^j * H^(2^s), j = 1..2^s
+    for (uint32_t s = 0; (1u << s) < nt_stream; ++s) {
+        const uint32_t half = 1u << s;
+        for (uint32_t j = tid; j < half; j += blockDim.x) {
+            const uint32_t dst = half + 1 + j;
+            if (dst <= nt_stream) kd->hpow_thread[dst] = gf_mul(kd->hpow_thread[1 + j], s_pow2[s]);
+        }
+        __syncthreads();
+    }
+    // (H^NT)^k for k = 1..ncta, same doubling with base powers pow2[log2(NT) + s]
+    uint32_t lg = 0;
+    while ((1u << lg) < nt_stream) ++lg;
+    if (tid == 0) kd->hpow_cta[1] = s_pow2[lg];
+    __syncthreads();
+    for (uint32_t s = 0; (1u << s) < ncta; ++s) {
+        const uint32_t half = 1u << s;
+        for (uint32_t j = tid; j < half; j += blockDim.x) {
+            const uint32_t dst = half + 1 + j;
+            if (dst <= ncta) kd->hpow_cta[dst] = gf_mul(kd->hpow_cta[1 + j], s_pow2[lg + s]);
+        }
+        __syncthreads();
+    }
+    // Shoup tables, row b per thread (blockDim.x == 256)
+    for (int j = 0; j < 8; ++j) {
+        gf128 c;
+        if (j < 6) c = s_pow2[j];
+        else if (j == 6) c = s_pow2[lg];
+        else c = kd->hpow_cta[ncta];
+        gf128 basis[8];
+        basis[0] = c;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) basis[k] = gf_mulx(basis[k - 1]);
+        for (uint32_t b = tid; b < 256; b += blockDim.x) kd->tab[j][b] = gf_table_row(basis, b);
+    }
+}
+
+// ===========================================================================
+// Single stream: fused GCTR + GHASH, grid-wide strided Horner.
+// grid = kd->ncta CTAs x kd->nt_stream threads; writes one 16 B partial per CTA.
+// ===========================================================================
+template <int NR, int MODE>
+__global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_constant__ StreamParams p)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+    if (MODE != AG_MODE_GHASH_ONLY) fill_aes_tables(p.te0);
+    if (MODE != AG_MODE_CTR_ONLY) fill_gh_tables(p.key->tab[7], nullptr);
+    __syncthreads();
+
+    TeSmem te{ag_smem, lane * 4};
+    GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
+    const uint64_t Gt = (uint64_t)gridDim.x * nt;
+    const uint64_t g = (uint64_t)blockIdx.x * nt + tid;
+    gf128 y = ag_stream_lane<NR, MODE>(p, g, Gt, te, gh);
+    if (MODE == AG_MODE_CTR_ONLY) return;
+
+    // lane weight H^(Gt-g) = (H^NT)^(ncta-1-cta) * H^(NT-tid)
+    y = gf_mul(y, p.key->hpow_thread[nt - tid]);
+    y = warp_xor(y);
+    gf128* red = reinterpret_cast<gf128*>(ag_smem + SM_MISC);
+    if (lane == 0) red[tid >> 5] = y;
+    __syncthreads();
+    if (tid < 32) {
+        gf128 v = (tid < (nt >> 5)) ? red[tid] : gf_zero();
+        v = warp_xor(v);
+        if (tid == 0) {
+            v = gf_mul(v, p.key->hpow_cta[gridDim.x - 1 - blockIdx.x]);
+            uint32_t* dst = p.partials + 4 * blockIdx.x;
+            dst[0] = v.w[0]; dst[1] = v.w[1]; dst[2] = v.w[2]; dst[3] = v.w[3];
+        }
+    }
+}
+
+// out16 = (xor of n_in partials) * H^e     (shard pre-scaling)
+__global__ void __launch_bounds__(32) k_reduce_scale(const KeyDev* kd, const uint32_t* __restrict__ parts, uint32_t n_in,
+                                                     uint64_t e, uint8_t* __restrict__ out)
+{
+    const uint32_t lane = threadIdx.x;
+    gf128 s = gf_zero();
+    for (uint32_t j = lane; j < n_in; j += 32) {
+        s.w[0] ^= parts[4 * j + 0]; s.w[1] ^= parts[4 * j + 1]; s.w[2] ^= parts[4 * j + 2]; s.w[3] ^= parts[4 * j + 3];
+    }
+    s = warp_xor(s);
+    if (e) {
+        gf128 he = warp_gf_pow(kd, e);
+        s = gf_mul(s, he);
+    }
+    if (lane == 0) {
+        const uint32_t o[4] = {ag_bswap32(s.w[0]), ag_bswap32(s.w[1]), ag_bswap32(s.w[2]), ag_bswap32(s.w[3])};
+        ag_store_block(out, 16, o);  // natural GHASH byte order
+    }
+}
+
+// Tag finish (gcm_ghash.vhd:257,293 + tb/gcm_model.py:33-51):
+//   S = xor parts (each already aligned so that the last CT block weighs H^1)
+//   QA = sum A_i H^(a-i) over the (short) AAD given here, if any
+//   TAG = ((QA * H^n) xor S xor LEN) * H xor E_K(J0)
+// decrypt: constant-time compare with the expected tag -> ok flag; the computed
+// tag is always written to tag_calc.
+
+__global__ void __launch_bounds__(32) k_stream_finish(const __grid_constant__ FinishParams p)
+{
+    const uint32_t lane = threadIdx.x;
+    const KeyDev* kd = p.key;
+    gf128 s = gf_zero();
+    for (uint32_t j = lane; j < p.n_parts; j += 32) {
+        uint32_t x[4];
+        ag_load_block(p.parts + 16 * j, 16, x);
+        s = gf_xor(s, gf_from_le_words(x[0], x[1], x[2], x[3]));
+    }
+    s = warp_xor(s);
+    const uint64_t n = (p.ct_len + 15) >> 4;
+    if (p.aad && p.aad_len) {  // uniform
+        // short AAD (host routes long AAD through k_stream<GHASH_ONLY>): the warp
+        // runs the same front-padded strided Horner with G = 32 and generic products.
+        const uint64_t a = (p.aad_len + 15) >> 4;
+        const uint64_t rows = (a + 31) >> 5, pad = rows * 32 - a;
+        const gf128 h32 = kd->pow2[5];
+        gf128 qa = gf_zero();
+        for (uint64_t u = 0; u < rows; ++u) {
+            const uint64_t v = u * 32 + lane;
+            if (u) qa = gf_mul(qa, h32);
+            if (v >= pad) {
+                const uint64_t i = v - pad;
+                const uint64_t left = p.aad_len - 16 * i;
+                uint32_t x[4];
+                ag_load_block(p.aad + 16 * i, left < 16 ? (uint32_t)left : 16u, x);
+                qa = gf_xor(qa, gf_from_le_words(x[0], x[1], x[2], x[3]));
+            }
+        }
+        qa = gf_mul(qa, kd->hpow_thread[32 - lane]);
+        qa = warp_xor(qa);                     // QA = sum A_i H^(a-i)
+        const gf128 hn = warp_gf_pow(kd, n);
+        if (lane == 0) s = gf_xor(s, gf_mul(qa, hn));
+    }
+    if (lane == 0) {
+        const uint64_t ab = p.aad_len * 8, cb = p.ct_len * 8;
+        s.w[0] ^= (uint32_t)(ab >> 32); s.w[1] ^= (uint32_t)ab; s.w[2] ^= (uint32_t)(cb >> 32); s.w[3] ^= (uint32_t)cb;
+        s = gf_mul(s, kd->H);
+        TeGlobal te{p.te0};
+        uint32_t e[4];
+        aes_encrypt_words(p.rk, (int)p.nr, p.iv[0], p.iv[1], p.iv[2], 0x01000000u, te, e);  // J0 = IV || 00000001
+        uint32_t t[4] = {ag_bswap32(s.w[0]) ^ e[0], ag_bswap32(s.w[1]) ^ e[1], ag_bswap32(s.w[2]) ^ e[2],
+                         ag_bswap32(s.w[3]) ^ e[3]};
+        ag_store_block(p.tag_calc, 16, t);
+        if (p.tag_expected && p.ok) {
+            uint32_t x[4];
+            ag_load_block(p.tag_expected, 16, x);
+            const uint32_t diff = (x[0] ^ t[0]) | (x[1] ^ t[1]) | (x[2] ^ t[2]) | (x[3] ^ t[3]);
+            *p.ok = diff ? 0 : 1;
+        }
+    }
+}
+
+// ===========================================================================
+// Batched messages under one shared key: G lanes per message, persistent grid.
+// Tables: T_a = H^G (row Horner), T_b = H (lane combine).
+// ===========================================================================
+template <int NR, bool DEC, int G>
+__global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_constant__ BatchParams p)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+    constexpr int LG = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : 5;
+    fill_aes_tables(p.te0);
+    fill_gh_tables(p.key->tab[LG], p.key->tab[0]);
+    __syncthreads();
+
+    TeSmem te{ag_smem, lane * 4};
+    GhSmem gh_g{ag_smem + SM_GH, (lane & 7) * 16};
+    GhSmem gh_1{ag_smem + SM_GH + 128, (lane & 7) * 16};
+
+    const uint32_t t = lane & (G - 1);
+    const uint32_t gbase = lane & ~(uint32_t)(G - 1);
+    const uint64_t groups_per_cta = nt / G;
+    const uint64_t n_groups = (uint64_t)gridDim.x * groups_per_cta;
+    const uint64_t gid = (uint64_t)blockIdx.x * groups_per_cta + tid / G;
+    // every warp runs the same trip count; lanes past the end are predicated off
+    const uint64_t warp_first = (uint64_t)blockIdx.x * groups_per_cta + (tid & ~31u) / G;
+    for (uint64_t w0 = warp_first, m = gid; w0 < p.n_msgs; w0 += n_groups, m += n_groups) {
+        const bool valid = m < p.n_msgs;
+        gf128 y = gf_zero();
+        AesCtrConst cc;
+        if (valid) {
+            const MsgDesc d = ag_batch_msg(p, m);
+            const uint8_t* ivp = p.iv + 12 * m;
+            uint32_t iv0 = 0, iv1 = 0, iv2 = 0;
+            if (((uintptr_t)ivp & 3) == 0) {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(ivp);
+                iv0 = q[0]; iv1 = q[1]; iv2 = q[2];
+            } else {
+                for (int j = 0; j < 4; ++j) {
+                    iv0 |= (uint32_t)ivp[j] << (8 * j);
+                    iv1 |= (uint32_t)ivp[4 + j] << (8 * j);
+                    iv2 |= (uint32_t)ivp[8 + j] << (8 * j);
+                }
+            }
+            cc = aes_ctr_precompute(p.rk, iv0, iv1, iv2, te);
+            y = ag_batch_lane<NR, DEC>(p.rk, cc, d, t, (uint32_t)G, te, gh_g);
+        }
+        __syncwarp();
+        // R = sum_t Y_t H^(G-t): serial Horner over the group's lanes with T_b = H
+        gf128 r = gf_zero();
+#pragma unroll 1
+        for (int k = 0; k < G; ++k) {
+            gf128 yk;
+            yk.w[0] = __shfl_sync(0xffffffffu, y.w[0], gbase + k);
+            yk.w[1] = __shfl_sync(0xffffffffu, y.w[1], gbase + k);
+            yk.w[2] = __shfl_sync(0xffffffffu, y.w[2], gbase + k);
+            yk.w[3] = __shfl_sync(0xffffffffu, y.w[3], gbase + k);
+            r = gf_xor(r, yk);
+            r = gf_mul_table(r, gh_1);
+        }
+        if (valid && t == 0) {
+            uint32_t e[4];
+            aes_ctr_block<NR>(p.rk, cc, 1u, te, e);  // E_K(J0), J0 = IV || 00000001 (aes_icb.vhd:34,99)
+            uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
+                              ag_bswap32(r.w[3]) ^ e[3]};
+            uint8_t* tp = p.tag + 16 * m;
+            if (DEC) {
+                uint32_t x[4];
+                ag_load_block(tp, 16, x);
+                const uint32_t diff = (x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3]);
+                p.ok[m] = diff ? 0 : 1;
+            } else {
+                ag_store_block(tp, 16, tg);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ===========================================================================
+// launchers (called from capi.cu)
+// ===========================================================================
+static const size_t kSmemBytes = SM_MISC + 2048;
+size_t ag_smem_bytes() { return kSmemBytes; }
+
+template <int NR, int MODE>
+static cudaError_t launch_stream_t(const StreamParams& p, int ncta, int nt, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_stream<NR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    k_stream<NR, MODE><<<ncta, nt, kSmemBytes, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int NR>
+static cudaError_t launch_stream_nr(const StreamParams& p, int mode, int ncta, int nt, cudaStream_t st)
+{
+    switch (mode) {
+        case AG_MODE_ENC: return launch_stream_t<NR, AG_MODE_ENC>(p, ncta, nt, st);
+        case AG_MODE_DEC: return launch_stream_t<NR, AG_MODE_DEC>(p, ncta, nt, st);
+        case AG_MODE_GHASH_ONLY: return launch_stream_t<NR, AG_MODE_GHASH_ONLY>(p, ncta, nt, st);
+        case AG_MODE_CTR_ONLY: return launch_stream_t<NR, AG_MODE_CTR_ONLY>(p, ncta, nt, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t ag_launch_stream(const StreamParams& p, int nr, int mode, int ncta, int nt, cudaStream_t st)
+{
+    switch (nr) {
+        case 10: return launch_stream_nr<10>(p, mode, ncta, nt, st);
+        case 12: return launch_stream_nr<12>(p, mode, ncta, nt, st);
+        case 14: return launch_stream_nr<14>(p, mode, ncta, nt, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int NR, bool DEC, int G>
+static cudaError_t launch_batch_t(const BatchParams& p, int ncta, int nt, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_batch<NR, DEC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    k_batch<NR, DEC, G><<<ncta, nt, kSmemBytes, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int NR, bool DEC>
+static cudaError_t launch_batch_g(const BatchParams& p, int g, int ncta, int nt, cudaStream_t st)
+{
+    switch (g) {
+        case 1: return launch_batch_t<NR, DEC, 1>(p, ncta, nt, st);
+        case 2: return launch_batch_t<NR, DEC, 2>(p, ncta, nt, st);
+        case 4: return launch_batch_t<NR, DEC, 4>(p, ncta, nt, st);
+        case 8: return launch_batch_t<NR, DEC, 8>(p, ncta, nt, st);
+        case 16: return launch_batch_t<NR, DEC, 16>(p, ncta, nt, st);
+        case 32: return launch_batch_t<NR, DEC, 32>(p, ncta, nt, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t ag_launch_batch(const BatchParams& p, int nr, int decrypt, int g, int ncta, int nt, cudaStream_t st)
+{
+    switch (nr) {
+        case 10: return decrypt ? launch_batch_g<10, true>(p, g, ncta, nt, st) : launch_batch_g<10, false>(p, g, ncta, nt, st);
+        case 12: return decrypt ? launch_batch_g<12, true>(p, g, ncta, nt, st) : launch_batch_g<12, false>(p, g, ncta, nt, st);
+        case 14: return decrypt ? launch_batch_g<14, true>(p, g, ncta, nt, st) : launch_batch_g<14, false>(p, g, ncta, nt, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_bytes, const uint32_t* te0,
+                                 uint8_t* round_keys, cudaStream_t st)
+{
+    if (n_keys == 0) return cudaSuccess;
+    const int nt = 128;
+    const uint64_t nb = (n_keys + nt - 1) / nt;
+    k_key_expand<<<(unsigned)nb, nt, 0, st>>>(keys, n_keys, key_bytes, te0, round_keys);
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_key_setup(KeyDev* kd, const uint32_t* te0, int nt_stream, int ncta, cudaStream_t st)
+{
+    k_key_setup<<<1, 256, 0, st>>>(kd, te0, (uint32_t)nt_stream, (uint32_t)ncta);
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_reduce_scale(const KeyDev* kd, const uint32_t* parts, uint32_t n_in, uint64_t e, uint8_t* out,
+                                   cudaStream_t st)
+{
+    k_reduce_scale<<<1, 32, 0, st>>>(kd, parts, n_in, e, out);
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_finish(const FinishParams& p, cudaStream_t st)
+{
+    k_stream_finish<<<1, 32, 0, st>>>(p);
+    return cudaGetLastError();
+}

@@ -1,0 +1,32 @@
+// Internal launcher interface between kernels.cu and capi.cu (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gcm_core.cuh"
+
+// Tag finish (gcm_ghash.vhd:257,293 + tb/gcm_model.py:33-51); see k_stream_finish.
+struct FinishParams {
+    uint32_t rk[60];
+    uint32_t nr;
+    uint32_t iv[3];
+    const KeyDev* key;
+    const uint32_t* te0;
+    const uint8_t* parts;         // n_parts x 16 B in natural GHASH byte order
+    uint32_t n_parts;
+    const uint8_t* aad;           // null: no AAD, or AAD already folded into parts
+    uint64_t aad_len;             // true AAD length (length block)
+    uint64_t ct_len;
+    uint8_t* tag_calc;            // 16 B out, always written
+    const uint8_t* tag_expected;  // 16 B in (decrypt) or null
+    uint8_t* ok;                  // 1 B out (decrypt) or null
+};
+
+cudaError_t ag_launch_stream(const StreamParams& p, int nr, int mode, int ncta, int nt, cudaStream_t st);
+cudaError_t ag_launch_batch(const BatchParams& p, int nr, int decrypt, int g, int ncta, int nt, cudaStream_t st);
+cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_bytes, const uint32_t* te0,
+                                 uint8_t* round_keys, cudaStream_t st);
+cudaError_t ag_launch_key_setup(KeyDev* kd, const uint32_t* te0, int nt_stream, int ncta, cudaStream_t st);
+cudaError_t ag_launch_reduce_scale(const KeyDev* kd, const uint32_t* parts_raw, uint32_t n_in, uint64_t e,
+                                   uint8_t* out16, cudaStream_t st);
+cudaError_t ag_launch_finish(const FinishParams& p, cudaStream_t st);
+size_t ag_smem_bytes();

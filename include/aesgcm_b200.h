@@ -1,0 +1,147 @@
+/*
+ * aesgcm_b200.h -- C ABI of the B200 (sm_100a) AES-GCM engine.
+ *
+ * This is the drop-in boundary for the golden-model side of
+ * BLu85/AES-GCM-128-192-256-bits.  The reference has no C API: its "plugin
+ * interface" is the Python surface tb/gcm_model.py (class gcm) and
+ * tb/key_exp.py (aes_expand_key), which delegate to pycryptodome.  Each entry
+ * point below names the reference interface it replaces (file:line relative to
+ * the reference checkout).  INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - Plain C: pointers and sizes only.  `d_` = DEVICE pointer, `h_` = HOST
+ *     pointer.  The caller owns every buffer; the library allocates only inside
+ *     the context.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device
+ *     entry points are asynchronous on that stream.  A context owns scratch
+ *     buffers: use one context per concurrently active stream.
+ *   - Return 0 on success, a negative AGCM_E_* otherwise.  Nothing throws.
+ *   - mode = key size in bits: 128 / 192 / 256 (src/aes_pkg.vhd:31-33 Nr=10/12/14).
+ *   - IV is always 96 bits; the counter block is IV || cnt32, cnt = 1 for J0 and
+ *     2.. for data (src/aes_icb.vhd:34,99-100,118).  More than 2^32-2 data
+ *     blocks per IV is AGCM_E_COUNTER_OVERFLOW (the IP raises its overflow flag,
+ *     src/aes_icb.vhd:65,114,119).
+ *   - There is no CPU fallback.  Every call needs a CUDA device of compute
+ *     capability 10.x.
+ */
+#ifndef AESGCM_B200_H
+#define AESGCM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGCM_OK 0
+#define AGCM_E_BAD_MODE (-1)         /* mode not 128/192/256, or key length mismatch (config/gcm_utils.py:163-171) */
+#define AGCM_E_BAD_LEN (-2)          /* inconsistent lengths / offsets */
+#define AGCM_E_COUNTER_OVERFLOW (-3) /* > 2^32-2 blocks under one IV (src/aes_icb.vhd:114) */
+#define AGCM_E_CUDA (-4)             /* CUDA runtime error; see agcm_last_cuda_error() */
+#define AGCM_E_NO_KEY (-5)           /* agcm_set_key() has not been called on this context */
+#define AGCM_E_BAD_ARG (-6)          /* null pointer / unsupported argument */
+#define AGCM_E_NO_DEVICE (-7)        /* no sm_100 device: the engine has no other path */
+
+typedef struct agcm_ctx agcm_ctx;
+
+/* ---- context ------------------------------------------------------------ */
+int agcm_ctx_create(agcm_ctx** out, int device);
+/* testing/tuning: explicit persistent-grid shape (n_cta <= 256, threads power of two <= 1024; 0 = default) */
+int agcm_ctx_create_ex(agcm_ctx** out, int device, int n_cta, int threads);
+void agcm_ctx_destroy(agcm_ctx* ctx);
+const char* agcm_strerror(int rc);
+int agcm_last_cuda_error(const agcm_ctx* ctx); /* cudaError_t of the last failure */
+const char* agcm_last_cuda_error_string(const agcm_ctx* ctx);
+/* persistent-grid shape and SM count actually used */
+int agcm_get_info(const agcm_ctx* ctx, int* n_cta, int* threads, int* sm_count);
+/* number of kernels this context has launched so far (bench.py gpu_launches) */
+uint64_t agcm_launch_count(const agcm_ctx* ctx);
+
+/* ---- key schedule ---------------------------------------------------------
+ * Replaces tb/key_exp.py:118 aes_expand_key(key_hex, size) and the on-the-fly
+ * aes_kexp block (config/config_aes_kexp.py:128-159): n_keys raw keys of
+ * mode/8 bytes each -> n_keys x (Nr+1)*16 bytes (176/208/240), stage r at bytes
+ * 16r..16r+15, byte-identical to the reference list.  One thread per key. */
+int agcm_key_expand(agcm_ctx* ctx, int mode, const uint8_t* d_keys, size_t n_keys, uint8_t* d_round_keys, void* stream);
+/* host convenience over the same kernel (1 key), for the key_exp.py adapter */
+int agcm_key_expand_host(agcm_ctx* ctx, int mode, const uint8_t* h_key, uint8_t* h_round_keys);
+
+/* ---- shared key ------------------------------------------------------------
+ * Replaces gcm_model.gcm.__init__'s key handling (tb/gcm_model.py:16,18) and the
+ * DUT key load: raw key (tb/gcm_gctr.py:144-175, expanded on the device) or
+ * pre-expanded stages (tb/gcm_gctr.py:180-214, config/config_aes_kprexp.py:66-95).
+ * key_len = mode/8 when pre_expanded == 0, (Nr+1)*16 otherwise.
+ * Derives on the device H = E_K(0^128) (src/gcm_gctr.vhd:141-144,
+ * src/gcm_ghash.vhd:128-139), its powers and the Shoup tables; H stays valid
+ * until the next agcm_set_key (src/gcm_ghash.vhd:123).  Synchronous. */
+int agcm_set_key(agcm_ctx* ctx, int mode, int pre_expanded, const uint8_t* h_key, size_t key_len);
+int agcm_get_round_keys(const agcm_ctx* ctx, uint8_t* h_round_keys, size_t cap); /* returns byte count */
+int agcm_get_h(const agcm_ctx* ctx, uint8_t h_h16[16]);
+
+/* ---- one message, data resident in HBM ---------------------------------------
+ * Replaces load_aad / load_plain_text / load_cipher_text / get_tag of
+ * tb/gcm_model.py:21-51 for a whole message (the datapath of src/gcm_gctr.vhd:150
+ * + src/gcm_ghash.vhd:225-293).
+ *   decrypt == 0: d_out = CT, d_tag receives the 16-byte tag.
+ *   decrypt == 1: d_out = PT, d_tag holds the EXPECTED tag, *d_ok = 1 if it
+ *                 matches the computed tag, else 0 (tb/gcm_model.py:42-51).
+ * d_in/d_out may alias exactly (in place).  16-byte alignment of d_in/d_out
+ * selects the 128-bit load/store path. */
+int agcm_stream_crypt(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], const uint8_t* d_aad, uint64_t aad_len,
+                      const uint8_t* d_in, uint8_t* d_out, uint64_t n_bytes, uint8_t* d_tag, uint8_t* d_ok, void* stream);
+
+/* Counter-range shard of one message (multi-GPU): blocks
+ * [first_block, first_block + ceil(n_bytes/16)) of the message, counter start
+ * 2 + first_block.  n_bytes must be a multiple of 16 unless this is the last
+ * shard.  Writes d_partial16 = sum_i C_i * H^(n_shard - i + blocks_after) in
+ * natural GHASH byte order, i.e. already scaled for the `blocks_after` CT blocks
+ * that follow the shard, so the partials of all shards simply XOR. */
+int agcm_stream_part(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in,
+                     uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, uint8_t* d_partial16, void* stream);
+/* Combine n_parts gathered partials with the AAD and the length block
+ * (src/gcm_ghash.vhd:257) and E_K(J0) (src/gcm_ghash.vhd:293).  ct_len is the
+ * TOTAL message length in bytes.  Tag semantics as agcm_stream_crypt. */
+int agcm_stream_finish(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], const uint8_t* d_partials16, int n_parts,
+                       const uint8_t* d_aad, uint64_t aad_len, uint64_t ct_len, uint8_t* d_tag, uint8_t* d_ok,
+                       void* stream);
+
+/* ---- many independent messages under the shared key ---------------------------
+ * Message i: IV d_iv12[12i..], AAD d_aad[aad_off[i]..aad_off[i+1]), payload
+ * d_in[in_off[i]..in_off[i+1]) -> d_out at the same offsets, tag at d_tag[16i..]
+ * (produced for encrypt, expected for decrypt), d_ok[i] (decrypt only).
+ * d_aad / d_aad_off may be NULL (no AAD).  lanes = threads cooperating on one
+ * message (1,2,4,8,16,32) or 0 = choose from n_msgs and avg_len_hint. */
+int agcm_batch_crypt(agcm_ctx* ctx, int decrypt, int lanes, uint64_t avg_len_hint, const uint8_t* d_iv12,
+                     const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
+                     uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);
+/* Same, fixed-size records: message i at d_in + i*stride (len bytes), AAD at
+ * d_aad + i*aad_stride (aad_len bytes). */
+int agcm_batch_crypt_uniform(agcm_ctx* ctx, int decrypt, int lanes, const uint8_t* d_iv12, const uint8_t* d_aad,
+                             uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out, uint64_t len,
+                             uint64_t stride, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);
+
+/* ---- host-buffer entry points (the call a reference-side user makes) ---------
+ * Inputs and outputs live in HOST memory; the library stages them through HBM
+ * in chunks, overlapping H2D, kernel and D2H on its own streams.  Pinned host
+ * memory (agcm_host_alloc, or any cudaHostAlloc/registered buffer) gives full
+ * PCIe rate.  Synchronous.  *h_ok is written for decrypt (may be NULL for
+ * encrypt). */
+int agcm_stream_crypt_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], const uint8_t* h_aad, uint64_t aad_len,
+                           const uint8_t* h_in, uint8_t* h_out, uint64_t n_bytes, uint8_t h_tag[16], int* h_ok);
+int agcm_batch_crypt_uniform_host(agcm_ctx* ctx, int decrypt, int lanes, const uint8_t* h_iv12, const uint8_t* h_aad,
+                                  uint64_t aad_len, uint64_t aad_stride, const uint8_t* h_in, uint8_t* h_out,
+                                  uint64_t len, uint64_t stride, uint8_t* h_tag, uint8_t* h_ok, size_t n_msgs);
+int agcm_host_alloc(void** out, size_t bytes); /* pinned */
+void agcm_host_free(void* p);
+
+/* ---- profiling aid (not part of the reference surface) ------------------------
+ * Runs only one half of the fused stream kernel: what = 2 GHASH only, 3 CTR only. */
+int agcm_stream_probe(agcm_ctx* ctx, int what, const uint8_t h_iv12[12], const uint8_t* d_in, uint8_t* d_out,
+                      uint64_t n_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AESGCM_B200_H */

@@ -1,0 +1,228 @@
+// tests/host_emul.cu -- TEST SCAFFOLDING, never shipped.
+//
+// Runs the engine's per-thread device code (csrc/gcm_core.cuh, aes_core.cuh,
+// gf128.cuh -- the very functions the CUDA kernels call) on the CPU, looping over
+// the "threads" of a small virtual grid, so that the CPU test-suite can check the
+// index arithmetic (front padding, strided Horner weights, ragged last block,
+// lane combine) against the oracle without a GPU.  The cross-thread steps that
+// the kernels do with shuffles / shared memory are restated here with plain
+// loops.  Built by tests/conftest.py with `nvcc -x cu` (host code only).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+#include "../aes-gcm-128-192-256-bits_b200/csrc/gcm_core.cuh"
+
+namespace {
+
+struct TeHost {
+    const uint32_t* te0;
+    __host__ __device__ uint32_t operator()(int tab, uint32_t w, int k) const
+    {
+        const uint32_t t = te0[(w >> (8 * k)) & 0xff];
+        return tab ? ag_rotl32(t, 8 * tab) : t;
+    }
+};
+
+struct GhHost {
+    const uint4* tab;
+    __host__ __device__ uint4 operator()(uint32_t w, int k) const { return tab[(w >> (8 * k)) & 0xff]; }
+};
+
+gf128 gf_from_bytes(const uint8_t b[16])
+{
+    gf128 r;
+    for (int i = 0; i < 4; ++i)
+        r.w[i] = ((uint32_t)b[4 * i] << 24) | ((uint32_t)b[4 * i + 1] << 16) | ((uint32_t)b[4 * i + 2] << 8) | b[4 * i + 3];
+    return r;
+}
+
+void gf_to_bytes(const gf128& v, uint8_t b[16])
+{
+    for (int i = 0; i < 4; ++i) {
+        b[4 * i] = (uint8_t)(v.w[i] >> 24);
+        b[4 * i + 1] = (uint8_t)(v.w[i] >> 16);
+        b[4 * i + 2] = (uint8_t)(v.w[i] >> 8);
+        b[4 * i + 3] = (uint8_t)v.w[i];
+    }
+}
+
+gf128 gf_pow(gf128 h, uint64_t e)
+{
+    gf128 r = gf_one();
+    while (e) {
+        if (e & 1) r = gf_mul(r, h);
+        h = gf_mul(h, h);
+        e >>= 1;
+    }
+    return r;
+}
+
+void build_table(const gf128& c, std::vector<uint4>& tab)
+{
+    gf128 basis[8];
+    basis[0] = c;
+    for (int k = 1; k < 8; ++k) basis[k] = gf_mulx(basis[k - 1]);
+    tab.resize(256);
+    for (uint32_t b = 0; b < 256; ++b) tab[b] = gf_table_row(basis, b);
+}
+
+struct Tables {
+    uint8_t sbox[256];
+    uint32_t te0[256];
+    Tables() { ag_build_sbox_te0(sbox, te0); }
+};
+const Tables& tables()
+{
+    static Tables t;
+    return t;
+}
+
+template <int NR>
+void stream_nr(const StreamParams& p, int mode, uint64_t ncta, uint64_t nt, const gf128& H, gf128& total)
+{
+    const uint64_t Gt = ncta * nt;
+    std::vector<uint4> tab;
+    build_table(gf_pow(H, Gt), tab);
+    TeHost te{tables().te0};
+    GhHost gh{tab.data()};
+    total = gf_zero();
+    for (uint64_t g = 0; g < Gt; ++g) {
+        gf128 y;
+        switch (mode) {
+            case AG_MODE_ENC: y = ag_stream_lane<NR, AG_MODE_ENC>(p, g, Gt, te, gh); break;
+            case AG_MODE_DEC: y = ag_stream_lane<NR, AG_MODE_DEC>(p, g, Gt, te, gh); break;
+            case AG_MODE_GHASH_ONLY: y = ag_stream_lane<NR, AG_MODE_GHASH_ONLY>(p, g, Gt, te, gh); break;
+            default: y = ag_stream_lane<NR, AG_MODE_CTR_ONLY>(p, g, Gt, te, gh); break;
+        }
+        // kernel: y *= hpow_thread[nt - tid]; CTA xor; *= hpow_cta[ncta-1-cta]
+        const uint64_t cta = g / nt, tid = g % nt;
+        y = gf_mul(y, gf_pow(H, nt - tid));
+        y = gf_mul(y, gf_pow(gf_pow(H, nt), ncta - 1 - cta));
+        total = gf_xor(total, y);
+    }
+}
+
+template <int NR, bool DEC>
+void batch_nr(const BatchParams& p, uint32_t G, const gf128& H)
+{
+    std::vector<uint4> tab_g, tab_1;
+    build_table(gf_pow(H, G), tab_g);
+    build_table(H, tab_1);
+    TeHost te{tables().te0};
+    GhHost gh_g{tab_g.data()}, gh_1{tab_1.data()};
+    for (uint64_t m = 0; m < p.n_msgs; ++m) {
+        const MsgDesc d = ag_batch_msg(p, m);
+        const uint8_t* ivp = p.iv + 12 * m;
+        uint32_t iv[3] = {0, 0, 0};
+        for (int j = 0; j < 12; ++j) iv[j >> 2] |= (uint32_t)ivp[j] << (8 * (j & 3));
+        const AesCtrConst cc = aes_ctr_precompute(p.rk, iv[0], iv[1], iv[2], te);
+        gf128 r = gf_zero();
+        for (uint32_t t = 0; t < G; ++t) {
+            gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, d, t, G, te, gh_g);
+            r = gf_xor(r, y);
+            r = gf_mul_table(r, gh_1);
+        }
+        uint32_t e[4];
+        aes_ctr_block<NR>(p.rk, cc, 1u, te, e);
+        uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
+                          ag_bswap32(r.w[3]) ^ e[3]};
+        uint8_t* tp = p.tag + 16 * m;
+        if (DEC) {
+            uint32_t x[4];
+            ag_load_block(tp, 16, x);
+            p.ok[m] = ((x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3])) ? 0 : 1;
+        } else {
+            ag_store_block(tp, 16, tg);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// rk_bytes: (nr+1)*16 expanded key bytes.  Returns the un-finished GHASH partial
+// sum_i C_i H^(n-i) (natural byte order) and writes `out`.
+int emul_stream(const uint8_t* rk_bytes, int nr, const uint8_t iv[12], uint32_t ctr0, const uint8_t* in, uint8_t* out,
+                uint64_t n_bytes, int mode, int ncta, int nt, uint8_t partial16[16])
+{
+    StreamParams p;
+    memset(&p, 0, sizeof(p));
+    memcpy(p.rk, rk_bytes, (size_t)16 * (nr + 1));
+    for (int j = 0; j < 12; ++j) p.iv[j >> 2] |= (uint32_t)iv[j] << (8 * (j & 3));
+    p.ctr0 = ctr0;
+    p.n_bytes = n_bytes;
+    p.in = in;
+    p.out = out;
+    const TeHost te{tables().te0};
+    uint32_t h[4];
+    aes_encrypt_words(p.rk, nr, 0, 0, 0, 0, te, h);
+    const gf128 H = gf_from_le_words(h[0], h[1], h[2], h[3]);
+    gf128 total;
+    switch (nr) {
+        case 10: stream_nr<10>(p, mode, ncta, nt, H, total); break;
+        case 12: stream_nr<12>(p, mode, ncta, nt, H, total); break;
+        case 14: stream_nr<14>(p, mode, ncta, nt, H, total); break;
+        default: return -1;
+    }
+    gf_to_bytes(total, partial16);
+    return 0;
+}
+
+int emul_batch(const uint8_t* rk_bytes, int nr, int decrypt, int G, const uint8_t* iv, const uint8_t* aad,
+               const uint64_t* aad_off, const uint8_t* in, const uint64_t* in_off, uint8_t* out, uint8_t* tag, uint8_t* ok,
+               uint64_t n_msgs)
+{
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    memcpy(p.rk, rk_bytes, (size_t)16 * (nr + 1));
+    p.iv = iv;
+    p.aad = aad;
+    p.aad_off = aad_off;
+    p.in = in;
+    p.in_off = in_off;
+    p.out = out;
+    p.tag = tag;
+    p.ok = ok;
+    p.n_msgs = n_msgs;
+    const TeHost te{tables().te0};
+    uint32_t h[4];
+    aes_encrypt_words(p.rk, nr, 0, 0, 0, 0, te, h);
+    const gf128 H = gf_from_le_words(h[0], h[1], h[2], h[3]);
+    switch (nr) {
+        case 10: decrypt ? batch_nr<10, true>(p, G, H) : batch_nr<10, false>(p, G, H); break;
+        case 12: decrypt ? batch_nr<12, true>(p, G, H) : batch_nr<12, false>(p, G, H); break;
+        case 14: decrypt ? batch_nr<14, true>(p, G, H) : batch_nr<14, false>(p, G, H); break;
+        default: return -1;
+    }
+    return 0;
+}
+
+int emul_key_expand(const uint8_t* key, int key_bytes, uint8_t* out)
+{
+    uint32_t rk[60];
+    const uint8_t* sb = tables().sbox;
+    const int nr = aes_key_expand_words(key, key_bytes, [&](uint32_t b) { return (uint32_t)sb[b & 0xff]; }, rk);
+    memcpy(out, rk, (size_t)16 * (nr + 1));
+    return nr;
+}
+
+void emul_gf_mul(const uint8_t a[16], const uint8_t b[16], uint8_t out[16])
+{
+    gf_to_bytes(gf_mul(gf_from_bytes(a), gf_from_bytes(b)), out);
+}
+
+// product through the Shoup-table path used on the per-block hot loop
+void emul_gf_mul_table(const uint8_t x[16], const uint8_t c[16], uint8_t out[16])
+{
+    std::vector<uint4> tab;
+    build_table(gf_from_bytes(c), tab);
+    GhHost gh{tab.data()};
+    gf_to_bytes(gf_mul_table(gf_from_bytes(x), gh), out);
+}
+
+void emul_sbox(uint8_t out[256]) { memcpy(out, tables().sbox, 256); }
+
+}  // extern "C"
