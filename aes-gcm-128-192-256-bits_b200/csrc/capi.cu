@@ -43,6 +43,13 @@ struct agcm_ctx {
     bool key_set = false;
     cudaError_t last_err = cudaSuccess;
     uint64_t launches = 0;
+    // optional per-launch timing of the dominant kernel (bench.py roofline)
+    bool timing = false;
+    static constexpr int kTimingRing = 64;
+    cudaEvent_t tev[2 * kTimingRing] = {};
+    int tev_pending = 0;
+    double t_total_ms = 0.0;
+    uint64_t t_count = 0;
     // host pipeline (lazy)
     cudaStream_t hs[kSlots] = {nullptr, nullptr, nullptr};
     uint8_t* d_stage[kSlots] = {nullptr, nullptr, nullptr};
@@ -85,6 +92,20 @@ void iv_words(const uint8_t iv[12], uint32_t w[3])
                ((uint32_t)iv[4 * i + 3] << 24);
 }
 
+// fold finished (event pair) timings of the stream kernel into the running total
+int timing_drain(agcm_ctx* c)
+{
+    for (int i = 0; i < c->tev_pending; ++i) {
+        AG_CUDA(c, cudaEventSynchronize(c->tev[2 * i + 1]));
+        float ms = 0.f;
+        AG_CUDA(c, cudaEventElapsedTime(&ms, c->tev[2 * i], c->tev[2 * i + 1]));
+        c->t_total_ms += ms;
+        c->t_count++;
+    }
+    c->tev_pending = 0;
+    return AGCM_OK;
+}
+
 // GHASH partial of `n_bytes` at d_in (optionally also CTR) -> 16 B at d_partial16,
 // scaled by H^blocks_after.  parts_raw: per-CTA scratch (AG_MAX_CTA x 4 words).
 int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
@@ -104,8 +125,22 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
     p.key = c->d_key;
     p.te0 = c->d_te0;
     p.partials = parts_raw;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (c->timing) {
+        if (c->tev_pending == agcm_ctx::kTimingRing) {
+            int rc = timing_drain(c);
+            if (rc) return rc;
+        }
+        ev0 = c->tev[2 * c->tev_pending];
+        ev1 = c->tev[2 * c->tev_pending + 1];
+        AG_CUDA(c, cudaEventRecord(ev0, st));
+    }
     AG_CUDA(c, ag_launch_stream(p, c->nr, mode, c->ncta, c->nt, st));
     c->launches++;
+    if (c->timing) {
+        AG_CUDA(c, cudaEventRecord(ev1, st));
+        c->tev_pending++;
+    }
     if (mode != AG_MODE_CTR_ONLY && d_partial16) {
         AG_CUDA(c, ag_launch_reduce_scale(c->d_key, parts_raw, (uint32_t)c->ncta, blocks_after, d_partial16, st));
         c->launches++;
@@ -255,6 +290,8 @@ void agcm_ctx_destroy(agcm_ctx* c)
         cudaFree(c->d_stage_aux[s]);
         cudaFree(c->d_stage_parts[s]);
     }
+    for (cudaEvent_t e : c->tev)
+        if (e) cudaEventDestroy(e);
     cudaFree(c->d_chunk_partials);
     cudaFree(c->d_aad_stage);
     cudaFree(c->d_te0);
@@ -267,6 +304,30 @@ void agcm_ctx_destroy(agcm_ctx* c)
 int agcm_last_cuda_error(const agcm_ctx* c) { return c ? (int)c->last_err : 0; }
 const char* agcm_last_cuda_error_string(const agcm_ctx* c) { return cudaGetErrorString(c ? c->last_err : cudaSuccess); }
 uint64_t agcm_launch_count(const agcm_ctx* c) { return c ? c->launches : 0; }
+
+int agcm_timing_enable(agcm_ctx* c, int on)
+{
+    if (!c) return AGCM_E_BAD_ARG;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    if (on && !c->tev[0])
+        for (cudaEvent_t& e : c->tev) AG_CUDA(c, cudaEventCreate(&e));
+    int rc = timing_drain(c);
+    if (rc) return rc;
+    c->timing = on != 0;
+    c->t_total_ms = 0.0;
+    c->t_count = 0;
+    return AGCM_OK;
+}
+
+int agcm_timing_read(agcm_ctx* c, double* total_ms, uint64_t* n_launches)
+{
+    if (!c) return AGCM_E_BAD_ARG;
+    int rc = timing_drain(c);
+    if (rc) return rc;
+    if (total_ms) *total_ms = c->t_total_ms;
+    if (n_launches) *n_launches = c->t_count;
+    return AGCM_OK;
+}
 
 int agcm_get_info(const agcm_ctx* c, int* n_cta, int* threads, int* sm_count)
 {
@@ -392,16 +453,25 @@ int agcm_stream_crypt(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const 
     return agcm_stream_finish(c, decrypt, h_iv12, part, 1, d_aad, aad_len, n_bytes, d_tag, d_ok, stream);
 }
 
-int agcm_stream_probe(agcm_ctx* c, int what, const uint8_t h_iv12[12], const uint8_t* d_in, uint8_t* d_out,
-                      uint64_t n_bytes, void* stream)
+int agcm_gctr(agcm_ctx* c, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
+              uint64_t n_bytes, void* stream)
 {
-    if (!c || !h_iv12 || !d_in) return AGCM_E_BAD_ARG;
+    if (!c || !h_iv12 || (n_bytes && (!d_in || !d_out))) return AGCM_E_BAD_ARG;
     if (!c->key_set) return AGCM_E_NO_KEY;
-    if (what != AG_MODE_GHASH_ONLY && what != AG_MODE_CTR_ONLY) return AGCM_E_BAD_ARG;
-    if (what == AG_MODE_CTR_ONLY && !d_out) return AGCM_E_BAD_ARG;
+    const uint64_t nb = (n_bytes + 15) >> 4;
+    if (first_block > kMaxBlocks || nb > kMaxBlocks - first_block) return AGCM_E_COUNTER_OVERFLOW;
     AG_CUDA(c, cudaSetDevice(c->device));
-    return run_stream(c, what, h_iv12, 0, d_in, d_out, n_bytes, 0, c->d_parts, c->d_scratch + SC_PART_CT,
+    return run_stream(c, AG_MODE_CTR_ONLY, h_iv12, first_block, d_in, d_out, n_bytes, 0, c->d_parts, nullptr,
                       (cudaStream_t)stream);
+}
+
+int agcm_ghash(agcm_ctx* c, const uint8_t* d_in, uint64_t n_bytes, uint8_t* d_y16, void* stream)
+{
+    if (!c || !d_y16 || (n_bytes && !d_in)) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    const uint8_t iv0[12] = {0};
+    return run_stream(c, AG_MODE_GHASH_ONLY, iv0, 0, d_in, nullptr, n_bytes, 0, c->d_parts, d_y16, (cudaStream_t)stream);
 }
 
 static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, BatchParams& p, size_t n_msgs, void* stream)
@@ -482,16 +552,102 @@ void agcm_host_free(void* p)
     if (p) cudaFreeHost(p);
 }
 
+// chunked H2D -> fused kernel -> D2H of one counter range; the per-chunk partials
+// (each scaled for everything after it, including `blocks_after0`) land in
+// c->d_chunk_partials[0..n_chunks).  Leaves the slot streams running.
+static int host_pipeline(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uint64_t first_block0, const uint8_t* h_in,
+                         uint8_t* h_out, uint64_t n_bytes, uint64_t blocks_after0, uint64_t* n_chunks_out)
+{
+    const uint64_t nblocks = (n_bytes + 15) >> 4;
+    const uint64_t n_chunks = (n_bytes + kChunkBytes - 1) / kChunkBytes;
+    if (n_chunks > kMaxChunks || n_chunks > SC_PARTS_MAX) return AGCM_E_BAD_LEN;
+    const int mode = decrypt ? AG_MODE_DEC : AG_MODE_ENC;
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        const int s = (int)(k % kSlots);
+        cudaStream_t st = c->hs[s];
+        const uint64_t off = k * kChunkBytes;
+        const uint64_t nb = (n_bytes - off) < kChunkBytes ? (n_bytes - off) : kChunkBytes;
+        const uint64_t fb = off >> 4;
+        const uint64_t after = nblocks - fb - ((nb + 15) >> 4) + blocks_after0;
+        AG_CUDA(c, cudaMemcpyAsync(c->d_stage[s], h_in + off, nb, cudaMemcpyHostToDevice, st));
+        int rc = run_stream(c, mode, h_iv12, first_block0 + fb, c->d_stage[s], c->d_stage[s], nb, after,
+                            c->d_stage_parts[s], c->d_chunk_partials + 16 * k, st);
+        if (rc) return rc;
+        AG_CUDA(c, cudaMemcpyAsync(h_out + off, c->d_stage[s], nb, cudaMemcpyDeviceToHost, st));
+    }
+    *n_chunks_out = n_chunks;
+    return AGCM_OK;
+}
+
+int agcm_stream_part_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* h_in,
+                          uint8_t* h_out, uint64_t n_bytes, uint64_t blocks_after, uint8_t h_partial16[16])
+{
+    if (!c || !h_iv12 || !h_partial16 || (n_bytes && (!h_in || !h_out))) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    const uint64_t nb = (n_bytes + 15) >> 4;
+    if (first_block > kMaxBlocks || nb > kMaxBlocks - first_block || blocks_after > kMaxBlocks - first_block - nb)
+        return AGCM_E_COUNTER_OVERFLOW;
+    if (blocks_after && (n_bytes & 15)) return AGCM_E_BAD_LEN;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc) return rc;
+    uint64_t n_chunks = 0;
+    rc = host_pipeline(c, decrypt, h_iv12, first_block, h_in, h_out, n_bytes, blocks_after, &n_chunks);
+    if (rc) return rc;
+    for (int s = 1; s < kSlots; ++s) AG_CUDA(c, cudaStreamSynchronize(c->hs[s]));
+    // xor of the chunk partials = this range's partial (exponent 0: already scaled)
+    uint8_t* d_p = c->d_scratch + SC_PART_CT;
+    if (n_chunks == 0) {
+        AG_CUDA(c, cudaMemsetAsync(d_p, 0, 16, c->hs[0]));
+    } else {
+        AG_CUDA(c, ag_launch_xor_parts(c->d_chunk_partials, (uint32_t)n_chunks, d_p, c->hs[0]));
+        c->launches++;
+    }
+    AG_CUDA(c, cudaMemcpyAsync(h_partial16, d_p, 16, cudaMemcpyDeviceToHost, c->hs[0]));
+    AG_CUDA(c, cudaStreamSynchronize(c->hs[0]));
+    return AGCM_OK;
+}
+
+int agcm_stream_finish_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const uint8_t* h_partials16, int n_parts,
+                            const uint8_t* h_aad, uint64_t aad_len, uint64_t ct_len, uint8_t h_tag[16], int* h_ok)
+{
+    if (!c || !h_iv12 || !h_tag || (n_parts && !h_partials16) || (aad_len && !h_aad) || (decrypt && !h_ok))
+        return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (n_parts < 0 || (size_t)n_parts > kMaxChunks) return AGCM_E_BAD_ARG;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc) return rc;
+    cudaStream_t st = c->hs[0];
+    if (aad_len > c->aad_stage_cap) {
+        cudaFree(c->d_aad_stage);
+        c->d_aad_stage = nullptr;
+        c->aad_stage_cap = 0;
+        AG_CUDA(c, cudaMalloc(&c->d_aad_stage, aad_len));
+        c->aad_stage_cap = aad_len;
+    }
+    if (aad_len) AG_CUDA(c, cudaMemcpyAsync(c->d_aad_stage, h_aad, aad_len, cudaMemcpyHostToDevice, st));
+    if (n_parts) AG_CUDA(c, cudaMemcpyAsync(c->d_chunk_partials, h_partials16, 16 * (size_t)n_parts, cudaMemcpyHostToDevice, st));
+    uint8_t* d_tag = c->d_scratch + SC_TAG;
+    uint8_t* d_ok = c->d_scratch + SC_OK;
+    if (decrypt) AG_CUDA(c, cudaMemcpyAsync(d_tag, h_tag, 16, cudaMemcpyHostToDevice, st));
+    rc = run_finish(c, decrypt, h_iv12, c->d_chunk_partials, n_parts, c->d_aad_stage, aad_len, ct_len, d_tag, d_ok, st);
+    if (rc) return rc;
+    uint8_t okb = 1;
+    if (decrypt) AG_CUDA(c, cudaMemcpyAsync(&okb, d_ok, 1, cudaMemcpyDeviceToHost, st));
+    else AG_CUDA(c, cudaMemcpyAsync(h_tag, d_tag, 16, cudaMemcpyDeviceToHost, st));
+    AG_CUDA(c, cudaStreamSynchronize(st));
+    if (h_ok) *h_ok = okb ? 1 : 0;
+    return AGCM_OK;
+}
+
 int agcm_stream_crypt_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const uint8_t* h_aad, uint64_t aad_len,
                            const uint8_t* h_in, uint8_t* h_out, uint64_t n_bytes, uint8_t h_tag[16], int* h_ok)
 {
     if (!c || !h_iv12 || !h_tag || (n_bytes && (!h_in || !h_out)) || (aad_len && !h_aad) || (decrypt && !h_ok))
         return AGCM_E_BAD_ARG;
     if (!c->key_set) return AGCM_E_NO_KEY;
-    const uint64_t total_blocks = (n_bytes + 15) >> 4;
-    if (total_blocks > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
-    const uint64_t n_chunks = (n_bytes + kChunkBytes - 1) / kChunkBytes;
-    if (n_chunks > kMaxChunks || n_chunks > SC_PARTS_MAX) return AGCM_E_BAD_LEN;
+    if (((n_bytes + 15) >> 4) > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
     AG_CUDA(c, cudaSetDevice(c->device));
     int rc = ensure_pipeline(c);
     if (rc) return rc;
@@ -503,20 +659,9 @@ int agcm_stream_crypt_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], c
         c->aad_stage_cap = aad_len;
     }
     if (aad_len) AG_CUDA(c, cudaMemcpyAsync(c->d_aad_stage, h_aad, aad_len, cudaMemcpyHostToDevice, c->hs[0]));
-    const int mode = decrypt ? AG_MODE_DEC : AG_MODE_ENC;
-    for (uint64_t k = 0; k < n_chunks; ++k) {
-        const int s = (int)(k % kSlots);
-        cudaStream_t st = c->hs[s];
-        const uint64_t off = k * kChunkBytes;
-        const uint64_t nb = (n_bytes - off) < kChunkBytes ? (n_bytes - off) : kChunkBytes;
-        const uint64_t first_block = off >> 4;
-        const uint64_t after = total_blocks - first_block - ((nb + 15) >> 4);
-        AG_CUDA(c, cudaMemcpyAsync(c->d_stage[s], h_in + off, nb, cudaMemcpyHostToDevice, st));
-        rc = run_stream(c, mode, h_iv12, first_block, c->d_stage[s], c->d_stage[s], nb, after, c->d_stage_parts[s],
-                        c->d_chunk_partials + 16 * k, st);
-        if (rc) return rc;
-        AG_CUDA(c, cudaMemcpyAsync(h_out + off, c->d_stage[s], nb, cudaMemcpyDeviceToHost, st));
-    }
+    uint64_t n_chunks = 0;
+    rc = host_pipeline(c, decrypt, h_iv12, 0, h_in, h_out, n_bytes, 0, &n_chunks);
+    if (rc) return rc;
     for (int s = 1; s < kSlots; ++s) AG_CUDA(c, cudaStreamSynchronize(c->hs[s]));
     uint8_t* d_tag = c->d_scratch + SC_TAG;
     uint8_t* d_ok = c->d_scratch + SC_OK;

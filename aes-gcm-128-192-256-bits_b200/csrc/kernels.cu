@@ -266,6 +266,20 @@ __global__ void __launch_bounds__(32) k_reduce_scale(const KeyDev* kd, const uin
     }
 }
 
+// out16 = xor of n 16-byte partials (natural byte order in and out)
+__global__ void __launch_bounds__(32) k_xor_parts(const uint8_t* __restrict__ parts, uint32_t n, uint8_t* __restrict__ out)
+{
+    const uint32_t lane = threadIdx.x;
+    gf128 s = gf_zero();
+    for (uint32_t j = lane; j < n; j += 32) {
+        uint32_t x[4];
+        ag_load_block(parts + 16 * j, 16, x);
+        s.w[0] ^= x[0]; s.w[1] ^= x[1]; s.w[2] ^= x[2]; s.w[3] ^= x[3];
+    }
+    s = warp_xor(s);
+    if (lane == 0) ag_store_block(out, 16, s.w);
+}
+
 // Tag finish (gcm_ghash.vhd:257,293 + tb/gcm_model.py:33-51):
 //   S = xor parts (each already aligned so that the last CT block weighs H^1)
 //   QA = sum A_i H^(a-i) over the (short) AAD given here, if any
@@ -494,6 +508,12 @@ cudaError_t ag_launch_reduce_scale(const KeyDev* kd, const uint32_t* parts, uint
                                    cudaStream_t st)
 {
     k_reduce_scale<<<1, 32, 0, st>>>(kd, parts, n_in, e, out);
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_xor_parts(const uint8_t* parts, uint32_t n, uint8_t* out, cudaStream_t st)
+{
+    k_xor_parts<<<1, 32, 0, st>>>(parts, n, out);
     return cudaGetLastError();
 }
 

@@ -29,4 +29,5 @@ cudaError_t ag_launch_key_setup(KeyDev* kd, const uint32_t* te0, int nt_stream, 
 cudaError_t ag_launch_reduce_scale(const KeyDev* kd, const uint32_t* parts_raw, uint32_t n_in, uint64_t e,
                                    uint8_t* out16, cudaStream_t st);
 cudaError_t ag_launch_finish(const FinishParams& p, cudaStream_t st);
+cudaError_t ag_launch_xor_parts(const uint8_t* parts16, uint32_t n, uint8_t* out16, cudaStream_t st);
 size_t ag_smem_bytes();

@@ -1,0 +1,122 @@
+"""Drop-in replacement for the reference golden model tb/gcm_model.py.
+
+Same class name, constructor arguments, methods, attributes and error behaviour
+(tb/gcm_model.py:5-51), so that tb/gcm_test.py:45,76-94 can bind its monitors and
+scoreboard to it unchanged -- but AES and GHASH run on the B200 through
+libaesgcm_b200.so instead of pycryptodome.
+
+Call pattern of the testbench: synchronous callbacks, one <=16-byte
+block per call, AAD blocks first, and the expected output must be in
+``data_out`` as soon as ``load_plain_text`` returns.  A kernel launch per 16 bytes
+would be all latency, so the adapter PREFETCHES keystream: the device runs GCTR
+(agcm_gctr, src/gcm_gctr.vhd:150) over a zero window starting at the current
+counter, and each callback XORs its bytes against that window.  The tag is
+produced at ``get_tag`` by one fused GCTR+GHASH pass of the device over the
+accumulated AAD and text (agcm_stream_crypt_host); that pass also re-derives the
+output text, which is checked against what the callbacks handed out.
+"""
+import logging
+
+try:  # the reference imports cocotb's logger (tb/gcm_model.py:2); optional here
+    from cocotb import log  # type: ignore
+except Exception:  # pragma: no cover - cocotb is not a dependency of this repo
+    log = logging.getLogger("aesgcm_b200.gcm_model")
+
+from .engine import GcmEngine
+
+_KS_WINDOW = 1 << 16  # bytes of keystream fetched per device call
+
+
+class gcm:
+    def __init__(self, key, icb, ed, device=0, engine=None):
+        # tb/gcm_model.py:8-18
+        self.ed = ed
+        self.data_out = []
+        self.tag = []
+
+        _key = int(key['data'], 16).to_bytes(key['n_bytes'], byteorder='big')
+        _icb = int(icb['data'], 16).to_bytes(icb['n_bytes'], byteorder='big')
+        if len(_icb) != 12:
+            raise ValueError("the IV must be 96 bits (src/gcm_pkg.vhd:17)")
+        self._own_engine = engine is None
+        self.model = engine if engine is not None else GcmEngine(device)
+        self.model.set_key(_key)          # raw 16/24/32 B, or 176/208/240 B pre-expanded stages
+        self._iv = _icb
+        self._aad = bytearray()
+        self._text = bytearray()          # everything fed to load_plain_text / load_cipher_text
+        self._out = bytearray()           # everything handed out
+        self._ks = b""                    # keystream window ...
+        self._ks_base = 0                 # ... covering message bytes [_ks_base, _ks_base + len(_ks))
+        self._zeros = None
+        self._ksbuf = None
+
+    # ------------------------------------------------------------------
+    def _keystream(self, pos, n):
+        """n bytes of keystream for message byte offset pos (device GCTR over zeros)."""
+        out = bytearray()
+        while n:
+            off = pos - self._ks_base
+            if off < 0 or off >= len(self._ks):
+                import torch
+                dev = "cuda:%d" % self.model.device
+                if self._zeros is None:
+                    self._zeros = torch.zeros(_KS_WINDOW, dtype=torch.uint8, device=dev)
+                    self._ksbuf = torch.empty(_KS_WINDOW, dtype=torch.uint8, device=dev)
+                first_block = pos // 16
+                with torch.cuda.device(self.model.device):
+                    self.model.gctr_device(self._iv, first_block, self._zeros, self._ksbuf)
+                    self._ks = self._ksbuf.cpu().numpy().tobytes()
+                self._ks_base = first_block * 16
+                off = pos - self._ks_base
+            take = min(n, len(self._ks) - off)
+            out += self._ks[off:off + take]
+            pos += take
+            n -= take
+        return bytes(out)
+
+    def _crypt(self, data):
+        data = bytes(data)
+        ks = self._keystream(len(self._text), len(data))
+        res = (int.from_bytes(data, 'big') ^ int.from_bytes(ks, 'big')).to_bytes(len(data), 'big') if data else b""
+        self._text += data
+        self._out += res
+        return res
+
+    # ------------------------------------------------------------------
+    def load_aad(self, aad):
+        # tb/gcm_model.py:21-22
+        self._aad += bytes(aad)
+
+    def load_plain_text(self, pt):
+        # tb/gcm_model.py:25-26
+        self.data_out.append(self._crypt(pt))
+
+    def load_cipher_text(self, ct):
+        # tb/gcm_model.py:29-30
+        self.data_out.append(self._crypt(ct))
+
+    # ------------------------------------------------------------------
+    def get_tag(self, tag):
+        # tb/gcm_model.py:33-51
+        if self.ed == 'enc':
+            ct, model_tag = self.model.encrypt(self._iv, bytes(self._aad), bytes(self._text))
+            if ct != bytes(self._out):
+                raise RuntimeError("fused pass and prefetched keystream disagree")
+            self.tag.append(model_tag)
+            log.info('Model\tTAG ' + '{:032X}'.format(int.from_bytes(model_tag, 'big')))
+            if tag == model_tag:
+                log.info('\33[92m' + "OK:\tTAGs match. " + '\33[00m')
+            else:
+                log.error('ERROR: TAGs mismatch')
+        else:
+            pt, ok = self.model.decrypt(self._iv, bytes(self._aad), bytes(self._text), bytes(tag), raise_on_fail=False)
+            if pt != bytes(self._out):
+                raise RuntimeError("fused pass and prefetched keystream disagree")
+            if ok:
+                self.tag.append(tag)
+                log.info('\33[92m' + "OK:\tTAGs match. " + '\33[00m' + "the message is authentic!")
+            else:
+                log.error("ERROR:\tKEY or IV incorrect, or message corrupted")
+                # Force TAG error: invert received TAG (tb/gcm_model.py:49-51)
+                not_tag = ~(int.from_bytes(tag, 'big'))
+                self.tag.append((not_tag & ((1 << 128) - 1)).to_bytes(16, 'big'))

@@ -1,0 +1,76 @@
+"""Multi-GPU sharding of the AES-GCM path; one process per GPU.
+
+Two regimes, matching the structure of the algorithm rather than inventing
+communication:
+
+* independent messages: `batch_split` hands each rank a contiguous message range;
+  there is NO data-path collective.
+* one large message: `shard_plan` splits the CT block range into contiguous
+  counter ranges.  Rank r runs the fused kernel on its range with counter start
+  2 + first_block (src/aes_icb.vhd:100) and gets a 16-byte GHASH partial already
+  scaled by H^(blocks after the shard) (agcm_stream_part).  One all_gather of 16
+  bytes per rank (NCCL over NVLink; NCCL has no XOR reduction, so gather + XOR
+  inside agcm_stream_finish) and any rank can finish the tag.  The combine rests
+  on the linearity the reference itself uses at src/gcm_ghash.vhd:317-344.
+"""
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class Shard:
+    rank: int
+    first_block: int    # index of the shard's first 16-byte block in the message
+    byte_offset: int
+    n_bytes: int        # bytes in this shard (only the last non-empty shard may be ragged)
+    blocks_after: int   # CT blocks of the message that follow this shard
+
+
+def shard_plan(n_bytes, world_size):
+    """Contiguous, block-aligned counter ranges; empty shards allowed when the
+    message has fewer blocks than ranks."""
+    if n_bytes < 0 or world_size < 1:
+        raise ValueError("bad shard request")
+    blocks = (n_bytes + 15) // 16
+    if blocks > 0xFFFFFFFE:
+        raise OverflowError("more than 2^32-2 blocks under one IV (src/aes_icb.vhd:114)")
+    per = (blocks + world_size - 1) // world_size
+    plan = []
+    for r in range(world_size):
+        fb = min(r * per, blocks)
+        nb = min(per, blocks - fb)
+        off = fb * 16
+        nbytes = max(0, min(n_bytes - off, nb * 16))
+        plan.append(Shard(r, fb, off, nbytes, blocks - fb - nb))
+    return plan
+
+
+def batch_split(n_msgs, world_size, rank):
+    """[lo, hi) message range of `rank` (balanced to within one message)."""
+    base, rem = divmod(n_msgs, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_partials(partial16, group=None):
+    """all_gather of one 16-byte uint8 tensor per rank -> [world, 16] tensor on the
+    same device (NCCL for CUDA tensors, gloo for CPU tensors in the host tests)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world, 16), dtype=torch.uint8, device=partial16.device)
+    dist.all_gather_into_tensor(out.view(-1), partial16.contiguous().view(-1), group=group)
+    return out
+
+
+def stream_crypt_sharded(engine, decrypt, iv, aad, shard, data_in, data_out, total_bytes, tag, ok=None, group=None,
+                         stream=None):
+    """Rank-local part + gather + finish.  `data_in`/`data_out` hold THIS rank's
+    shard (CUDA uint8, shard.n_bytes long); `aad` is the full AAD (CUDA uint8 or
+    None) on every rank; every rank ends up with the tag / ok flag."""
+    import torch
+    part = torch.empty(16, dtype=torch.uint8, device=data_in.device)
+    engine.stream_part_device(decrypt, iv, shard.first_block, data_in, data_out, shard.blocks_after, part,
+                              n_bytes=shard.n_bytes, stream=stream)
+    parts = gather_partials(part, group)
+    engine.stream_finish_device(decrypt, iv, parts, parts.shape[0], aad, total_bytes, tag, ok, stream=stream)
+    return parts

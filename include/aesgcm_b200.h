@@ -58,6 +58,10 @@ const char* agcm_last_cuda_error_string(const agcm_ctx* ctx);
 int agcm_get_info(const agcm_ctx* ctx, int* n_cta, int* threads, int* sm_count);
 /* number of kernels this context has launched so far (bench.py gpu_launches) */
 uint64_t agcm_launch_count(const agcm_ctx* ctx);
+/* Optional CUDA-event timing of every fused stream-kernel launch, on the stream it
+ * is launched on (bench.py roofline).  read: sum of durations and launch count since enable. */
+int agcm_timing_enable(agcm_ctx* ctx, int on);
+int agcm_timing_read(agcm_ctx* ctx, double* total_ms, uint64_t* n_launches);
 
 /* ---- key schedule ---------------------------------------------------------
  * Replaces tb/key_exp.py:118 aes_expand_key(key_hex, size) and the on-the-fly
@@ -130,16 +134,28 @@ int agcm_batch_crypt_uniform(agcm_ctx* ctx, int decrypt, int lanes, const uint8_
  * encrypt). */
 int agcm_stream_crypt_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], const uint8_t* h_aad, uint64_t aad_len,
                            const uint8_t* h_in, uint8_t* h_out, uint64_t n_bytes, uint8_t h_tag[16], int* h_ok);
+/* Host-buffer forms of agcm_stream_part / agcm_stream_finish (one rank's shard of a
+ * sharded message; the 16-byte partials travel between ranks). */
+int agcm_stream_part_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* h_in,
+                          uint8_t* h_out, uint64_t n_bytes, uint64_t blocks_after, uint8_t h_partial16[16]);
+int agcm_stream_finish_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], const uint8_t* h_partials16, int n_parts,
+                            const uint8_t* h_aad, uint64_t aad_len, uint64_t ct_len, uint8_t h_tag[16], int* h_ok);
 int agcm_batch_crypt_uniform_host(agcm_ctx* ctx, int decrypt, int lanes, const uint8_t* h_iv12, const uint8_t* h_aad,
                                   uint64_t aad_len, uint64_t aad_stride, const uint8_t* h_in, uint8_t* h_out,
                                   uint64_t len, uint64_t stride, uint8_t* h_tag, uint8_t* h_ok, size_t n_msgs);
 int agcm_host_alloc(void** out, size_t bytes); /* pinned */
 void agcm_host_free(void* p);
 
-/* ---- profiling aid (not part of the reference surface) ------------------------
- * Runs only one half of the fused stream kernel: what = 2 GHASH only, 3 CTR only. */
-int agcm_stream_probe(agcm_ctx* ctx, int what, const uint8_t h_iv12[12], const uint8_t* d_in, uint8_t* d_out,
-                      uint64_t n_bytes, void* stream);
+/* ---- the two halves of the datapath on their own -------------------------------
+ * agcm_gctr: the gcm_gctr entity alone (src/gcm_gctr.vhd:150, aes_icb.vhd:100):
+ *   d_out[i] = d_in[i] xor E_K(IV || 2 + first_block + i/16).  With a zero input
+ *   it yields raw keystream (used by the streaming gcm adapter to prefetch).
+ * agcm_ghash: the gcm_ghash absorb alone (src/gcm_ghash.vhd:259-272) over n_bytes
+ *   (zero-padded to a block): d_y16 = sum_i X_i * H^(n-i), natural byte order,
+ *   i.e. the running Y after absorbing the data from Y = 0. */
+int agcm_gctr(agcm_ctx* ctx, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
+              uint64_t n_bytes, void* stream);
+int agcm_ghash(agcm_ctx* ctx, const uint8_t* d_in, uint64_t n_bytes, uint8_t* d_y16, void* stream);
 
 #ifdef __cplusplus
 }

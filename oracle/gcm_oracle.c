@@ -268,6 +268,7 @@ ORACLE_API int oracle_gcm_crypt(const uint8_t *key, int key_len, const uint8_t i
 {
     uint8_t rk[240];
     int nr;
+    if ((len + 15) / 16 > 0xFFFFFFFEull) return -2;
     if (key_len == 16 || key_len == 24 || key_len == 32) {
         nr = oracle_key_expand(key, key_len, rk);
     } else if (key_len == 176 || key_len == 208 || key_len == 240) {
@@ -276,7 +277,6 @@ ORACLE_API int oracle_gcm_crypt(const uint8_t *key, int key_len, const uint8_t i
     } else {
         return -1;
     }
-    if ((len + 15) / 16 > 0xFFFFFFFEull) return -2;
     uint8_t h[16], ej0[16], y[16], lenblk[16];
     oracle_h_ej0(rk, nr, iv, h, ej0);
     memset(y, 0, 16);

@@ -1,0 +1,470 @@
+"""Parity of the CUDA engine (through the C ABI) against the CPU oracle, the
+committed golden fixtures and OpenSSL.  Everything here needs a B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def _rb(rng, n):
+    return rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    return torch
+
+
+def _dev(torch, b):
+    a = np.frombuffer(bytes(b), dtype=np.uint8) if not isinstance(b, np.ndarray) else b
+    if a.size == 0:
+        return torch.empty(0, dtype=torch.uint8, device="cuda")
+    return torch.from_numpy(a.copy()).cuda()
+
+
+# --------------------------------------------------------------------------- keys
+def test_key_expand_device_matches_reference_fixtures(engine, torch_mod):
+    torch = torch_mod
+    fx = _load("key_exp_vectors.json")
+    for size, kb in (("128", 16), ("192", 24), ("256", 32)):
+        cases = [c for c in fx["cases"] if c["size"] == size]
+        keys = np.frombuffer(b"".join(bytes.fromhex(c["key"]) for c in cases), dtype=np.uint8)
+        rks = engine.expand_keys_device(int(size), _dev(torch, keys))
+        torch.cuda.synchronize()
+        got = rks.cpu().numpy()
+        for i, c in enumerate(cases):
+            assert got[i].tobytes().hex() == c["expanded"], c["key"]
+        # host convenience call + the key_exp.py drop-in
+        assert engine.expand_key_host(bytes.fromhex(cases[0]["key"])).hex() == cases[0]["expanded"]
+
+
+def test_key_exp_adapter_signature(engine):
+    from aesgcm_b200 import key_exp
+    fx = _load("key_exp_vectors.json")
+    for c in fx["cases"][:6] + fx["cases"][-6:]:
+        out = key_exp.aes_expand_key(c["key"], c["size"])
+        assert isinstance(out, list) and bytes(out).hex() == c["expanded"]
+
+
+def test_set_key_raw_and_preexpanded(engine, oracle):
+    rng = np.random.default_rng(21)
+    for kb in (16, 24, 32):
+        key = _rb(rng, kb)
+        engine.set_key(key)
+        rk = engine.round_keys()
+        assert rk == oracle.key_expand(key)
+        h, _ = oracle.h_ej0(rk, bytes(12))
+        assert engine.hash_subkey() == h
+        engine.set_key(rk)  # pre-expanded stages, used as they are
+        assert engine.round_keys() == rk and engine.hash_subkey() == h
+    import aesgcm_b200
+    with pytest.raises(aesgcm_b200.AgcmError):
+        engine.set_key(b"x" * 17)
+
+
+# --------------------------------------------------------------------------- KATs
+def test_known_answer_vectors_host_api(engine):
+    for v in _load("kat_vectors.json")["vectors"]:
+        key, iv = bytes.fromhex(v["key"]), bytes.fromhex(v["iv"])
+        pt, aad = bytes.fromhex(v["pt"]), bytes.fromhex(v["aad"])
+        engine.set_key(key)
+        ct, tag = engine.encrypt(iv, aad, pt)
+        assert ct.hex() == v["ct"] and tag.hex() == v["tag"], v["name"]
+        assert engine.decrypt(iv, aad, ct, tag) == pt
+
+
+def test_known_answer_vectors_device_api(engine, torch_mod):
+    torch = torch_mod
+    for v in _load("kat_vectors.json")["vectors"]:
+        key, iv = bytes.fromhex(v["key"]), bytes.fromhex(v["iv"])
+        pt, aad = bytes.fromhex(v["pt"]), bytes.fromhex(v["aad"])
+        engine.set_key(key)
+        d_in, d_aad = _dev(torch, pt), _dev(torch, aad)
+        d_out = torch.empty_like(d_in)
+        d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+        engine.stream_crypt_device(0, iv, d_aad if len(aad) else None, d_in, d_out, d_tag)
+        torch.cuda.synchronize()
+        assert d_out.cpu().numpy().tobytes().hex() == v["ct"], v["name"]
+        assert d_tag.cpu().numpy().tobytes().hex() == v["tag"], v["name"]
+        # batched path, every lane count
+        for lanes in (1, 2, 4, 8, 16, 32):
+            n = 3
+            ivs = _dev(torch, iv * n)
+            data = _dev(torch, pt * n)
+            outb = torch.empty_like(data)
+            tags = torch.zeros(16 * n, dtype=torch.uint8, device="cuda")
+            aadb = _dev(torch, aad * n) if len(aad) else None
+            engine.batch_crypt_uniform_device(0, ivs, aadb, len(aad), len(aad), data, outb, len(pt), len(pt), tags,
+                                              n_msgs=n, lanes=lanes)
+            torch.cuda.synchronize()
+            assert outb.cpu().numpy().tobytes().hex() == v["ct"] * n, (v["name"], lanes)
+            assert tags.cpu().numpy().tobytes().hex() == v["tag"] * n, (v["name"], lanes)
+
+
+# ------------------------------------------------------------------- random messages
+@pytest.mark.parametrize("kb", [16, 24, 32])
+def test_stream_random_sizes_vs_oracle(engine, oracle, torch_mod, kb):
+    torch = torch_mod
+    rng = np.random.default_rng(100 + kb)
+    sizes = [0, 1, 15, 16, 17, 31, 32, 33, 1500, 4096, 65536 + 3, 1024 * 151552 // 64 + 7, 3 * 16 * 151552 + 16 * 5 + 9]
+    for n in sizes:
+        for alen in (0, 16, 20):
+            key, iv, aad, pt = _rb(rng, kb), _rb(rng, 12), _rb(rng, alen), _rb(rng, n)
+            engine.set_key(key)
+            want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt, threads=8)
+            ct, tag = engine.encrypt(iv, aad, pt)
+            assert ct == want_ct, (kb, n, alen)
+            assert tag == want_tag, (kb, n, alen)
+            # decrypt + verify, then reject a flipped ciphertext bit and a flipped tag bit
+            assert engine.decrypt(iv, aad, ct, tag) == pt
+            if n:
+                bad = bytearray(ct)
+                bad[n // 2] ^= 0x01
+                _, ok = engine.decrypt(iv, aad, bytes(bad), tag, raise_on_fail=False)
+                assert not ok
+            badtag = bytearray(tag)
+            badtag[15] ^= 0x80
+            _, ok = engine.decrypt(iv, aad, ct, bytes(badtag), raise_on_fail=False)
+            assert not ok
+
+
+def test_stream_long_aad_paths(engine, oracle):
+    # AAD > 4 KiB goes through the grid-wide GHASH-only kernel, AAD <= 4 KiB is folded in the finish kernel
+    rng = np.random.default_rng(7)
+    key, iv = _rb(rng, 16), _rb(rng, 12)
+    engine.set_key(key)
+    for alen in (1, 511, 512, 513, 4095, 4096, 4097, 100000 + 1, 16 * 151552 + 3):
+        for n in (0, 64, 5000):
+            aad, pt = _rb(rng, alen), _rb(rng, n)
+            want = oracle.gcm_crypt(key, iv, aad, pt, threads=8)
+            assert engine.encrypt(iv, aad, pt) == want, (alen, n)
+
+
+def test_config1_aes128_4k_messages_vs_oracle_and_openssl(engine, oracle, torch_mod):
+    """BASELINE config 1: AES-128, random 4096 B messages, AAD in {0,16,20,64}."""
+    torch = torch_mod
+    AESGCM = pytest.importorskip("cryptography.hazmat.primitives.ciphers.aead").AESGCM
+    rng = np.random.default_rng(0)
+    key = _rb(rng, 16)
+    engine.set_key(key)
+    n_msgs, length = 2000, 4096
+    for alen in (0, 16, 20, 64):
+        ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+        data = rng.integers(0, 256, n_msgs * length, dtype=np.uint8)
+        aad = rng.integers(0, 256, max(1, n_msgs * alen), dtype=np.uint8)
+        in_off = (np.arange(n_msgs + 1) * length).astype(np.uint64)
+        aad_off = (np.arange(n_msgs + 1) * alen).astype(np.uint64)
+        want_out, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), 16, True, ivs, aad, aad_off, data, in_off,
+                                               threads=8)
+        for lanes in (0, 1, 8, 32):
+            d_out = torch.empty(n_msgs * length, dtype=torch.uint8, device="cuda")
+            d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+            engine.batch_crypt_uniform_device(0, _dev(torch, ivs), _dev(torch, aad) if alen else None, alen, alen,
+                                              _dev(torch, data), d_out, length, length, d_tags, n_msgs=n_msgs, lanes=lanes)
+            torch.cuda.synchronize()
+            assert (d_out.cpu().numpy() == want_out).all(), (alen, lanes)
+            assert (d_tags.cpu().numpy() == want_tags).all(), (alen, lanes)
+        a = AESGCM(key)
+        for i in (0, 1, n_msgs - 1):
+            ref = a.encrypt(ivs[12 * i:12 * i + 12].tobytes(), data[i * length:(i + 1) * length].tobytes(),
+                            aad[i * alen:(i + 1) * alen].tobytes() if alen else None)
+            assert ref[:-16] == want_out[i * length:(i + 1) * length].tobytes()
+            assert ref[-16:] == want_tags[16 * i:16 * i + 16].tobytes()
+
+
+@pytest.mark.parametrize("kb", [16, 24, 32])
+def test_batch_ragged_offsets_all_lane_counts(engine, oracle, torch_mod, kb):
+    """Ragged, unaligned (contiguous) messages incl. empty ones; encrypt, decrypt, corrupted tags."""
+    torch = torch_mod
+    rng = np.random.default_rng(300 + kb)
+    n_msgs = 700
+    lens = rng.integers(0, 400, n_msgs)
+    lens[:6] = [0, 1, 15, 16, 17, 1500]
+    alens = rng.integers(0, 80, n_msgs)
+    alens[:4] = [0, 16, 0, 64]
+    in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.uint64)
+    data = rng.integers(0, 256, int(in_off[-1]), dtype=np.uint8)
+    aad = rng.integers(0, 256, int(aad_off[-1]), dtype=np.uint8)
+    ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+    key = _rb(rng, kb)
+    rk = oracle.key_expand(key)
+    engine.set_key(rk)  # shared PRE-EXPANDED key (config 3 flavour)
+    want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), kb, True, ivs, aad, aad_off, data, in_off, threads=8)
+    d_ivs, d_aad, d_data = _dev(torch, ivs), _dev(torch, aad), _dev(torch, data)
+    d_in_off, d_aad_off = torch.from_numpy(in_off.view(np.int64)).cuda(), torch.from_numpy(aad_off.view(np.int64)).cuda()
+    for lanes in (1, 2, 4, 8, 16, 32, 0):
+        d_ct = torch.zeros_like(d_data)
+        d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_device(0, d_ivs, d_aad, d_aad_off, d_data, d_in_off, d_ct, d_tags, lanes=lanes, avg_len_hint=200)
+        torch.cuda.synchronize()
+        assert (d_ct.cpu().numpy() == want_ct).all(), lanes
+        assert (d_tags.cpu().numpy() == want_tags).all(), lanes
+        # decrypt + verify with 1% corrupted tags
+        bad = rng.choice(n_msgs, n_msgs // 100 + 1, replace=False)
+        tags_in = want_tags.copy().reshape(n_msgs, 16)
+        tags_in[bad, rng.integers(0, 16)] ^= 0x04
+        d_pt = torch.zeros_like(d_data)
+        d_ok = torch.full((n_msgs,), 7, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_device(1, d_ivs, d_aad, d_aad_off, d_ct, d_in_off, d_pt, _dev(torch, tags_in.reshape(-1)), d_ok,
+                                  lanes=lanes, avg_len_hint=200)
+        torch.cuda.synchronize()
+        assert (d_pt.cpu().numpy() == data).all(), lanes
+        ok = d_ok.cpu().numpy()
+        expect = np.ones(n_msgs, np.uint8)
+        expect[bad] = 0
+        assert (ok == expect).all(), lanes
+
+
+def test_config3_shape_strided_packets(engine, oracle, torch_mod):
+    """BASELINE config 3 shape at reduced count: AES-192, 1500 B packets at a 1504 B stride,
+    per-message IV, shared pre-expanded key, no AAD; plus the contiguous 1500 B layout."""
+    torch = torch_mod
+    rng = np.random.default_rng(2)
+    key = _rb(rng, 24)
+    engine.set_key(oracle.key_expand(key))
+    n_msgs = 4096
+    ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+    for stride in (1504, 1500):
+        buf = rng.integers(0, 256, n_msgs * stride, dtype=np.uint8)
+        in_off = np.arange(n_msgs + 1, dtype=np.uint64) * 1500
+        packed = buf.reshape(n_msgs, stride)[:, :1500].reshape(-1).copy()
+        want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), 24, True, ivs, None, None, packed, in_off,
+                                              threads=8)
+        for lanes in (0, 1, 4):
+            d_buf = _dev(torch, buf)
+            d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+            engine.batch_crypt_uniform_device(0, _dev(torch, ivs), None, 0, 0, d_buf, d_buf, 1500, stride, d_tags,
+                                              n_msgs=n_msgs, lanes=lanes)  # in place
+            torch.cuda.synchronize()
+            got = d_buf.cpu().numpy().reshape(n_msgs, stride)
+            assert (got[:, :1500].reshape(-1) == want_ct).all(), (stride, lanes)
+            assert (got[:, 1500:] == buf.reshape(n_msgs, stride)[:, 1500:]).all()  # padding untouched
+            assert (d_tags.cpu().numpy() == want_tags).all(), (stride, lanes)
+
+
+def test_batch_host_api_roundtrip(engine, oracle):
+    rng = np.random.default_rng(9)
+    key = _rb(rng, 32)
+    engine.set_key(key)
+    n_msgs, length, stride, alen = 3000, 1500, 1504, 64
+    ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+    data = rng.integers(0, 256, n_msgs * stride, dtype=np.uint8)
+    aad = rng.integers(0, 256, n_msgs * alen, dtype=np.uint8)
+    out = data.copy()
+    tags = np.zeros(16 * n_msgs, np.uint8)
+    engine.crypt_batch_uniform_host(0, ivs, aad, alen, alen, data, out, length, stride, tags)
+    in_off = np.arange(n_msgs + 1, dtype=np.uint64) * length
+    aad_off = np.arange(n_msgs + 1, dtype=np.uint64) * alen
+    packed = data.reshape(n_msgs, stride)[:, :length].reshape(-1).copy()
+    want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), 32, True, ivs, aad, aad_off, packed, in_off, threads=8)
+    assert (out.reshape(n_msgs, stride)[:, :length].reshape(-1) == want_ct).all()
+    assert (tags == want_tags).all()
+    back = out.copy()
+    ok = np.zeros(n_msgs, np.uint8)
+    tags[16 * 5] ^= 1
+    engine.crypt_batch_uniform_host(1, ivs, aad, alen, alen, out, back, length, stride, tags, ok)
+    assert (back.reshape(n_msgs, stride)[:, :length] == data.reshape(n_msgs, stride)[:, :length]).all()
+    assert ok.sum() == n_msgs - 1 and ok[5] == 0
+
+
+# ------------------------------------------------------------ shards (one GPU, k parts)
+def test_counter_range_shards_combine(engine, oracle, torch_mod):
+    """SURVEY 8(e) regime 2 on one GPU: k counter-range shards + XOR of pre-scaled partials."""
+    torch = torch_mod
+    from aesgcm_b200.parallel import shard_plan
+    rng = np.random.default_rng(31)
+    key, iv, aad = _rb(rng, 32), _rb(rng, 12), _rb(rng, 16)
+    engine.set_key(key)
+    for n in (0, 100, 16 * 1000, 5 * 16 * 151552 + 11):
+        pt = rng.integers(0, 256, n, dtype=np.uint8)
+        want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt, threads=8)
+        d_in = _dev(torch, pt)
+        for world in (1, 2, 4, 8):
+            d_out = torch.zeros_like(d_in)
+            parts = torch.zeros((world, 16), dtype=torch.uint8, device="cuda")
+            for s in shard_plan(n, world):
+                sl = slice(s.byte_offset, s.byte_offset + s.n_bytes)
+                engine.stream_part_device(0, iv, s.first_block, d_in[sl], d_out[sl], s.blocks_after, parts[s.rank],
+                                          n_bytes=s.n_bytes)
+            d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+            engine.stream_finish_device(0, iv, parts, world, _dev(torch, aad), n, d_tag)
+            torch.cuda.synchronize()
+            assert d_out.cpu().numpy().tobytes() == want_ct, (n, world)
+            assert d_tag.cpu().numpy().tobytes() == want_tag, (n, world)
+
+
+def test_gctr_and_ghash_halves(engine, oracle, torch_mod):
+    torch = torch_mod
+    rng = np.random.default_rng(41)
+    key, iv = _rb(rng, 24), _rb(rng, 12)
+    engine.set_key(key)
+    rk = oracle.key_expand(key)
+    h, _ = oracle.h_ej0(rk, iv)
+    for n in (1, 16, 1000, 70000 + 5):
+        data = _rb(rng, n)
+        d_in = _dev(torch, data)
+        d_out = torch.empty_like(d_in)
+        for first_block in (0, 5, 2 ** 32 - 2 - (n + 15) // 16):
+            engine.gctr_device(iv, first_block, d_in, d_out)
+            torch.cuda.synchronize()
+            assert d_out.cpu().numpy().tobytes() == oracle.gctr(rk, iv, 2 + first_block, data)
+        y = torch.zeros(16, dtype=torch.uint8, device="cuda")
+        engine.ghash_device(d_in, y)
+        torch.cuda.synchronize()
+        assert y.cpu().numpy().tobytes() == oracle.ghash_absorb(h, data)
+
+
+def test_counter_overflow_rejected(engine, torch_mod):
+    torch = torch_mod
+    import aesgcm_b200
+    engine.set_key(bytes(16))
+    buf = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    part = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    with pytest.raises(aesgcm_b200.AgcmError) as ei:
+        engine.stream_part_device(0, bytes(12), 2 ** 32 - 3, buf, buf, 0, part)  # 4 blocks from 2^32-3: past 2^32-2
+    assert ei.value.rc == aesgcm_b200._lib.E_COUNTER_OVERFLOW
+    with pytest.raises(aesgcm_b200.AgcmError):
+        aesgcm_b200.GcmEngine(0).encrypt(bytes(12), b"", b"abc")  # no key
+
+
+# ------------------------------------------------------- the gcm_model.py drop-in surface
+@pytest.mark.parametrize("ed", ["enc", "dec"])
+def test_gcm_model_adapter_streaming_callbacks(oracle, ed):
+    """Drives the adapter exactly like tb/gcm_test.py:76-94 / tb/gcm_sequencer.py:137-231:
+    <=16-byte callbacks, AAD first, output available right after each call, tag at the end."""
+    from aesgcm_b200 import gcm_model
+    rng = np.random.default_rng(55)
+    for kb, n, alen in ((16, 48, 28), (32, 0, 68), (24, 1000 + 7, 5), (32, 70000, 0)):
+        key, iv, aad, text = _rb(rng, kb), _rb(rng, 12), _rb(rng, alen), _rb(rng, n)
+        want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, text)
+        src = text if ed == "enc" else want_ct
+        want_out = want_ct if ed == "enc" else text
+        m = gcm_model.gcm({'data': key.hex().upper(), 'n_bytes': kb}, {'data': iv.hex().upper(), 'n_bytes': 12}, ed)
+        for i in range(0, alen, 16):
+            m.load_aad(aad[i:i + 16])
+        for i in range(0, n, 16):
+            blk = src[i:i + 16]
+            (m.load_plain_text if ed == "enc" else m.load_cipher_text)(blk)
+            assert m.data_out[-1] == want_out[i:i + 16]          # available immediately
+        m.get_tag(want_tag)
+        assert b"".join(m.data_out) == want_out
+        assert m.tag == [want_tag]
+    if ed == "dec":  # forced mismatch path (tb/gcm_model.py:47-51): inverted received tag is appended
+        m = gcm_model.gcm({'data': key.hex(), 'n_bytes': kb}, {'data': iv.hex(), 'n_bytes': 12}, 'dec')
+        m.load_cipher_text(want_ct[:16])
+        wrong = bytes(16)
+        m.get_tag(wrong)
+        assert m.tag == [bytes([0xFF] * 16)]
+
+
+def test_readme_vectors_through_adapter():
+    """The two command lines of README.md:251,257 (802.1AE vectors), via the model surface."""
+    from aesgcm_b200 import gcm_model
+    v = [x for x in _load("kat_vectors.json")["vectors"] if "802.1AE" in x["name"]]
+    assert len(v) == 2
+    for x in v:
+        key, pt, aad = x["key"], bytes.fromhex(x["pt"]), bytes.fromhex(x["aad"])
+        m = gcm_model.gcm({'data': key, 'n_bytes': len(key) // 2}, {'data': x["iv"], 'n_bytes': 12}, 'enc')
+        for i in range(0, len(aad), 16):
+            m.load_aad(aad[i:i + 16])
+        for i in range(0, len(pt), 16):
+            m.load_plain_text(pt[i:i + 16])
+        m.get_tag(bytes.fromhex(x["tag"]))
+        assert b"".join(m.data_out).hex() == x["ct"] and m.tag[0].hex() == x["tag"]
+
+
+# --------------------------------------------------------------- full-size properties
+def test_config2_full_size_stream_properties(engine, oracle, torch_mod):
+    """BASELINE config 2 at full size (AES-256, 2^30 B, 16 B AAD, default_rng(1)): too big for the
+    bit-serial oracle, so: (1) windows of CT vs the oracle's GCTR at the matching counter, (2) the
+    tag vs the sharded combine (8 parts) -- two different decompositions must agree, (3) decrypt
+    round-trips and verifies, a flipped bit is rejected, (4) OpenSSL computes the same tag."""
+    torch = torch_mod
+    rng = np.random.default_rng(1)
+    key, iv, aad = _rb(rng, 32), _rb(rng, 12), _rb(rng, 16)
+    n = 1 << 30
+    engine.set_key(key)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(1)
+    d_pt = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=gen)
+    d_ct = torch.empty_like(d_pt)
+    d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    d_aad = _dev(torch, aad)
+    engine.stream_crypt_device(0, iv, d_aad, d_pt, d_ct, d_tag)
+    torch.cuda.synchronize()
+    rk = oracle.key_expand(key)
+    for off in (0, 16 * 151552 - 32, n // 2 - 48, n - 4096):
+        w = 4096
+        pt_w = d_pt[off:off + w].cpu().numpy().tobytes()
+        assert d_ct[off:off + w].cpu().numpy().tobytes() == oracle.gctr(rk, iv, 2 + off // 16, pt_w), off
+    from aesgcm_b200.parallel import shard_plan
+    parts = torch.zeros((8, 16), dtype=torch.uint8, device="cuda")
+    d_ct2 = torch.empty_like(d_pt)
+    for s in shard_plan(n, 8):
+        sl = slice(s.byte_offset, s.byte_offset + s.n_bytes)
+        engine.stream_part_device(0, iv, s.first_block, d_pt[sl], d_ct2[sl], s.blocks_after, parts[s.rank])
+    d_tag2 = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    engine.stream_finish_device(0, iv, parts, 8, d_aad, n, d_tag2)
+    torch.cuda.synchronize()
+    assert torch.equal(d_ct, d_ct2) and torch.equal(d_tag, d_tag2)
+    del d_ct2
+    d_back = torch.empty_like(d_pt)
+    d_ok = torch.zeros(1, dtype=torch.uint8, device="cuda")
+    engine.stream_crypt_device(1, iv, d_aad, d_ct, d_back, d_tag, d_ok)
+    torch.cuda.synchronize()
+    assert int(d_ok.item()) == 1 and torch.equal(d_back, d_pt)
+    d_ct[n // 3] ^= 0x20
+    engine.stream_crypt_device(1, iv, d_aad, d_ct, d_back, d_tag, d_ok)
+    torch.cuda.synchronize()
+    assert int(d_ok.item()) == 0
+    d_ct[n // 3] ^= 0x20
+    try:
+        from cryptography.hazmat.primitives.ciphers.aead import AESGCM
+    except Exception:
+        return
+    ref = AESGCM(key).encrypt(iv, d_pt.cpu().numpy().tobytes(), aad)
+    assert ref[-16:] == d_tag.cpu().numpy().tobytes()
+    assert ref[:4096] == d_ct[:4096].cpu().numpy().tobytes() and ref[-16 - 4096:-16] == d_ct[-4096:].cpu().numpy().tobytes()
+
+
+def test_config3_full_size_roundtrip(engine, oracle, torch_mod):
+    """BASELINE config 3 at full size: 2^20 x 1500 B at a 1504 B stride, AES-192, shared
+    pre-expanded key.  Sampled messages vs the oracle; full decrypt round trip; ok flags all 1."""
+    torch = torch_mod
+    rng = np.random.default_rng(2)
+    key = _rb(rng, 24)
+    engine.set_key(oracle.key_expand(key))
+    n_msgs, length, stride = 1 << 20, 1500, 1504
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(2)
+    d_pt = torch.randint(0, 256, (n_msgs * stride,), dtype=torch.uint8, device="cuda", generator=gen)
+    d_iv = torch.randint(0, 256, (n_msgs * 12,), dtype=torch.uint8, device="cuda", generator=gen)
+    d_ct = torch.zeros_like(d_pt)
+    d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+    engine.batch_crypt_uniform_device(0, d_iv, None, 0, 0, d_pt, d_ct, length, stride, d_tags, n_msgs=n_msgs)
+    torch.cuda.synchronize()
+    for i in (0, 1, 12345, n_msgs // 2, n_msgs - 1):
+        pt = d_pt[i * stride:i * stride + length].cpu().numpy().tobytes()
+        iv = d_iv[12 * i:12 * i + 12].cpu().numpy().tobytes()
+        want_ct, want_tag = oracle.gcm_crypt(key, iv, b"", pt)
+        assert d_ct[i * stride:i * stride + length].cpu().numpy().tobytes() == want_ct, i
+        assert d_tags[16 * i:16 * i + 16].cpu().numpy().tobytes() == want_tag, i
+    d_back = torch.zeros_like(d_pt)
+    d_ok = torch.zeros(n_msgs, dtype=torch.uint8, device="cuda")
+    engine.batch_crypt_uniform_device(1, d_iv, None, 0, 0, d_ct, d_back, length, stride, d_tags, d_ok, n_msgs=n_msgs)
+    torch.cuda.synchronize()
+    assert int(d_ok.sum().item()) == n_msgs
+    v = d_back.view(n_msgs, stride)[:, :length]
+    assert torch.equal(v, d_pt.view(n_msgs, stride)[:, :length])

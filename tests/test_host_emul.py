@@ -1,0 +1,101 @@
+"""CPU check of the engine's per-thread device code (tests/host_emul.cu runs the
+functions of csrc/gcm_core.cuh on the host) against the oracle: index arithmetic
+of the strided Horner, table multiply, T-table AES, ragged last block."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import u8p, u64p
+
+
+def test_sbox_and_key_expand(emul, oracle):
+    sb = np.zeros(256, np.uint8)
+    emul.emul_sbox(u8p(sb))
+    assert (sb == oracle.sbox_table()).all()
+    rng = np.random.default_rng(11)
+    for kb in (16, 24, 32):
+        for _ in range(8):
+            k = rng.integers(0, 256, kb, dtype=np.uint8)
+            out = np.zeros(240, np.uint8)
+            nr = emul.emul_key_expand(u8p(k), kb, u8p(out))
+            assert out[:16 * (nr + 1)].tobytes() == oracle.key_expand(k.tobytes())
+
+
+def test_gf_multiplies(emul, oracle):
+    rng = np.random.default_rng(12)
+    out = np.zeros(16, np.uint8)
+    cases = [rng.integers(0, 256, (2, 16), dtype=np.uint8) for _ in range(300)]
+    edge = [np.zeros(16, np.uint8), np.full(16, 255, np.uint8), np.array([0x80] + [0] * 15, np.uint8),
+            np.array([0] * 15 + [1], np.uint8)]
+    cases += [np.stack([a, b]) for a in edge for b in edge]
+    for ab in cases:
+        a, b = np.ascontiguousarray(ab[0]), np.ascontiguousarray(ab[1])
+        want = oracle.gfmul(a.tobytes(), b.tobytes())
+        emul.emul_gf_mul(u8p(a), u8p(b), u8p(out))
+        assert out.tobytes() == want
+        emul.emul_gf_mul_table(u8p(a), u8p(b), u8p(out))  # Shoup-table path of the hot loop
+        assert out.tobytes() == want
+
+
+@pytest.mark.parametrize("kb", [16, 24, 32])
+def test_stream_lanes(emul, oracle, kb):
+    rng = np.random.default_rng(13 + kb)
+    for n in (0, 1, 15, 16, 17, 31, 32, 100, 1000, 4096 + 5):
+        for (ncta, nt) in ((1, 1), (1, 4), (3, 8), (2, 32)):
+            for mode in (0, 1, 2):
+                key = rng.integers(0, 256, kb, dtype=np.uint8).tobytes()
+                iv = rng.integers(0, 256, 12, dtype=np.uint8)
+                data = rng.integers(0, 256, max(n, 1), dtype=np.uint8)[:n].copy()
+                rk = np.frombuffer(oracle.key_expand(key), dtype=np.uint8).copy()
+                nr = len(rk) // 16 - 1
+                out = np.zeros(max(n, 1), np.uint8)
+                part = np.zeros(16, np.uint8)
+                inp = data if n else np.zeros(1, np.uint8)
+                ctr0 = int(rng.integers(2, 2 ** 32))  # includes wrap-around of the 32-bit counter
+                rc = emul.emul_stream(u8p(rk), nr, u8p(iv), ctypes.c_uint32(ctr0), u8p(inp), u8p(out), ctypes.c_uint64(n),
+                                      mode, ncta, nt, u8p(part))
+                assert rc == 0
+                h, _ = oracle.h_ej0(rk.tobytes(), iv.tobytes())
+                if mode == 2:
+                    assert part.tobytes() == oracle.ghash_absorb(h, data.tobytes())
+                    continue
+                exp_out = oracle.gctr(rk.tobytes(), iv.tobytes(), ctr0, data.tobytes())
+                assert out[:n].tobytes() == exp_out, (kb, n, ncta, nt, mode)
+                ct = data.tobytes() if mode == 1 else exp_out
+                assert part.tobytes() == oracle.ghash_absorb(h, ct), (kb, n, ncta, nt, mode)
+
+
+@pytest.mark.parametrize("G", [1, 2, 4, 8, 16, 32])
+def test_batch_lanes(emul, oracle, G):
+    rng = np.random.default_rng(17 + G)
+    for kb in (16, 24, 32):
+        for dec in (0, 1):
+            nm = 9
+            lens = rng.integers(0, 200, nm)
+            lens[0], lens[1], lens[2] = 0, 16, 1500
+            alens = rng.integers(0, 70, nm)
+            alens[2], alens[3] = 0, 16
+            in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+            aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.uint64)
+            data = rng.integers(0, 256, int(in_off[-1]) + 1, dtype=np.uint8)
+            aad = rng.integers(0, 256, int(aad_off[-1]) + 1, dtype=np.uint8)
+            ivs = rng.integers(0, 256, 12 * nm, dtype=np.uint8)
+            key = rng.integers(0, 256, kb, dtype=np.uint8)
+            rk = np.frombuffer(oracle.key_expand(key.tobytes()), dtype=np.uint8).copy()
+            nr = len(rk) // 16 - 1
+            eo, et = oracle.gcm_batch(key, kb, True, ivs, aad, aad_off, data[:int(in_off[-1])], in_off, decrypt=bool(dec))
+            out = np.zeros_like(data)
+            tag = np.zeros(16 * nm, np.uint8)
+            ok = np.zeros(nm, np.uint8)
+            if dec:
+                tag[:] = et
+                tag[16 * 3 + 5] ^= 0x10  # corrupt one tag: must be rejected
+            rc = emul.emul_batch(u8p(rk), nr, dec, G, u8p(ivs), u8p(aad), u64p(aad_off), u8p(data), u64p(in_off), u8p(out),
+                                 u8p(tag), u8p(ok), ctypes.c_uint64(nm))
+            assert rc == 0
+            assert (out[:int(in_off[-1])] == eo).all(), (kb, G, dec)
+            if dec:
+                assert list(ok) == [1, 1, 1, 0, 1, 1, 1, 1, 1]
+            else:
+                assert (tag == et).all(), (kb, G)

@@ -1,0 +1,42 @@
+#!/bin/bash
+# One gpurun call: smoke, GPU parity tests, bench, ncu launch list + full capture.
+# Usage (from the repo root on the GPU box): bash tools/gpu_round.sh [tag] [steps...]
+# Every step runs under its own timeout and logs into gpurun_out/<tag>_*.log.
+TAG=${1:-r1}
+shift
+STEPS=${@:-smoke tests bench launches ncu}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/${TAG}_gpu.txt 2>&1
+for s in $STEPS; do
+  echo "=== $s ($(date +%T))"
+  case $s in
+    smoke)
+      timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/${TAG}_smoke.log ;;
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -15 $OUT/${TAG}_tests.log ;;
+    testsall)
+      timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -40 $OUT/${TAG}_tests.log ;;
+    bench)
+      timeout 600 python bench.py --steps 50 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; cat $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err ;;
+    benchref)
+      timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2>&1; echo "benchref rc=$?"; cat $OUT/${TAG}_bench_ref.json ;;
+    variants)
+      timeout 900 python tools/bench_variants.py > $OUT/${TAG}_variants.log 2>&1; echo "variants rc=$?"; cat $OUT/${TAG}_variants.log ;;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+        python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches_run.log 2>&1; echo "launches rc=$?"; tail -3 $OUT/${TAG}_launches_run.log ;;
+    ncu)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream -s 3 -c 2 -f -o $OUT/${TAG}_prof \
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_run.log 2>&1; echo "ncu rc=$?"; tail -3 $OUT/${TAG}_ncu_run.log ;;
+    ncubatch)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch -s 2 -c 2 -f -o $OUT/${TAG}_prof_batch \
+        python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_ncubatch_run.log 2>&1; echo "ncubatch rc=$?"; tail -3 $OUT/${TAG}_ncubatch_run.log ;;
+    sanitize)
+      timeout 900 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_sanitize.log 2>&1; echo "sanitize rc=$?"; tail -8 $OUT/${TAG}_sanitize.log ;;
+    scale2)
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        bench.py --gpus 2 --steps 30 --warmup 5 > $OUT/${TAG}_scale2.json 2> $OUT/${TAG}_scale2.err; echo "scale2 rc=$?"; cat $OUT/${TAG}_scale2.json; tail -5 $OUT/${TAG}_scale2.err ;;
+  esac
+done
+echo "=== done ($(date +%T))"
