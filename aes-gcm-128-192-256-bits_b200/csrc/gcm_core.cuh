@@ -65,8 +65,11 @@ AG_HD void ag_load_block(const uint8_t* p, uint32_t nvalid, uint32_t x[4])
         }
 #endif
     }
+    // ragged / unaligned path; static register indexing (no local-memory array)
     x[0] = x[1] = x[2] = x[3] = 0;
-    for (uint32_t j = 0; j < nvalid; ++j) x[j >> 2] |= (uint32_t)p[j] << (8 * (j & 3));
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j)
+        if (j < nvalid) x[j >> 2] |= (uint32_t)p[j] << (8 * (j & 3));
 }
 
 AG_HD void ag_store_block(uint8_t* p, uint32_t nvalid, const uint32_t x[4])
@@ -85,7 +88,9 @@ AG_HD void ag_store_block(uint8_t* p, uint32_t nvalid, const uint32_t x[4])
         }
 #endif
     }
-    for (uint32_t j = 0; j < nvalid; ++j) p[j] = (uint8_t)(x[j >> 2] >> (8 * (j & 3)));
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j)
+        if (j < nvalid) p[j] = (uint8_t)(x[j >> 2] >> (8 * (j & 3)));
 }
 
 // zero bytes nvalid..15 of a block held as LE words (gcm_ghash.vhd:228-246 mask)
@@ -113,48 +118,44 @@ struct StreamParams {
 };
 
 // Returns Y_g for global lane g of Gt lanes; the caller multiplies by H^(Gt-g).
+// Block indices fit 32 bits (a counter range holds < 2^32 blocks).
 template <int NR, int MODE, class TE, class GH>
-AG_HD gf128 ag_stream_lane(const StreamParams& p, uint64_t g, uint64_t Gt, TE&& te, GH&& gh)
+AG_HD gf128 ag_stream_lane(const StreamParams& p, uint32_t g, uint32_t Gt, TE&& te, GH&& gh)
 {
-    const uint64_t n_blocks = (p.n_bytes + 15) >> 4;
-    const uint64_t rows = (n_blocks + Gt - 1) / Gt;
-    const uint64_t pad = rows * Gt - n_blocks;
+    const uint32_t n_blocks = (uint32_t)((p.n_bytes + 15) >> 4);
+    const uint32_t rows = (uint32_t)(((uint64_t)n_blocks + Gt - 1) / Gt);
+    const uint32_t pad = (uint32_t)((uint64_t)rows * Gt - n_blocks);   // < Gt
     const uint32_t tail = (uint32_t)(p.n_bytes & 15);  // bytes in a short last block, 0 = full
+    const uint32_t last = n_blocks - 1;
 
     AesCtrConst cc;
     if (MODE != AG_MODE_GHASH_ONLY) cc = aes_ctr_precompute(p.rk, p.iv[0], p.iv[1], p.iv[2], te);
 
     gf128 y = gf_zero();
     uint32_t xn[4] = {0, 0, 0, 0};
+    // row 0 may start inside the front padding: i is the block index of this lane
+    // in the current row, valid when `have`.
+    bool have = rows && g >= pad;
+    uint32_t i = g - pad;  // wraps when !have; row 1 then lands on g + Gt - pad
     // software prefetch: row u+1's block is requested before row u is processed
-    {
-        const uint64_t v = g;
-        if (rows && v >= pad) {
-            const uint64_t i = v - pad;
-            const uint32_t nv = (i == n_blocks - 1 && tail) ? tail : 16u;
-            ag_load_block(p.in + 16 * i, nv, xn);
-        }
-    }
-    for (uint64_t u = 0; u < rows; ++u) {
-        const uint64_t v = u * Gt + g;
+    if (have) ag_load_block(p.in + 16 * (uint64_t)i, (i == last && tail) ? tail : 16u, xn);
+    for (uint32_t u = 0; u < rows; ++u) {
         uint32_t x[4] = {xn[0], xn[1], xn[2], xn[3]};
         if (u + 1 < rows) {
-            const uint64_t i1 = v + Gt - pad;  // row >= 1 is never padding
-            const uint32_t nv1 = (i1 == n_blocks - 1 && tail) ? tail : 16u;
-            ag_load_block(p.in + 16 * i1, nv1, xn);
+            const uint32_t i1 = i + Gt;  // rows >= 1 are never padding
+            ag_load_block(p.in + 16 * (uint64_t)i1, (i1 == last && tail) ? tail : 16u, xn);
         }
         if (MODE != AG_MODE_CTR_ONLY && u) y = gf_mul_table(y, gh);
-        if (v >= pad) {
-            const uint64_t i = v - pad;
-            const uint32_t nv = (i == n_blocks - 1 && tail) ? tail : 16u;
+        if (have) {
+            const uint32_t nv = (i == last && tail) ? tail : 16u;
             uint32_t s[4];
             if (MODE == AG_MODE_GHASH_ONLY) {
                 s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = x[3];
             } else {
                 uint32_t ks[4];
-                aes_ctr_block<NR>(p.rk, cc, p.ctr0 + (uint32_t)i, te, ks);
+                aes_ctr_block<NR>(p.rk, cc, p.ctr0 + i, te, ks);
                 uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
-                ag_store_block(p.out + 16 * i, nv, o);
+                ag_store_block(p.out + 16 * (uint64_t)i, nv, o);
                 if (MODE == AG_MODE_ENC) {
                     if (nv != 16) ag_mask_block(o, nv);
                     s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
@@ -169,6 +170,8 @@ AG_HD gf128 ag_stream_lane(const StreamParams& p, uint64_t g, uint64_t Gt, TE&& 
                 y.w[3] ^= ag_bswap32(s[3]);
             }
         }
+        have = true;
+        i += Gt;
     }
     return y;
 }

@@ -18,6 +18,16 @@
 #define AG_HD inline
 #endif
 
+// Keeps at most 8 of the 16 row lookups of one table product in flight (32
+// registers), so the 64-register budget of the 1024-thread CTA is not blown by
+// the compiler hoisting all sixteen 128-bit loads: a compiler-level memory fence
+// after the second group of four.
+#if defined(__CUDA_ARCH__)
+#define AG_LOOKUP_FENCE(r) do { if ((r) == 1) asm volatile("" ::: "memory"); } while (0)
+#else
+#define AG_LOOKUP_FENCE(r) do { } while (0)
+#endif
+
 struct gf128 {
     uint32_t w[4];
 };
@@ -151,6 +161,7 @@ AG_HD gf128 gf_mul_table(const gf128& x, LOOKUP&& lookup)
             for (int m = 1; m < 7; ++m) z[m] ^= ag_funnel_r(a[m], a[m - 1], 8 * r);
             z[7] ^= a[6] << (32 - 8 * r);
         }
+        AG_LOOKUP_FENCE(r);
     }
     // fold bytes 16..30 (degrees 128..247); the last byte of z[7] is always zero,
     // so the shifts by 1, 2 and 7 bits lose nothing.

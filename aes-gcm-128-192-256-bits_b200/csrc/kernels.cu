@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_con
 
     TeSmem te{ag_smem, lane * 4};
     GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
-    const uint64_t Gt = (uint64_t)gridDim.x * nt;
-    const uint64_t g = (uint64_t)blockIdx.x * nt + tid;
+    const uint32_t Gt = gridDim.x * nt;
+    const uint32_t g = blockIdx.x * nt + tid;
     gf128 y = ag_stream_lane<NR, MODE>(p, g, Gt, te, gh);
     if (MODE == AG_MODE_CTR_ONLY) return;
 

@@ -82,13 +82,13 @@ const Tables& tables()
 template <int NR>
 void stream_nr(const StreamParams& p, int mode, uint64_t ncta, uint64_t nt, const gf128& H, gf128& total)
 {
-    const uint64_t Gt = ncta * nt;
+    const uint32_t Gt = (uint32_t)(ncta * nt);
     std::vector<uint4> tab;
     build_table(gf_pow(H, Gt), tab);
     TeHost te{tables().te0};
     GhHost gh{tab.data()};
     total = gf_zero();
-    for (uint64_t g = 0; g < Gt; ++g) {
+    for (uint32_t g = 0; g < Gt; ++g) {
         gf128 y;
         switch (mode) {
             case AG_MODE_ENC: y = ag_stream_lane<NR, AG_MODE_ENC>(p, g, Gt, te, gh); break;
