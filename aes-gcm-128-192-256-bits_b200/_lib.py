@@ -45,6 +45,10 @@ SIGNATURES = {
                                  c_sz, c_vp]),
     "agcm_batch_crypt_uniform": (c_int, [c_vp, c_int, c_int, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u8p, c_u64, c_u64,
                                          c_u8p, c_u8p, c_sz, c_vp]),
+    "agcm_batch_crypt_perkey": (c_int, [c_vp, c_int, c_int, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
+                                        c_sz, c_vp]),
+    "agcm_batch_crypt_perkey_uniform": (c_int, [c_vp, c_int, c_int, c_u8p, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u8p,
+                                                c_u64, c_u64, c_u8p, c_u8p, c_sz, c_vp]),
     "agcm_stream_crypt_host": (c_int, [c_vp, c_int, c_u8p, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u8p,
                                        ctypes.POINTER(c_int)]),
     "agcm_stream_part_host": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p]),

@@ -538,6 +538,67 @@ int agcm_batch_crypt_uniform(agcm_ctx* c, int decrypt, int lanes, const uint8_t*
     return batch_common(c, decrypt, lanes, len, p, n_msgs, stream);
 }
 
+static int perkey_common(agcm_ctx* c, int mode, int decrypt, BatchParams& p, size_t n_msgs, void* stream)
+{
+    const int nr = mode_to_nr(mode);
+    if (!nr) return AGCM_E_BAD_MODE;
+    if (n_msgs == 0) return AGCM_OK;
+    if (!p.keys || !p.iv || !p.tag || (decrypt && !p.ok)) return AGCM_E_BAD_ARG;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    p.key = nullptr;
+    p.te0 = c->d_te0;
+    p.n_msgs = n_msgs;
+    AG_CUDA(c, ag_launch_batch_perkey(p, nr, decrypt, c->ncta, (cudaStream_t)stream));
+    c->launches++;
+    return AGCM_OK;
+}
+
+int agcm_batch_crypt_perkey(agcm_ctx* c, int mode, int decrypt, const uint8_t* d_keys, const uint8_t* d_iv12,
+                            const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
+                            uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
+{
+    if (!c) return AGCM_E_BAD_ARG;
+    if (n_msgs && (!d_in_off || !d_in || !d_out)) return AGCM_E_BAD_ARG;
+    if ((d_aad == nullptr) != (d_aad_off == nullptr)) return AGCM_E_BAD_ARG;
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.keys = d_keys;
+    p.iv = d_iv12;
+    p.aad = d_aad;
+    p.aad_off = d_aad_off;
+    p.in = d_in;
+    p.in_off = d_in_off;
+    p.out = d_out;
+    p.tag = d_tag;
+    p.ok = d_ok;
+    return perkey_common(c, mode, decrypt, p, n_msgs, stream);
+}
+
+int agcm_batch_crypt_perkey_uniform(agcm_ctx* c, int mode, int decrypt, const uint8_t* d_keys, const uint8_t* d_iv12,
+                                    const uint8_t* d_aad, uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in,
+                                    uint8_t* d_out, uint64_t len, uint64_t stride, uint8_t* d_tag, uint8_t* d_ok,
+                                    size_t n_msgs, void* stream)
+{
+    if (!c) return AGCM_E_BAD_ARG;
+    if (n_msgs && len && (!d_in || !d_out)) return AGCM_E_BAD_ARG;
+    if (stride < len || (aad_len && (!d_aad || aad_stride < aad_len))) return AGCM_E_BAD_LEN;
+    if (((len + 15) >> 4) > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.keys = d_keys;
+    p.iv = d_iv12;
+    p.aad = aad_len ? d_aad : nullptr;
+    p.in = d_in;
+    p.out = d_out;
+    p.tag = d_tag;
+    p.ok = d_ok;
+    p.len = len;
+    p.stride = stride;
+    p.aad_len = aad_len;
+    p.aad_stride = aad_stride;
+    return perkey_common(c, mode, decrypt, p, n_msgs, stream);
+}
+
 // ---------------------------------------------------------------------------
 // host-buffer entry points
 // ---------------------------------------------------------------------------

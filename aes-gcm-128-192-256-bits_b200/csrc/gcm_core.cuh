@@ -181,6 +181,7 @@ struct BatchParams {
     uint32_t rk[60];
     const KeyDev* key;
     const uint32_t* te0;
+    const uint8_t* keys;       // per-message raw keys (n_msgs x key_bytes) for k_batch_perkey, else null
     const uint8_t* iv;         // n_msgs x 12
     const uint8_t* aad;        // may be null when there is no AAD
     const uint64_t* aad_off;   // n_msgs+1 offsets, or null => uniform (aad_stride, aad_len)

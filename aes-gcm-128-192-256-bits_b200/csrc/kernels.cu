@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "gcm_core.cuh"
+#include "perkey_core.cuh"
 #include "kernels.h"
 
 namespace {
@@ -416,6 +417,146 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
         }
         __syncwarp();
     }
+}
+
+// ===========================================================================
+// Batched messages, one DISTINCT key per message (BASELINE config 4): one thread
+// per message, key schedule on the fly (aes_kexp expand variant), private 4-bit
+// GHASH table.  512 threads (128 registers each); shared memory: Te0|Te1 (64 KB,
+// Te2/Te3 by a 16-bit rotate) + 512 x 256 B private tables.
+// ===========================================================================
+namespace {
+
+constexpr uint32_t PK_NT = 512;
+constexpr uint32_t PK_GH4 = 65536;          // + up to 2 KB alignment pad
+constexpr uint32_t PK_SMEM = PK_GH4 + 2048 + PK_NT * 256;
+
+struct TeSmem2 {
+    const uint8_t* base;
+    uint32_t lane4;
+    __device__ __forceinline__ uint32_t operator()(int tab, uint32_t w, int k) const
+    {
+        const uint32_t off = __byte_perm(w, lane4, 0x5504 | (k << 4));
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(base + off + (tab & 1) * 128);
+        return (tab & 2) ? __byte_perm(v, 0, 0x1032) : v;
+    }
+};
+
+// SubWord through byte 1 of the lane-private Te0 rows (Te0 = {2S, S, S, 3S})
+struct SubWordSmem {
+    const uint8_t* base;
+    uint32_t lane4;
+    __device__ __forceinline__ uint32_t operator()(uint32_t w) const
+    {
+        const uint32_t b0 = *(base + __byte_perm(w, lane4, 0x5504) + 1);
+        const uint32_t b1 = *(base + __byte_perm(w, lane4, 0x5514) + 1);
+        const uint32_t b2 = *(base + __byte_perm(w, lane4, 0x5524) + 1);
+        const uint32_t b3 = *(base + __byte_perm(w, lane4, 0x5534) + 1);
+        return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    }
+};
+
+// thread-private column: row n at base + n*128 (8 threads interleave 16 B slots in a
+// 128 B row, so the 8 lanes of a quarter-warp never share a bank group)
+struct Rows4Smem {
+    uint32_t base;  // 32-bit shared address, bits 7..10 clear
+    __device__ __forceinline__ void put(int n, uint4 r) const
+    {
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(base + n * 128), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w)
+                     : "memory");
+    }
+    __device__ __forceinline__ uint4 get(uint32_t w, int k) const
+    {
+        const uint32_t n7 = (4 * k >= 7) ? (w >> (4 * k - 7)) : (w << (7 - 4 * k));
+        const uint32_t addr = (n7 & 0x780u) | base;
+        uint4 r;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+        return r;
+    }
+};
+
+__device__ __forceinline__ void load_words(const uint8_t* p, int n_words, uint32_t* w)
+{
+    if (((uintptr_t)p & 3) == 0) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < n_words) w[i] = q[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < n_words)
+                w[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) |
+                       ((uint32_t)p[4 * i + 3] << 24);
+    }
+}
+
+}  // namespace
+
+template <int NK, bool DEC>
+__global__ void __launch_bounds__(PK_NT, 1) k_batch_perkey(const __grid_constant__ BatchParams p)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    // Te0 | Te1 only
+    for (uint32_t idx = tid; idx < 256 * 32; idx += blockDim.x) {
+        const uint32_t x = idx >> 5, l = idx & 31;
+        const uint32_t t = __ldg(p.te0 + x);
+        uint32_t* a = reinterpret_cast<uint32_t*>(ag_smem + SM_AES_A + x * 256 + l * 4);
+        a[0] = t;
+        a[32] = ag_rotl32(t, 8);
+    }
+    __syncthreads();
+    TeSmem2 te{ag_smem, lane * 4};
+    SubWordSmem sb{ag_smem, lane * 4};
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(ag_smem) + PK_GH4;
+    const uint32_t s_al = (s0 + 2047u) & ~2047u;
+    Rows4Smem rows{s_al + (tid >> 3) * 2048u + (tid & 7) * 16u};
+
+    for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + tid; m < p.n_msgs; m += (uint64_t)gridDim.x * blockDim.x) {
+        const MsgDesc d = ag_batch_msg(p, m);
+        uint32_t key[8], iv[3];
+        load_words(p.keys + m * (uint64_t)(4 * NK), NK, key);
+        load_words(p.iv + 12 * m, 3, iv);
+        uint32_t tg[4];
+        ag_perkey_message<NK, DEC>(key, iv[0], iv[1], iv[2], d, te, sb, rows, tg);
+        uint8_t* tp = p.tag + 16 * m;
+        if (DEC) {
+            uint32_t x[4];
+            ag_load_block(tp, 16, x);
+            const uint32_t diff = (x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3]);
+            p.ok[m] = diff ? 0 : 1;
+        } else {
+            ag_store_block(tp, 16, tg);
+        }
+    }
+}
+
+template <int NK>
+static cudaError_t launch_perkey_t(const BatchParams& p, int decrypt, int ncta, cudaStream_t st)
+{
+    cudaError_t e;
+    if (decrypt) {
+        e = cudaFuncSetAttribute(k_batch_perkey<NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
+        if (e != cudaSuccess) return e;
+        k_batch_perkey<NK, true><<<ncta, PK_NT, PK_SMEM, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(k_batch_perkey<NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
+        if (e != cudaSuccess) return e;
+        k_batch_perkey<NK, false><<<ncta, PK_NT, PK_SMEM, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_batch_perkey(const BatchParams& p, int nr, int decrypt, int max_cta, cudaStream_t st)
+{
+    const uint64_t need = (p.n_msgs + PK_NT - 1) / PK_NT;
+    const int ncta = (int)(need < (uint64_t)max_cta ? need : (uint64_t)max_cta);
+    switch (nr) {
+        case 10: return launch_perkey_t<4>(p, decrypt, ncta, st);
+        case 12: return launch_perkey_t<6>(p, decrypt, ncta, st);
+        case 14: return launch_perkey_t<8>(p, decrypt, ncta, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 // ===========================================================================

@@ -1,0 +1,188 @@
+// One message per thread with its OWN key (BASELINE config 4): the key schedule is
+// generated on the fly, one stage per round, exactly like the reference's expand
+// variant of aes_kexp (config/config_aes_kexp.py:113-159,191-225 streams one
+// 128-bit stage per round; word recurrence of tb/key_exp.py:98-112) -- a thread
+// cannot hold 60 stage words next to the AES state, and 2^20 distinct schedules
+// would not fit shared memory.  GHASH uses a thread-private 4-bit Shoup table of
+// H (16 rows of 16 B in the thread's own shared-memory column) and the serial
+// recurrence Y <- (Y xor X)*H of src/gcm_ghash.vhd:269-272 -- with one message
+// per thread the recurrence IS the parallel form: 2^20 independent chains.
+//
+// Host+device, exercised on the CPU by tests/host_emul.cu.
+#pragma once
+#include "gcm_core.cuh"
+
+// ---- on-the-fly key schedule ------------------------------------------------
+// Emits stage words in order; all indices are compile-time after unrolling.
+// SB: functor uint32_t(uint32_t word) -> SubWord(word) (S-box on each byte).
+template <int NK>
+struct RkStream {
+    uint32_t w[NK];   // sliding window: w[i % NK] = word i-NK .. i-1
+    uint32_t rcon;
+
+    AG_HD void init(const uint32_t* key)
+    {
+#pragma unroll
+        for (int i = 0; i < NK; ++i) w[i] = key[i];
+        rcon = 1;
+    }
+
+    // word i of the expanded key; must be called for i = 0, 1, 2, ... in order
+    template <class SB>
+    AG_HD uint32_t word(int i, SB&& sb)
+    {
+        if (i < NK) return w[i];
+        uint32_t t = w[(i - 1) % NK];
+        if (i % NK == 0) {
+            t = sb((t >> 8) | (t << 24));  // SubWord(RotWord)
+            t ^= rcon;
+            rcon = (rcon << 1) ^ ((rcon & 0x80) ? 0x11Bu : 0u);
+        } else if (NK == 8 && (i % 8) == 4) {
+            t = sb(t);
+        }
+        w[i % NK] ^= t;
+        return w[i % NK];
+    }
+};
+
+// One block with the schedule generated alongside the rounds (NR = NK + 6).
+template <int NK, class TE, class SB>
+AG_HD void aes_encrypt_otf(const uint32_t* key, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, TE&& te, SB&& sb,
+                           uint32_t out[4])
+{
+    constexpr int NR = NK + 6;
+    RkStream<NK> ks;
+    ks.init(key);
+    s0 ^= ks.word(0, sb);
+    s1 ^= ks.word(1, sb);
+    s2 ^= ks.word(2, sb);
+    s3 ^= ks.word(3, sb);
+#pragma unroll
+    for (int r = 1; r < NR; ++r) {
+        const uint32_t k0 = ks.word(4 * r + 0, sb), k1 = ks.word(4 * r + 1, sb), k2 = ks.word(4 * r + 2, sb),
+                       k3 = ks.word(4 * r + 3, sb);
+        const uint32_t t0 = te(0, s0, 0) ^ te(1, s1, 1) ^ te(2, s2, 2) ^ te(3, s3, 3) ^ k0;
+        const uint32_t t1 = te(0, s1, 0) ^ te(1, s2, 1) ^ te(2, s3, 2) ^ te(3, s0, 3) ^ k1;
+        const uint32_t t2 = te(0, s2, 0) ^ te(1, s3, 1) ^ te(2, s0, 2) ^ te(3, s1, 3) ^ k2;
+        const uint32_t t3 = te(0, s3, 0) ^ te(1, s0, 1) ^ te(2, s1, 2) ^ te(3, s2, 3) ^ k3;
+        s0 = t0;
+        s1 = t1;
+        s2 = t2;
+        s3 = t3;
+    }
+    const uint32_t k0 = ks.word(4 * NR + 0, sb), k1 = ks.word(4 * NR + 1, sb), k2 = ks.word(4 * NR + 2, sb),
+                   k3 = ks.word(4 * NR + 3, sb);
+    out[0] = (te(2, s0, 0) & 0x000000ffu) ^ (te(3, s1, 1) & 0x0000ff00u) ^ (te(0, s2, 2) & 0x00ff0000u) ^
+             (te(1, s3, 3) & 0xff000000u) ^ k0;
+    out[1] = (te(2, s1, 0) & 0x000000ffu) ^ (te(3, s2, 1) & 0x0000ff00u) ^ (te(0, s3, 2) & 0x00ff0000u) ^
+             (te(1, s0, 3) & 0xff000000u) ^ k1;
+    out[2] = (te(2, s2, 0) & 0x000000ffu) ^ (te(3, s3, 1) & 0x0000ff00u) ^ (te(0, s0, 2) & 0x00ff0000u) ^
+             (te(1, s1, 3) & 0xff000000u) ^ k2;
+    out[3] = (te(2, s3, 0) & 0x000000ffu) ^ (te(3, s0, 1) & 0x0000ff00u) ^ (te(0, s1, 2) & 0x00ff0000u) ^
+             (te(1, s2, 3) & 0xff000000u) ^ k3;
+}
+
+// ---- thread-private 4-bit Shoup table ------------------------------------------
+// T[n] = n*H for the 4-bit polynomial n (bit 3 of n = x^0).  ROWS: object with
+//   void put(int n, uint4 row);   uint4 get(uint32_t be_word, int nibble /*0 = low*/);
+template <class ROWS>
+AG_HD void gf_build_table4(const gf128& h, ROWS&& rows)
+{
+    gf128 b[4];
+    b[0] = h;  // n = 8
+    b[1] = gf_mulx(b[0]);  // n = 4
+    b[2] = gf_mulx(b[1]);  // n = 2
+    b[3] = gf_mulx(b[2]);  // n = 1
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+        uint4 r = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (n & (8 >> k)) {
+                r.x ^= b[k].w[0];
+                r.y ^= b[k].w[1];
+                r.z ^= b[k].w[2];
+                r.w ^= b[k].w[3];
+            }
+        rows.put(n, r);
+    }
+}
+
+// X*H by Horner over the 32 nibbles of X, last nibble first:
+//   Z <- Z*x^4 xor T[n_j];   Z*x^4 = (Z >> 4) xor R[dropped nibble],
+//   R[d] = d (x) (x^128 mod P) = (d<<28) ^ (d<<27) ^ (d<<26) ^ (d<<21) in word 0.
+template <class ROWS>
+AG_HD gf128 gf_mul_table4(const gf128& x, ROWS&& rows)
+{
+    uint32_t z0 = 0, z1 = 0, z2 = 0, z3 = 0;
+#pragma unroll
+    for (int q = 3; q >= 0; --q) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // nibble k of BE word q, k = 0 is the last (highest-degree) nibble
+            if (!(q == 3 && k == 0)) {
+                const uint32_t d = z3 & 0xfu;
+                z3 = ag_funnel_r(z3, z2, 4);
+                z2 = ag_funnel_r(z2, z1, 4);
+                z1 = ag_funnel_r(z1, z0, 4);
+                z0 = (z0 >> 4) ^ (d * ((1u << 28) | (1u << 21))) ^ (d << 27) ^ (d << 26);
+            }
+            const uint4 t = rows.get(x.w[q], k);
+            z0 ^= t.x;
+            z1 ^= t.y;
+            z2 ^= t.z;
+            z3 ^= t.w;
+        }
+    }
+    gf128 o;
+    o.w[0] = z0; o.w[1] = z1; o.w[2] = z2; o.w[3] = z3;
+    return o;
+}
+
+// ---- one whole message ------------------------------------------------------------
+// key: NK little-endian words of the raw key.  Returns the computed tag words (LE) and
+// writes the payload.  Unified order AAD | CT | length block (gcm_ghash.vhd:259-272,257).
+template <int NK, bool DEC, class TE, class SB, class ROWS>
+AG_HD void ag_perkey_message(const uint32_t* key, uint32_t iv0, uint32_t iv1, uint32_t iv2, const MsgDesc& d, TE&& te,
+                             SB&& sb, ROWS&& rows, uint32_t tag[4])
+{
+    uint32_t e[4];
+    aes_encrypt_otf<NK>(key, 0, 0, 0, 0, te, sb, e);  // H = E_K(0^128)  (gcm_gctr.vhd:141-144)
+    gf_build_table4(gf_from_le_words(e[0], e[1], e[2], e[3]), rows);
+    aes_encrypt_otf<NK>(key, iv0, iv1, iv2, 0x01000000u, te, sb, e);  // E_K(J0), J0 = IV || 00000001
+
+    gf128 y = gf_zero();
+    const uint64_t a = (d.aad_len + 15) >> 4, n = (d.len + 15) >> 4;
+    for (uint64_t i = 0; i < a; ++i) {
+        const uint64_t left = d.aad_len - 16 * i;
+        uint32_t s[4];
+        ag_load_block(d.aad + 16 * i, left < 16 ? (uint32_t)left : 16u, s);
+        y = gf_xor(y, gf_from_le_words(s[0], s[1], s[2], s[3]));
+        y = gf_mul_table4(y, rows);
+    }
+    for (uint64_t j = 0; j < n; ++j) {
+        const uint64_t left = d.len - 16 * j;
+        const uint32_t nv = left < 16 ? (uint32_t)left : 16u;
+        uint32_t x[4], ks[4];
+        ag_load_block(d.in + 16 * j, nv, x);
+        aes_encrypt_otf<NK>(key, iv0, iv1, iv2, ag_bswap32(2u + (uint32_t)j), te, sb, ks);
+        uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
+        ag_store_block(d.out + 16 * j, nv, o);
+        if (DEC) {
+            y = gf_xor(y, gf_from_le_words(x[0], x[1], x[2], x[3]));
+        } else {
+            if (nv != 16) ag_mask_block(o, nv);
+            y = gf_xor(y, gf_from_le_words(o[0], o[1], o[2], o[3]));
+        }
+        y = gf_mul_table4(y, rows);
+    }
+    const uint64_t ab = d.aad_len * 8, cb = d.len * 8;
+    y.w[0] ^= (uint32_t)(ab >> 32);
+    y.w[1] ^= (uint32_t)ab;
+    y.w[2] ^= (uint32_t)(cb >> 32);
+    y.w[3] ^= (uint32_t)cb;
+    y = gf_mul_table4(y, rows);
+    tag[0] = ag_bswap32(y.w[0]) ^ e[0];
+    tag[1] = ag_bswap32(y.w[1]) ^ e[1];
+    tag[2] = ag_bswap32(y.w[2]) ^ e[2];
+    tag[3] = ag_bswap32(y.w[3]) ^ e[3];
+}

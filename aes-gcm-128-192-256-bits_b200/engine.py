@@ -256,6 +256,22 @@ class GcmEngine:
                                                   int(aad_len), int(aad_stride), _dptr(data_in), _dptr(data_out),
                                                   int(length), int(stride), _dptr(tags), _dptr(ok), n, _stream(stream)))
 
+    def batch_crypt_perkey_device(self, mode, decrypt, keys, ivs, aad, aad_off, data_in, in_off, data_out, tags, ok=None,
+                                  stream=None):
+        """One distinct raw key per message (keys: CUDA uint8 [n, mode/8]); BASELINE config 4."""
+        n = in_off.numel() - 1
+        self._ck(self._L.agcm_batch_crypt_perkey(self._ctx, int(mode), int(decrypt), _dptr(keys), _dptr(ivs), _dptr(aad),
+                                                 _dptr(aad_off), _dptr(data_in), _dptr(in_off), _dptr(data_out),
+                                                 _dptr(tags), _dptr(ok), n, _stream(stream)))
+
+    def batch_crypt_perkey_uniform_device(self, mode, decrypt, keys, ivs, aad, aad_len, aad_stride, data_in, data_out,
+                                          length, stride, tags, ok=None, n_msgs=None, stream=None):
+        n = ivs.numel() // 12 if n_msgs is None else int(n_msgs)
+        self._ck(self._L.agcm_batch_crypt_perkey_uniform(self._ctx, int(mode), int(decrypt), _dptr(keys), _dptr(ivs),
+                                                         _dptr(aad), int(aad_len), int(aad_stride), _dptr(data_in),
+                                                         _dptr(data_out), int(length), int(stride), _dptr(tags),
+                                                         _dptr(ok), n, _stream(stream)))
+
 
 def _stream(stream):
     if stream is None:

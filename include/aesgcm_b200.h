@@ -126,6 +126,20 @@ int agcm_batch_crypt_uniform(agcm_ctx* ctx, int decrypt, int lanes, const uint8_
                              uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out, uint64_t len,
                              uint64_t stride, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);
 
+/* ---- many independent messages, one DISTINCT key per message ----------------------
+ * BASELINE config 4.  d_keys holds n_msgs raw keys of mode/8 bytes; each thread runs
+ * the aes_kexp schedule on the fly, one stage per round (config/config_aes_kexp.py:
+ * 113-159), derives its own H and E_K(J0), and absorbs GHASH with the serial
+ * recurrence of src/gcm_ghash.vhd:269-272.  Does not use or change the context key.
+ * Other arguments as agcm_batch_crypt / agcm_batch_crypt_uniform. */
+int agcm_batch_crypt_perkey(agcm_ctx* ctx, int mode, int decrypt, const uint8_t* d_keys, const uint8_t* d_iv12,
+                            const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
+                            uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);
+int agcm_batch_crypt_perkey_uniform(agcm_ctx* ctx, int mode, int decrypt, const uint8_t* d_keys, const uint8_t* d_iv12,
+                                    const uint8_t* d_aad, uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in,
+                                    uint8_t* d_out, uint64_t len, uint64_t stride, uint8_t* d_tag, uint8_t* d_ok,
+                                    size_t n_msgs, void* stream);
+
 /* ---- host-buffer entry points (the call a reference-side user makes) ---------
  * Inputs and outputs live in HOST memory; the library stages them through HBM
  * in chunks, overlapping H2D, kernel and D2H on its own streams.  Pinned host

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../aes-gcm-128-192-256-bits_b200/csrc/gcm_core.cuh"
+#include "../aes-gcm-128-192-256-bits_b200/csrc/perkey_core.cuh"
 
 namespace {
 
@@ -28,6 +29,21 @@ struct TeHost {
 struct GhHost {
     const uint4* tab;
     __host__ __device__ uint4 operator()(uint32_t w, int k) const { return tab[(w >> (8 * k)) & 0xff]; }
+};
+
+struct SubWordHost {
+    const uint8_t* sbox;
+    __host__ __device__ uint32_t operator()(uint32_t w) const
+    {
+        return (uint32_t)sbox[w & 0xff] | ((uint32_t)sbox[(w >> 8) & 0xff] << 8) | ((uint32_t)sbox[(w >> 16) & 0xff] << 16) |
+               ((uint32_t)sbox[w >> 24] << 24);
+    }
+};
+
+struct Rows4Host {
+    uint4 r[16];
+    __host__ __device__ void put(int n, uint4 v) { r[n] = v; }
+    __host__ __device__ uint4 get(uint32_t w, int k) const { return r[(w >> (4 * k)) & 0xf]; }
 };
 
 gf128 gf_from_bytes(const uint8_t b[16])
@@ -139,9 +155,61 @@ void batch_nr(const BatchParams& p, uint32_t G, const gf128& H)
     }
 }
 
+template <int NK, bool DEC>
+void perkey_nk(const BatchParams& p)
+{
+    TeHost te{tables().te0};
+    SubWordHost sb{tables().sbox};
+    for (uint64_t m = 0; m < p.n_msgs; ++m) {
+        const MsgDesc d = ag_batch_msg(p, m);
+        uint32_t key[8] = {0}, iv[3] = {0, 0, 0};
+        const uint8_t* kp = p.keys + m * (uint64_t)(4 * NK);
+        for (int j = 0; j < 4 * NK; ++j) key[j >> 2] |= (uint32_t)kp[j] << (8 * (j & 3));
+        const uint8_t* ivp = p.iv + 12 * m;
+        for (int j = 0; j < 12; ++j) iv[j >> 2] |= (uint32_t)ivp[j] << (8 * (j & 3));
+        Rows4Host rows;
+        uint32_t tg[4];
+        ag_perkey_message<NK, DEC>(key, iv[0], iv[1], iv[2], d, te, sb, rows, tg);
+        uint8_t* tp = p.tag + 16 * m;
+        if (DEC) {
+            uint32_t x[4];
+            ag_load_block(tp, 16, x);
+            p.ok[m] = ((x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3])) ? 0 : 1;
+        } else {
+            ag_store_block(tp, 16, tg);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int emul_batch_perkey(const uint8_t* keys, int key_bytes, int decrypt, const uint8_t* iv, const uint8_t* aad,
+                      const uint64_t* aad_off, const uint8_t* in, const uint64_t* in_off, uint8_t* out, uint8_t* tag,
+                      uint8_t* ok, uint64_t n_msgs)
+{
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.keys = keys;
+    p.iv = iv;
+    p.aad = aad;
+    p.aad_off = aad_off;
+    p.in = in;
+    p.in_off = in_off;
+    p.out = out;
+    p.tag = tag;
+    p.ok = ok;
+    p.n_msgs = n_msgs;
+    switch (key_bytes) {
+        case 16: decrypt ? perkey_nk<4, true>(p) : perkey_nk<4, false>(p); break;
+        case 24: decrypt ? perkey_nk<6, true>(p) : perkey_nk<6, false>(p); break;
+        case 32: decrypt ? perkey_nk<8, true>(p) : perkey_nk<8, false>(p); break;
+        default: return -1;
+    }
+    return 0;
+}
+
 
 // rk_bytes: (nr+1)*16 expanded key bytes.  Returns the un-finished GHASH partial
 // sum_i C_i H^(n-i) (natural byte order) and writes `out`.

@@ -279,6 +279,101 @@ def test_batch_host_api_roundtrip(engine, oracle):
     assert ok.sum() == n_msgs - 1 and ok[5] == 0
 
 
+def test_config4_perkey_decrypt_verify(engine, oracle, torch_mod):
+    """BASELINE config 4 semantics at reduced count: AES-256 decrypt+verify, a DISTINCT key per
+    message expanded on the device, 64 B AAD, payload swept over {64, 256, 1500, 4096} B, some tags
+    corrupted; plus the other key sizes and ragged offsets; encrypt leg vs the oracle."""
+    torch = torch_mod
+    rng = np.random.default_rng(3)
+    for kb, length, alen, n_msgs in ((32, 1500, 64, 3000), (32, 64, 64, 2000), (32, 256, 64, 2000), (32, 4096, 64, 600),
+                                     (16, 1500, 0, 1500), (24, 333, 20, 1500)):
+        keys = rng.integers(0, 256, kb * n_msgs, dtype=np.uint8)
+        ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+        pt = rng.integers(0, 256, n_msgs * length, dtype=np.uint8)
+        aad = rng.integers(0, 256, max(1, n_msgs * alen), dtype=np.uint8)
+        in_off = np.arange(n_msgs + 1, dtype=np.uint64) * length
+        aad_off = np.arange(n_msgs + 1, dtype=np.uint64) * alen
+        want_ct, want_tags = oracle.gcm_batch(keys, kb, False, ivs, aad, aad_off, pt, in_off, threads=8)
+        d_keys, d_ivs, d_pt = _dev(torch, keys), _dev(torch, ivs), _dev(torch, pt)
+        d_aad = _dev(torch, aad) if alen else None
+        d_ct = torch.zeros_like(d_pt)
+        d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_perkey_uniform_device(kb * 8, 0, d_keys, d_ivs, d_aad, alen, alen, d_pt, d_ct, length, length,
+                                                 d_tags, n_msgs=n_msgs)
+        torch.cuda.synchronize()
+        assert (d_ct.cpu().numpy() == want_ct).all(), (kb, length)
+        assert (d_tags.cpu().numpy() == want_tags).all(), (kb, length)
+        bad = rng.choice(n_msgs, max(1, n_msgs // 1000 + 2), replace=False)
+        tags_in = want_tags.copy().reshape(n_msgs, 16)
+        tags_in[bad, 3] ^= 0x40
+        d_back = torch.zeros_like(d_pt)
+        d_ok = torch.full((n_msgs,), 9, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_perkey_uniform_device(kb * 8, 1, d_keys, d_ivs, d_aad, alen, alen, d_ct, d_back, length, length,
+                                                 _dev(torch, tags_in.reshape(-1)), d_ok, n_msgs=n_msgs)
+        torch.cuda.synchronize()
+        assert (d_back.cpu().numpy() == pt).all()
+        expect = np.ones(n_msgs, np.uint8)
+        expect[bad] = 0
+        assert (d_ok.cpu().numpy() == expect).all()
+    # ragged offsets
+    n_msgs = 500
+    lens = rng.integers(0, 300, n_msgs)
+    alens = rng.integers(0, 70, n_msgs)
+    in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.uint64)
+    keys = rng.integers(0, 256, 32 * n_msgs, dtype=np.uint8)
+    ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+    pt = rng.integers(0, 256, int(in_off[-1]), dtype=np.uint8)
+    aad = rng.integers(0, 256, int(aad_off[-1]), dtype=np.uint8)
+    want_ct, want_tags = oracle.gcm_batch(keys, 32, False, ivs, aad, aad_off, pt, in_off, threads=8)
+    d_ct = torch.zeros(pt.size, dtype=torch.uint8, device="cuda")
+    d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+    engine.batch_crypt_perkey_device(256, 0, _dev(torch, keys), _dev(torch, ivs), _dev(torch, aad),
+                                     torch.from_numpy(aad_off.view(np.int64)).cuda(), _dev(torch, pt),
+                                     torch.from_numpy(in_off.view(np.int64)).cuda(), d_ct, d_tags)
+    torch.cuda.synchronize()
+    assert (d_ct.cpu().numpy() == want_ct).all() and (d_tags.cpu().numpy() == want_tags).all()
+
+
+def test_config4_full_size_roundtrip(engine, oracle, torch_mod):
+    """BASELINE config 4 at full size: 2^20 messages x 1500 B, distinct AES-256 key each, 64 B AAD.
+    Inputs for the decrypt come from the engine's own (parity-checked) encrypt; 0.1 % of the tags
+    are corrupted and the ok flags must say exactly which; sampled messages vs the oracle."""
+    torch = torch_mod
+    n_msgs, length, alen = 1 << 20, 1500, 64
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(3)
+    d_keys = torch.randint(0, 256, (n_msgs * 32,), dtype=torch.uint8, device="cuda", generator=gen)
+    d_ivs = torch.randint(0, 256, (n_msgs * 12,), dtype=torch.uint8, device="cuda", generator=gen)
+    d_aad = torch.randint(0, 256, (n_msgs * alen,), dtype=torch.uint8, device="cuda", generator=gen)
+    d_pt = torch.randint(0, 256, (n_msgs * length,), dtype=torch.uint8, device="cuda", generator=gen)
+    d_ct = torch.zeros_like(d_pt)
+    d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+    engine.batch_crypt_perkey_uniform_device(256, 0, d_keys, d_ivs, d_aad, alen, alen, d_pt, d_ct, length, length, d_tags,
+                                             n_msgs=n_msgs)
+    torch.cuda.synchronize()
+    for i in (0, 7, 99999, n_msgs - 1):
+        key = d_keys[32 * i:32 * i + 32].cpu().numpy().tobytes()
+        iv = d_ivs[12 * i:12 * i + 12].cpu().numpy().tobytes()
+        aad = d_aad[alen * i:alen * (i + 1)].cpu().numpy().tobytes()
+        pt = d_pt[length * i:length * (i + 1)].cpu().numpy().tobytes()
+        want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt)
+        assert d_ct[length * i:length * (i + 1)].cpu().numpy().tobytes() == want_ct, i
+        assert d_tags[16 * i:16 * i + 16].cpu().numpy().tobytes() == want_tag, i
+    rng = np.random.default_rng(3)
+    bad = np.sort(rng.choice(n_msgs, n_msgs // 1000, replace=False))
+    d_tags_in = d_tags.clone()
+    d_tags_in.view(n_msgs, 16)[torch.from_numpy(bad).cuda(), 0] ^= 1
+    d_back = torch.zeros_like(d_pt)
+    d_ok = torch.zeros(n_msgs, dtype=torch.uint8, device="cuda")
+    engine.batch_crypt_perkey_uniform_device(256, 1, d_keys, d_ivs, d_aad, alen, alen, d_ct, d_back, length, length,
+                                             d_tags_in, d_ok, n_msgs=n_msgs)
+    torch.cuda.synchronize()
+    assert torch.equal(d_back, d_pt)
+    ok = d_ok.cpu().numpy()
+    assert int(ok.sum()) == n_msgs - bad.size and (ok[bad] == 0).all()
+
+
 # ------------------------------------------------------------ shards (one GPU, k parts)
 def test_counter_range_shards_combine(engine, oracle, torch_mod):
     """SURVEY 8(e) regime 2 on one GPU: k counter-range shards + XOR of pre-scaled partials."""

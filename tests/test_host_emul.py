@@ -99,3 +99,36 @@ def test_batch_lanes(emul, oracle, G):
                 assert list(ok) == [1, 1, 1, 0, 1, 1, 1, 1, 1]
             else:
                 assert (tag == et).all(), (kb, G)
+
+
+@pytest.mark.parametrize("kb", [16, 24, 32])
+def test_perkey_messages(emul, oracle, kb):
+    """One distinct key per message: on-the-fly key schedule + private 4-bit GHASH table."""
+    rng = np.random.default_rng(23 + kb)
+    for dec in (0, 1):
+        nm = 12
+        lens = rng.integers(0, 300, nm)
+        lens[0], lens[1], lens[2] = 0, 16, 1500
+        alens = rng.integers(0, 80, nm)
+        alens[2], alens[3] = 64, 0
+        in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.uint64)
+        data = rng.integers(0, 256, int(in_off[-1]) + 1, dtype=np.uint8)
+        aad = rng.integers(0, 256, int(aad_off[-1]) + 1, dtype=np.uint8)
+        ivs = rng.integers(0, 256, 12 * nm, dtype=np.uint8)
+        keys = rng.integers(0, 256, kb * nm, dtype=np.uint8)
+        eo, et = oracle.gcm_batch(keys, kb, False, ivs, aad, aad_off, data[:int(in_off[-1])], in_off, decrypt=bool(dec))
+        out = np.zeros_like(data)
+        tag = np.zeros(16 * nm, np.uint8)
+        ok = np.zeros(nm, np.uint8)
+        if dec:
+            tag[:] = et
+            tag[16 * 4 + 9] ^= 0x01
+        rc = emul.emul_batch_perkey(u8p(keys), kb, dec, u8p(ivs), u8p(aad), u64p(aad_off), u8p(data), u64p(in_off), u8p(out),
+                                    u8p(tag), u8p(ok), ctypes.c_uint64(nm))
+        assert rc == 0
+        assert (out[:int(in_off[-1])] == eo).all(), (kb, dec)
+        if dec:
+            assert list(ok) == [1, 1, 1, 1, 0] + [1] * 7
+        else:
+            assert (tag == et).all(), kb
