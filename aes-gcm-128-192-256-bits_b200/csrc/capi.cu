@@ -208,7 +208,11 @@ int ensure_pipeline(agcm_ctx* c)
 int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len)
 {
     if (lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32) return lanes;
+    if (lanes == 1024) return 1024;  // one CTA per message
     if (lanes != 0) return -1;
+    // long messages that cannot give every warp its own message: one CTA per message
+    // (>= 4 rows of the CTA-wide Horner so the per-message lane weights amortise)
+    if (avg_len >= (uint64_t)c->nt * 16 * 4 && n_msgs * 32 < (uint64_t)c->ncta * c->nt) return 1024;
     // enough groups to occupy every lane of the persistent grid, but never more
     // lanes than blocks in a message
     const uint64_t total_lanes = (uint64_t)c->ncta * c->nt;
@@ -486,6 +490,12 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
     p.key = c->d_key;
     p.te0 = c->d_te0;
     p.n_msgs = n_msgs;
+    if (g == 1024) {
+        const int ncta_m = (int)(n_msgs < (uint64_t)c->ncta ? n_msgs : (uint64_t)c->ncta);
+        AG_CUDA(c, ag_launch_batch_cta(p, c->nr, decrypt, ncta_m, c->nt, (cudaStream_t)stream));
+        c->launches++;
+        return AGCM_OK;
+    }
     // no more CTAs than there is work for
     const uint64_t groups_per_cta = (uint64_t)c->nt / g;
     uint64_t need = (n_msgs + groups_per_cta - 1) / groups_per_cta;

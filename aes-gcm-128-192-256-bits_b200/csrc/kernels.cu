@@ -420,6 +420,61 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
 }
 
 // ===========================================================================
+// Batched LONG messages under the shared key: one CTA per message (G = blockDim.x
+// lanes).  Same front-padded strided Horner as k_batch, constant H^NT (tab[6]); lane
+// weights H^(NT-tid) by one bit-serial product per lane per message, then a CTA
+// XOR-reduce.  Used when messages are too few to give every warp its own message.
+// ===========================================================================
+template <int NR, bool DEC>
+__global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_constant__ BatchParams p)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+    fill_aes_tables(p.te0);
+    fill_gh_tables(p.key->tab[6], nullptr);
+    __syncthreads();
+    TeSmem te{ag_smem, lane * 4};
+    GhSmem gh_g{ag_smem + SM_GH, (lane & 7) * 16};
+    gf128* red = reinterpret_cast<gf128*>(ag_smem + SM_MISC);
+    const gf128 wgt = p.key->hpow_thread[nt - tid];
+    for (uint64_t m = blockIdx.x; m < p.n_msgs; m += gridDim.x) {
+        const MsgDesc d = ag_batch_msg(p, m);
+        const uint8_t* ivp = p.iv + 12 * m;
+        uint32_t iv0 = 0, iv1 = 0, iv2 = 0;
+        for (int j = 0; j < 4; ++j) {
+            iv0 |= (uint32_t)ivp[j] << (8 * j);
+            iv1 |= (uint32_t)ivp[4 + j] << (8 * j);
+            iv2 |= (uint32_t)ivp[8 + j] << (8 * j);
+        }
+        const AesCtrConst cc = aes_ctr_precompute(p.rk, iv0, iv1, iv2, te);
+        gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, d, tid, nt, te, gh_g);
+        y = gf_mul(y, wgt);
+        y = warp_xor(y);
+        if (lane == 0) red[tid >> 5] = y;
+        __syncthreads();
+        if (tid < 32) {
+            gf128 r = (tid < (nt >> 5)) ? red[tid] : gf_zero();
+            r = warp_xor(r);
+            if (tid == 0) {
+                uint32_t e[4];
+                aes_ctr_block<NR>(p.rk, cc, 1u, te, e);
+                uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
+                                  ag_bswap32(r.w[3]) ^ e[3]};
+                uint8_t* tp = p.tag + 16 * m;
+                if (DEC) {
+                    uint32_t x[4];
+                    ag_load_block(tp, 16, x);
+                    const uint32_t diff = (x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3]);
+                    p.ok[m] = diff ? 0 : 1;
+                } else {
+                    ag_store_block(tp, 16, tg);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ===========================================================================
 // Batched messages, one DISTINCT key per message (BASELINE config 4): one thread
 // per message, key schedule on the fly (aes_kexp expand variant), private 4-bit
 // GHASH table.  512 threads (128 registers each); shared memory: Te0|Te1 (64 KB,
@@ -615,6 +670,25 @@ static cudaError_t launch_batch_g(const BatchParams& p, int g, int ncta, int nt,
         case 8: return launch_batch_t<NR, DEC, 8>(p, ncta, nt, st);
         case 16: return launch_batch_t<NR, DEC, 16>(p, ncta, nt, st);
         case 32: return launch_batch_t<NR, DEC, 32>(p, ncta, nt, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int NR, bool DEC>
+static cudaError_t launch_batch_cta_t(const BatchParams& p, int ncta, int nt, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_batch_cta<NR, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    k_batch_cta<NR, DEC><<<ncta, nt, kSmemBytes, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_batch_cta(const BatchParams& p, int nr, int decrypt, int ncta, int nt, cudaStream_t st)
+{
+    switch (nr) {
+        case 10: return decrypt ? launch_batch_cta_t<10, true>(p, ncta, nt, st) : launch_batch_cta_t<10, false>(p, ncta, nt, st);
+        case 12: return decrypt ? launch_batch_cta_t<12, true>(p, ncta, nt, st) : launch_batch_cta_t<12, false>(p, ncta, nt, st);
+        case 14: return decrypt ? launch_batch_cta_t<14, true>(p, ncta, nt, st) : launch_batch_cta_t<14, false>(p, ncta, nt, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -227,6 +227,42 @@ def test_batch_ragged_offsets_all_lane_counts(engine, oracle, torch_mod, kb):
         assert (ok == expect).all(), lanes
 
 
+def test_batch_cta_per_message(engine, oracle, torch_mod):
+    """Few long messages: one CTA per message (lanes=1024), ragged lengths, AAD longer than the payload."""
+    torch = torch_mod
+    rng = np.random.default_rng(77)
+    key = _rb(rng, 32)
+    engine.set_key(key)
+    lens = np.array([0, 5, 16 * 1024, 16 * 1024 * 3 + 7, 200000, 16 * 1024 * 16 + 1, 1 << 20])
+    alens = np.array([70000, 0, 16, 20, 0, 64, 300000])
+    n_msgs = len(lens)
+    in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.uint64)
+    data = rng.integers(0, 256, int(in_off[-1]), dtype=np.uint8)
+    aad = rng.integers(0, 256, int(aad_off[-1]), dtype=np.uint8)
+    ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+    want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), 32, True, ivs, aad, aad_off, data, in_off, threads=8)
+    d_in_off, d_aad_off = torch.from_numpy(in_off.view(np.int64)).cuda(), torch.from_numpy(aad_off.view(np.int64)).cuda()
+    d_data, d_aad, d_ivs = _dev(torch, data), _dev(torch, aad), _dev(torch, ivs)
+    for lanes in (1024, 0, 32):
+        d_ct = torch.zeros_like(d_data)
+        d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_device(0, d_ivs, d_aad, d_aad_off, d_data, d_in_off, d_ct, d_tags, lanes=lanes,
+                                  avg_len_hint=int(lens.mean()))
+        torch.cuda.synchronize()
+        assert (d_ct.cpu().numpy() == want_ct).all(), lanes
+        assert (d_tags.cpu().numpy() == want_tags).all(), lanes
+        d_pt = torch.zeros_like(d_data)
+        d_ok = torch.zeros(n_msgs, dtype=torch.uint8, device="cuda")
+        tags_in = want_tags.copy()
+        tags_in[16 * 2] ^= 2
+        engine.batch_crypt_device(1, d_ivs, d_aad, d_aad_off, d_ct, d_in_off, d_pt, _dev(torch, tags_in), d_ok, lanes=lanes,
+                                  avg_len_hint=int(lens.mean()))
+        torch.cuda.synchronize()
+        assert (d_pt.cpu().numpy() == data).all(), lanes
+        assert list(d_ok.cpu().numpy()) == [1, 1, 0, 1, 1, 1, 1], lanes
+
+
 def test_config3_shape_strided_packets(engine, oracle, torch_mod):
     """BASELINE config 3 shape at reduced count: AES-192, 1500 B packets at a 1504 B stride,
     per-message IV, shared pre-expanded key, no AAD; plus the contiguous 1500 B layout."""
