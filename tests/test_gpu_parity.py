@@ -516,6 +516,28 @@ def test_readme_vectors_through_adapter():
         assert b"".join(m.data_out).hex() == x["ct"] and m.tag[0].hex() == x["tag"]
 
 
+def test_recorded_configs_replay_through_cuda_model(oracle):
+    """reference test configurations (tb/tmp/<seed>.json shape) replayed against
+    the CUDA-backed model with no cocotb, incl. RANDOM stimulus, the decrypt flow and the
+    pre-expanded-key flow; outputs equal the oracle's."""
+    from aesgcm_b200 import gcm_model, key_exp, stimulus as st
+    cfg = {'seed': 1, 'aes_mode': '256', 'key': '691D3EE909D7F54167FD1CA0B5D769081F2BDE1AEE655FDBAB80BD5295AE6BE7',
+           'iv': 'F0761E8DCD3D000176D457ED', 'data': 'EMPTY', 'enc_dec': 'enc', 'max_n_byte': 4095,
+           'aad': 'E20106D7CD0DF0761E8DCD3D88E5400076D457ED08000F101112131415161718191A1B1C1D1E1F202122232425262728292A2B2C2D2E2F303132333435363738393A0003'}
+    r = st.replay(cfg, gcm_model.gcm)
+    assert r['tag'].hex().upper() == '35217C774BBC31B63166BCF9D4ABED07' and r['ct_words'] == []   # README.md:257
+    for seed in range(6):
+        c = {'seed': 100 + seed, 'aes_mode': 'ALL', 'key': 'RANDOM', 'iv': 'RANDOM', 'aad': 'RANDOM', 'data': 'RANDOM',
+             'enc_dec': 'dec' if seed % 2 else 'enc', 'max_n_byte': 4095}
+        r = st.replay(c, gcm_model.gcm, pre_expanded=(seed % 3 == 0), expand_key=key_exp.aes_expand_key)
+        key = bytes.fromhex(r['data']['key']['data'])
+        iv = bytes.fromhex(r['data']['iv']['data'])
+        want_ct, want_tag = oracle.gcm_crypt(key, iv, b"".join(r['aad_words']), b"".join(r['pt_words']))
+        assert b"".join(r['ct_words']) == want_ct and r['tag'] == want_tag
+        if c['enc_dec'] == 'dec':
+            assert b"".join(r['dec_words']) == b"".join(r['pt_words']) and r['dec_tag'] == want_tag
+
+
 # --------------------------------------------------------------- full-size properties
 def test_config2_full_size_stream_properties(engine, oracle, torch_mod):
     """BASELINE config 2 at full size (AES-256, 2^30 B, 16 B AAD, default_rng(1)): too big for the
