@@ -157,3 +157,60 @@ AG_HD void aes_ctr_block(const uint32_t* rk, const AesCtrConst& cc, uint32_t ctr
     out[3] = (te(2, s3, 0) & 0x000000ffu) ^ (te(3, s0, 1) & 0x0000ff00u) ^ (te(0, s1, 2) & 0x00ff0000u) ^
              (te(1, s2, 3) & 0xff000000u) ^ rk[4 * NR + 3];
 }
+
+// ---- counter mode for a lane whose counter keeps its low byte (and, almost always, its
+// high byte) from one block to the next: the grid-wide stream kernel steps the counter by
+// Gt = ncta*1024, so bits 0..7 never change and bits 24..31 change once per 2^24 blocks.
+// Round-1 columns 0 and 3 then stay put, and so do the eight round-2 lookups that read them:
+// they are folded into q[0..3].  Rounds 1+2 cost 10 lookups instead of 20.  The cache is keyed
+// on the two counter bytes; a mismatch (also: any grid whose stride is not a multiple of 256)
+// just recomputes it.
+struct AesCtrCache {
+    uint32_t key;    // (s3i & 0xFF0000FF) the cache was built for; s3i = bswap(ctr) ^ rk[3]
+    uint32_t q[4];   // round-2 constants incl. rk[8..11]
+};
+
+template <class TE>
+AG_HD void aes_ctr_cache_fill(const uint32_t* rk, const AesCtrConst& cc, uint32_t s3i, TE&& te, AesCtrCache& c)
+{
+    const uint32_t a = cc.k[0] ^ te(3, s3i, 3);  // round-1 column 0
+    const uint32_t b = cc.k[3] ^ te(0, s3i, 0);  // round-1 column 3
+    c.key = s3i & 0xFF0000FFu;
+    c.q[0] = te(0, a, 0) ^ te(3, b, 3) ^ rk[8];
+    c.q[1] = te(2, b, 2) ^ te(3, a, 3) ^ rk[9];
+    c.q[2] = te(1, b, 1) ^ te(2, a, 2) ^ rk[10];
+    c.q[3] = te(0, b, 0) ^ te(1, a, 1) ^ rk[11];
+}
+
+template <int NR, class TE>
+AG_HD void aes_ctr_block_cached(const uint32_t* rk, const AesCtrConst& cc, AesCtrCache& c, uint32_t ctr, TE&& te,
+                                uint32_t out[4])
+{
+    const uint32_t s3i = ag_bswap32(ctr) ^ rk[3];
+    if ((s3i & 0xFF0000FFu) != c.key) aes_ctr_cache_fill(rk, cc, s3i, te, c);
+    const uint32_t r1 = cc.k[1] ^ te(2, s3i, 2);  // round-1 column 1
+    const uint32_t r2 = cc.k[2] ^ te(1, s3i, 1);  // round-1 column 2
+    uint32_t s0 = c.q[0] ^ te(1, r1, 1) ^ te(2, r2, 2);
+    uint32_t s1 = c.q[1] ^ te(0, r1, 0) ^ te(1, r2, 1);
+    uint32_t s2 = c.q[2] ^ te(0, r2, 0) ^ te(3, r1, 3);
+    uint32_t s3 = c.q[3] ^ te(2, r1, 2) ^ te(3, r2, 3);
+#pragma unroll
+    for (int r = 3; r < NR; ++r) {
+        uint32_t t0 = te(0, s0, 0) ^ te(1, s1, 1) ^ te(2, s2, 2) ^ te(3, s3, 3) ^ rk[4 * r + 0];
+        uint32_t t1 = te(0, s1, 0) ^ te(1, s2, 1) ^ te(2, s3, 2) ^ te(3, s0, 3) ^ rk[4 * r + 1];
+        uint32_t t2 = te(0, s2, 0) ^ te(1, s3, 1) ^ te(2, s0, 2) ^ te(3, s1, 3) ^ rk[4 * r + 2];
+        uint32_t t3 = te(0, s3, 0) ^ te(1, s0, 1) ^ te(2, s1, 2) ^ te(3, s2, 3) ^ rk[4 * r + 3];
+        s0 = t0;
+        s1 = t1;
+        s2 = t2;
+        s3 = t3;
+    }
+    out[0] = (te(2, s0, 0) & 0x000000ffu) ^ (te(3, s1, 1) & 0x0000ff00u) ^ (te(0, s2, 2) & 0x00ff0000u) ^
+             (te(1, s3, 3) & 0xff000000u) ^ rk[4 * NR + 0];
+    out[1] = (te(2, s1, 0) & 0x000000ffu) ^ (te(3, s2, 1) & 0x0000ff00u) ^ (te(0, s3, 2) & 0x00ff0000u) ^
+             (te(1, s0, 3) & 0xff000000u) ^ rk[4 * NR + 1];
+    out[2] = (te(2, s2, 0) & 0x000000ffu) ^ (te(3, s3, 1) & 0x0000ff00u) ^ (te(0, s0, 2) & 0x00ff0000u) ^
+             (te(1, s1, 3) & 0xff000000u) ^ rk[4 * NR + 2];
+    out[3] = (te(2, s3, 0) & 0x000000ffu) ^ (te(3, s0, 1) & 0x0000ff00u) ^ (te(0, s1, 2) & 0x00ff0000u) ^
+             (te(1, s2, 3) & 0xff000000u) ^ rk[4 * NR + 3];
+}

@@ -119,45 +119,71 @@ struct StreamParams {
 
 // Returns Y_g for global lane g of Gt lanes; the caller multiplies by H^(Gt-g).
 // Block indices fit 32 bits (a counter range holds < 2^32 blocks).
-template <int NR, int MODE, class TE, class GH>
+// ALIGNED: `in`/`out` are 16-byte aligned, so every full block moves with one 128-bit
+// load/store and only the owner of a ragged last block takes the byte path.
+template <int NR, int MODE, bool ALIGNED, class TE, class GH>
 AG_HD gf128 ag_stream_lane(const StreamParams& p, uint32_t g, uint32_t Gt, TE&& te, GH&& gh)
 {
     const uint32_t n_blocks = (uint32_t)((p.n_bytes + 15) >> 4);
+    const uint32_t n_full = (uint32_t)(p.n_bytes >> 4);               // blocks that are whole
     const uint32_t rows = (uint32_t)(((uint64_t)n_blocks + Gt - 1) / Gt);
     const uint32_t pad = (uint32_t)((uint64_t)rows * Gt - n_blocks);   // < Gt
-    const uint32_t tail = (uint32_t)(p.n_bytes & 15);  // bytes in a short last block, 0 = full
-    const uint32_t last = n_blocks - 1;
+    const uint32_t tail = (uint32_t)(p.n_bytes & 15);                  // bytes in a short last block
 
     AesCtrConst cc;
-    if (MODE != AG_MODE_GHASH_ONLY) cc = aes_ctr_precompute(p.rk, p.iv[0], p.iv[1], p.iv[2], te);
+    AesCtrCache cache;
+    // row 0 may start inside the front padding: i is the block index of this lane in the
+    // current row, valid when `have`.
+    bool have = rows && g >= pad;
+    uint32_t i = g - pad;  // wraps when !have; row 1 then lands on g + Gt - pad
+    if (MODE != AG_MODE_GHASH_ONLY) {
+        cc = aes_ctr_precompute(p.rk, p.iv[0], p.iv[1], p.iv[2], te);
+        aes_ctr_cache_fill(p.rk, cc, ag_bswap32(p.ctr0 + i) ^ p.rk[3], te, cache);
+    }
+
+    auto load = [&](uint32_t bi, uint32_t x[4]) {
+        const uint8_t* src = p.in + 16 * (uint64_t)bi;
+        if (ALIGNED && bi < n_full) {
+#if defined(__CUDA_ARCH__)
+            const uint4 v = *reinterpret_cast<const uint4*>(src);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+#else
+            ag_load_block(src, 16, x);
+#endif
+        } else {
+            ag_load_block(src, bi < n_full ? 16u : tail, x);
+        }
+    };
 
     gf128 y = gf_zero();
     uint32_t xn[4] = {0, 0, 0, 0};
-    // row 0 may start inside the front padding: i is the block index of this lane
-    // in the current row, valid when `have`.
-    bool have = rows && g >= pad;
-    uint32_t i = g - pad;  // wraps when !have; row 1 then lands on g + Gt - pad
     // software prefetch: row u+1's block is requested before row u is processed
-    if (have) ag_load_block(p.in + 16 * (uint64_t)i, (i == last && tail) ? tail : 16u, xn);
+    if (have) load(i, xn);
     for (uint32_t u = 0; u < rows; ++u) {
         uint32_t x[4] = {xn[0], xn[1], xn[2], xn[3]};
-        if (u + 1 < rows) {
-            const uint32_t i1 = i + Gt;  // rows >= 1 are never padding
-            ag_load_block(p.in + 16 * (uint64_t)i1, (i1 == last && tail) ? tail : 16u, xn);
-        }
+        if (u + 1 < rows) load(i + Gt, xn);  // rows >= 1 are never padding
         if (MODE != AG_MODE_CTR_ONLY && u) y = gf_mul_table(y, gh);
         if (have) {
-            const uint32_t nv = (i == last && tail) ? tail : 16u;
             uint32_t s[4];
             if (MODE == AG_MODE_GHASH_ONLY) {
                 s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = x[3];
             } else {
                 uint32_t ks[4];
-                aes_ctr_block<NR>(p.rk, cc, p.ctr0 + i, te, ks);
+                aes_ctr_block_cached<NR>(p.rk, cc, cache, p.ctr0 + i, te, ks);
                 uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
-                ag_store_block(p.out + 16 * (uint64_t)i, nv, o);
+                uint8_t* dst = p.out + 16 * (uint64_t)i;
+                if (ALIGNED && i < n_full) {
+#if defined(__CUDA_ARCH__)
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+#else
+                    ag_store_block(dst, 16, o);
+#endif
+                } else {
+                    const uint32_t nv = i < n_full ? 16u : tail;
+                    ag_store_block(dst, nv, o);
+                    if (MODE == AG_MODE_ENC && nv != 16) ag_mask_block(o, nv);
+                }
                 if (MODE == AG_MODE_ENC) {
-                    if (nv != 16) ag_mask_block(o, nv);
                     s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
                 } else {
                     s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = x[3];

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) k_key_setup(KeyDev* kd, const uint32_t* _
 // Single stream: fused GCTR + GHASH, grid-wide strided Horner.
 // grid = kd->ncta CTAs x kd->nt_stream threads; writes one 16 B partial per CTA.
 // ===========================================================================
-template <int NR, int MODE>
+template <int NR, int MODE, bool ALIGNED>
 __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_constant__ StreamParams p)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_con
     GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
     const uint32_t Gt = gridDim.x * nt;
     const uint32_t g = blockIdx.x * nt + tid;
-    gf128 y = ag_stream_lane<NR, MODE>(p, g, Gt, te, gh);
+    gf128 y = ag_stream_lane<NR, MODE, ALIGNED>(p, g, Gt, te, gh);
     if (MODE == AG_MODE_CTR_ONLY) return;
 
     // lane weight H^(Gt-g) = (H^NT)^(ncta-1-cta) * H^(NT-tid)
@@ -623,9 +623,18 @@ size_t ag_smem_bytes() { return kSmemBytes; }
 template <int NR, int MODE>
 static cudaError_t launch_stream_t(const StreamParams& p, int ncta, int nt, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_stream<NR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) return e;
-    k_stream<NR, MODE><<<ncta, nt, kSmemBytes, st>>>(p);
+    // 128-bit path when both buffers are 16-byte aligned (GHASH-only has no output buffer)
+    const bool aligned = (((uintptr_t)p.in | (uintptr_t)p.out) & 15) == 0;
+    cudaError_t e;
+    if (aligned) {
+        e = cudaFuncSetAttribute(k_stream<NR, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return e;
+        k_stream<NR, MODE, true><<<ncta, nt, kSmemBytes, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(k_stream<NR, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return e;
+        k_stream<NR, MODE, false><<<ncta, nt, kSmemBytes, st>>>(p);
+    }
     return cudaGetLastError();
 }
 

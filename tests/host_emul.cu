@@ -107,10 +107,10 @@ void stream_nr(const StreamParams& p, int mode, uint64_t ncta, uint64_t nt, cons
     for (uint32_t g = 0; g < Gt; ++g) {
         gf128 y;
         switch (mode) {
-            case AG_MODE_ENC: y = ag_stream_lane<NR, AG_MODE_ENC>(p, g, Gt, te, gh); break;
-            case AG_MODE_DEC: y = ag_stream_lane<NR, AG_MODE_DEC>(p, g, Gt, te, gh); break;
-            case AG_MODE_GHASH_ONLY: y = ag_stream_lane<NR, AG_MODE_GHASH_ONLY>(p, g, Gt, te, gh); break;
-            default: y = ag_stream_lane<NR, AG_MODE_CTR_ONLY>(p, g, Gt, te, gh); break;
+            case AG_MODE_ENC: y = ag_stream_lane<NR, AG_MODE_ENC, false>(p, g, Gt, te, gh); break;
+            case AG_MODE_DEC: y = ag_stream_lane<NR, AG_MODE_DEC, true>(p, g, Gt, te, gh); break;
+            case AG_MODE_GHASH_ONLY: y = ag_stream_lane<NR, AG_MODE_GHASH_ONLY, true>(p, g, Gt, te, gh); break;
+            default: y = ag_stream_lane<NR, AG_MODE_CTR_ONLY, false>(p, g, Gt, te, gh); break;
         }
         // kernel: y *= hpow_thread[nt - tid]; CTA xor; *= hpow_cta[ncta-1-cta]
         const uint64_t cta = g / nt, tid = g % nt;
