@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 
@@ -14,7 +15,7 @@
 namespace {
 
 constexpr int kSlots = 3;
-constexpr size_t kChunkBytes = 32u << 20;  // host pipeline granule
+constexpr size_t kChunkBytesMax = 64u << 20;  // host pipeline granule (upper bound; AGCM_CHUNK_MB tunes it)
 constexpr size_t kMaxChunks = 8192;
 constexpr uint64_t kAadInlineMax = 4096;   // bytes of AAD folded inside k_stream_finish
 constexpr uint64_t kMaxBlocks = 0xFFFFFFFEull;
@@ -59,6 +60,7 @@ struct agcm_ctx {
     uint8_t* d_aad_stage = nullptr;
     size_t aad_stage_cap = 0;
     bool pipeline_ready = false;
+    size_t chunk_bytes = 32u << 20;
 };
 
 namespace {
@@ -194,10 +196,14 @@ int run_finish(agcm_ctx* c, int decrypt, const uint8_t iv[12], const uint8_t* d_
 int ensure_pipeline(agcm_ctx* c)
 {
     if (c->pipeline_ready) return AGCM_OK;
+    if (const char* e = getenv("AGCM_CHUNK_MB")) {
+        const long mb = atol(e);
+        if (mb >= 1 && (size_t)mb <= (kChunkBytesMax >> 20)) c->chunk_bytes = (size_t)mb << 20;
+    }
     for (int s = 0; s < kSlots; ++s) {
         AG_CUDA(c, cudaStreamCreateWithFlags(&c->hs[s], cudaStreamNonBlocking));
-        AG_CUDA(c, cudaMalloc(&c->d_stage[s], kChunkBytes));
-        AG_CUDA(c, cudaMalloc(&c->d_stage_aux[s], kChunkBytes / 8));
+        AG_CUDA(c, cudaMalloc(&c->d_stage[s], kChunkBytesMax));
+        AG_CUDA(c, cudaMalloc(&c->d_stage_aux[s], kChunkBytesMax / 8));
         AG_CUDA(c, cudaMalloc(&c->d_stage_parts[s], sizeof(uint32_t) * 4 * AG_MAX_CTA));
     }
     AG_CUDA(c, cudaMalloc(&c->d_chunk_partials, 16 * kMaxChunks));
@@ -630,6 +636,9 @@ static int host_pipeline(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uin
                          uint8_t* h_out, uint64_t n_bytes, uint64_t blocks_after0, uint64_t* n_chunks_out)
 {
     const uint64_t nblocks = (n_bytes + 15) >> 4;
+    // granule: the tuned size, grown for very long ranges so the partial list stays bounded
+    uint64_t kChunkBytes = c->chunk_bytes;
+    while ((n_bytes + kChunkBytes - 1) / kChunkBytes > SC_PARTS_MAX && kChunkBytes < kChunkBytesMax) kChunkBytes <<= 1;
     const uint64_t n_chunks = (n_bytes + kChunkBytes - 1) / kChunkBytes;
     if (n_chunks > kMaxChunks || n_chunks > SC_PARTS_MAX) return AGCM_E_BAD_LEN;
     const int mode = decrypt ? AG_MODE_DEC : AG_MODE_ENC;
@@ -762,6 +771,7 @@ int agcm_batch_crypt_uniform_host(agcm_ctx* c, int decrypt, int lanes, const uin
     if (rc) return rc;
     // messages per chunk: payload fits the stage buffer, side data fits the aux buffer
     const uint64_t per_msg_aux = 12 + 16 + 1 + aad_stride + 16;
+    const uint64_t kChunkBytes = 32u << 20;
     uint64_t m_chunk = stride ? kChunkBytes / stride : n_msgs;
     const uint64_t m_aux = (kChunkBytes / 8) / per_msg_aux;
     if (m_chunk > m_aux) m_chunk = m_aux;

@@ -139,6 +139,40 @@ def test_stream_random_sizes_vs_oracle(engine, oracle, torch_mod, kb):
             assert not ok
 
 
+def test_stream_unaligned_and_in_place_device_buffers(engine, oracle, torch_mod):
+    """Device pointers at byte offsets 1 / 4 / 8 (byte and 32-bit paths), different in/out
+    alignments, and exact in-place operation."""
+    torch = torch_mod
+    rng = np.random.default_rng(61)
+    key, iv, aad = _rb(rng, 32), _rb(rng, 12), _rb(rng, 16)
+    engine.set_key(key)
+    d_aad = _dev(torch, aad)
+    for n in (1, 100, 16 * 151552 + 33, 3 * 16 * 151552 + 5):
+        pt = rng.integers(0, 256, n, dtype=np.uint8)
+        want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt, threads=8)
+        for off_in, off_out in ((1, 1), (4, 4), (8, 0), (0, 3), (16, 16)):
+            buf_in = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+            buf_out = torch.full((n + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+            buf_in[off_in:off_in + n] = torch.from_numpy(pt).cuda()
+            d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+            engine.stream_crypt_device(0, iv, d_aad, buf_in[off_in:off_in + n], buf_out[off_out:off_out + n], d_tag, n_bytes=n)
+            torch.cuda.synchronize()
+            out = buf_out.cpu().numpy()
+            assert out[off_out:off_out + n].tobytes() == want_ct, (n, off_in, off_out)
+            assert (out[:off_out] == 0xEE).all() and (out[off_out + n:] == 0xEE).all()   # nothing written outside
+            assert d_tag.cpu().numpy().tobytes() == want_tag
+        # in place
+        buf = torch.from_numpy(pt).cuda()
+        d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+        engine.stream_crypt_device(0, iv, d_aad, buf, buf, d_tag)
+        torch.cuda.synchronize()
+        assert buf.cpu().numpy().tobytes() == want_ct and d_tag.cpu().numpy().tobytes() == want_tag
+        d_ok = torch.zeros(1, dtype=torch.uint8, device="cuda")
+        engine.stream_crypt_device(1, iv, d_aad, buf, buf, d_tag, d_ok)
+        torch.cuda.synchronize()
+        assert int(d_ok.item()) == 1 and buf.cpu().numpy().tobytes() == pt.tobytes()
+
+
 def test_stream_long_aad_paths(engine, oracle):
     # AAD > 4 KiB goes through the grid-wide GHASH-only kernel, AAD <= 4 KiB is folded in the finish kernel
     rng = np.random.default_rng(7)
