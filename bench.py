@@ -302,10 +302,19 @@ def run_ours(args, rank, world, local_rank):
         k_avg_ms = k_ms / max(k_n, 1)
         achieved = alg / (k_avg_ms * 1e-3) / 1e9
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        # shared-memory lookup bound of the formulation: per 16 B block 13*16+4 AES
-        # word lookups (4 B) + 16 GHASH row lookups (16 B) through a 128 B/clk/SM crossbar
-        smem_bytes_per_block = (13 * 16 + 4) * 4 + 16 * 16
-        smem_bound = eng.sm_count * 128.0 * sm_mhz * 1e6 / smem_bytes_per_block * 16 / 1e9  # payload GB/s
+        # L1/shared-memory data-pipe bound of the formulation: per warp-row of 32
+        # blocks 202 AES word lookups + 16 GHASH 128-bit row lookups (4 wavefronts each) + 8 global
+        # load/store wavefronts, through a pipe that retires 1 wavefront (128 B) per clock per SM
+        wavefronts_per_row = 202 + 64 + 8
+        smem_bound = eng.sm_count * sm_mhz * 1e6 / wavefronts_per_row * 32 * 16 / 1e9  # payload GB/s
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("n_bytes") == shard.n_bytes:
+                traffic = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
@@ -318,14 +327,15 @@ def run_ours(args, rank, world, local_rank):
                     "api": "GcmEngine.encrypt (agcm_stream_crypt_host), pinned host buffers" if world == 1 else
                            "GcmEngine.stream_part_host + all_gather + stream_finish_host, pinned host buffers"},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "kernel": "k_stream<14,ENC>",
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "k_stream<14,ENC>",
                          "kernel_ms": round(k_avg_ms, 4), "kernel_launches": int(k_n), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg)},
             "bound_smem_lookup": {"payload_GBps_bound": round(smem_bound, 1), "sm_mhz_used": sm_mhz,
-                                  "smem_bytes_per_block": smem_bytes_per_block,
+                                  "lsu_wavefronts_per_32_blocks": wavefronts_per_row,
                                   "frac": round(shard.n_bytes / (k_avg_ms * 1e-3) / 1e9 / smem_bound, 4),
-                                  "note": "the binding roofline of this formulation is the 128 B/clk/SM shared-memory "
-                                          "crossbar, not HBM (DESIGN.md)"},
+                                  "note": "the binding roofline of this formulation is the 128 B/clk/SM L1/shared-memory "
+                                          "data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 97 % of peak), not HBM "
+                                          "(DESIGN.md 4.1, profiles/r1_ncu_stream_final.md)"},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
