@@ -34,6 +34,15 @@ for s in $STEPS; do
         python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_ncubatch_run.log 2>&1; echo "ncubatch rc=$?"; tail -3 $OUT/${TAG}_ncubatch_run.log ;;
     sanitize)
       timeout 900 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_sanitize.log 2>&1; echo "sanitize rc=$?"; tail -8 $OUT/${TAG}_sanitize.log ;;
+    scale4|scale8)
+      N=${s#scale}
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2953$N \
+        bench.py --gpus $N --steps 30 --warmup 5 > $OUT/${TAG}_scale$N.json 2> $OUT/${TAG}_scale$N.err; echo "scale$N rc=$?"; cat $OUT/${TAG}_scale$N.json; tail -3 $OUT/${TAG}_scale$N.err ;;
+    refN8)
+      timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29549 \
+        bench.py --impl reference --gpus 8 --steps 2 --warmup 1 > $OUT/${TAG}_ref8.json 2> $OUT/${TAG}_ref8.err; echo "ref8 rc=$?"; cat $OUT/${TAG}_ref8.json; tail -3 $OUT/${TAG}_ref8.err ;;
+    racecheck)
+      timeout 900 compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -8 $OUT/${TAG}_racecheck.log ;;
     scale2)
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
         bench.py --gpus 2 --steps 30 --warmup 5 > $OUT/${TAG}_scale2.json 2> $OUT/${TAG}_scale2.err; echo "scale2 rc=$?"; cat $OUT/${TAG}_scale2.json; tail -5 $OUT/${TAG}_scale2.err ;;
