@@ -38,6 +38,7 @@ struct agcm_ctx {
     KeyDev* d_key = nullptr;
     uint32_t* d_parts = nullptr;  // 2 x AG_MAX_CTA x 4 words: [0] CT partials, [1] AAD partials
     uint8_t* d_scratch = nullptr;
+    uint32_t* d_counters = nullptr;  // last-CTA tickets: [0] context scratch, [1+s] pipeline slot s
     uint32_t h_rk[60];
     uint8_t h_H[16];
     int nr = 0;
@@ -108,16 +109,28 @@ int timing_drain(agcm_ctx* c)
     return AGCM_OK;
 }
 
+// optional tag finish fused into the stream kernel (single-shard message, short AAD)
+struct FuseFinish {
+    const uint8_t* aad;
+    uint64_t aad_len, ct_len;
+    uint8_t* tag_calc;
+    const uint8_t* tag_expected;
+    uint8_t* ok;
+};
+
 // GHASH partial of `n_bytes` at d_in (optionally also CTR) -> 16 B at d_partial16,
-// scaled by H^blocks_after.  parts_raw: per-CTA scratch (AG_MAX_CTA x 4 words).
+// scaled by H^blocks_after; the fold of the per-CTA partials runs in the last CTA of
+// the same launch.  parts_raw: per-CTA scratch (AG_MAX_CTA x 4 words); counter: its ticket.
 int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
-               uint64_t n_bytes, uint64_t blocks_after, uint32_t* parts_raw, uint8_t* d_partial16, cudaStream_t st)
+               uint64_t n_bytes, uint64_t blocks_after, uint32_t* parts_raw, uint8_t* d_partial16, cudaStream_t st,
+               uint32_t* counter, const FuseFinish* ff = nullptr)
 {
     if (n_bytes == 0) {
         if (d_partial16) AG_CUDA(c, cudaMemsetAsync(d_partial16, 0, 16, st));
         return AGCM_OK;
     }
     StreamParams p;
+    memset(&p, 0, sizeof(p));
     memcpy(p.rk, c->h_rk, sizeof(p.rk));
     iv_words(iv, p.iv);
     p.ctr0 = (uint32_t)(2 + first_block);
@@ -127,6 +140,20 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
     p.key = c->d_key;
     p.te0 = c->d_te0;
     p.partials = parts_raw;
+    if (mode != AG_MODE_CTR_ONLY) {
+        p.done_counter = counter;
+        p.scale_e = blocks_after;
+        p.out16 = d_partial16;
+        if (ff) {
+            p.fuse_finish = 1;
+            p.aad = ff->aad;
+            p.aad_len = ff->aad_len;
+            p.ct_len = ff->ct_len;
+            p.tag_calc = ff->tag_calc;
+            p.tag_expected = ff->tag_expected;
+            p.ok = ff->ok;
+        }
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (c->timing) {
         if (c->tev_pending == agcm_ctx::kTimingRing) {
@@ -142,10 +169,6 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
     if (c->timing) {
         AG_CUDA(c, cudaEventRecord(ev1, st));
         c->tev_pending++;
-    }
-    if (mode != AG_MODE_CTR_ONLY && d_partial16) {
-        AG_CUDA(c, ag_launch_reduce_scale(c->d_key, parts_raw, (uint32_t)c->ncta, blocks_after, d_partial16, st));
-        c->launches++;
     }
     return AGCM_OK;
 }
@@ -168,7 +191,7 @@ int run_finish(agcm_ctx* c, int decrypt, const uint8_t iv[12], const uint8_t* d_
         uint8_t* list = c->d_scratch + SC_PARTS;
         if (n_parts) AG_CUDA(c, cudaMemcpyAsync(list, d_parts16, 16 * (size_t)n_parts, cudaMemcpyDeviceToDevice, st));
         int rc = run_stream(c, AG_MODE_GHASH_ONLY, iv, 0, d_aad, nullptr, aad_len, n_ct_blocks,
-                            c->d_parts + 4 * AG_MAX_CTA, list + 16 * (size_t)n_parts, st);
+                            c->d_parts + 4 * AG_MAX_CTA, list + 16 * (size_t)n_parts, st, c->d_counters);
         if (rc) return rc;
         parts = list;
         np = n_parts + 1;
@@ -274,6 +297,8 @@ int agcm_ctx_create_ex(agcm_ctx** out, int device, int n_cta, int threads)
     if (e == cudaSuccess) e = cudaMalloc(&c->d_parts, sizeof(uint32_t) * 4 * AG_MAX_CTA * 2);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_scratch, SC_BYTES);
     if (e == cudaSuccess) e = cudaMemset(c->d_scratch, 0, SC_BYTES);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(uint32_t) * (1 + kSlots));
+    if (e == cudaSuccess) e = cudaMemset(c->d_counters, 0, sizeof(uint32_t) * (1 + kSlots));
     if (e == cudaSuccess) {
         uint8_t sbox[256];
         uint32_t te0[256];
@@ -308,6 +333,7 @@ void agcm_ctx_destroy(agcm_ctx* c)
     cudaFree(c->d_key);
     cudaFree(c->d_parts);
     cudaFree(c->d_scratch);
+    cudaFree(c->d_counters);
     delete c;
 }
 
@@ -441,7 +467,7 @@ int agcm_stream_part(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uint64_
     if (blocks_after && (n_bytes & 15)) return AGCM_E_BAD_LEN;  // only the last shard may be ragged
     AG_CUDA(c, cudaSetDevice(c->device));
     return run_stream(c, decrypt ? AG_MODE_DEC : AG_MODE_ENC, h_iv12, first_block, d_in, d_out, n_bytes, blocks_after,
-                      c->d_parts, d_partial16, (cudaStream_t)stream);
+                      c->d_parts, d_partial16, (cudaStream_t)stream, c->d_counters);
 }
 
 int agcm_stream_finish(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const uint8_t* d_partials16, int n_parts,
@@ -458,6 +484,22 @@ int agcm_stream_crypt(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const 
 {
     if (!c || !h_iv12) return AGCM_E_BAD_ARG;
     uint8_t* part = c->d_scratch + SC_PART_CT;
+    if (n_bytes && aad_len <= kAadInlineMax) {
+        // whole message in ONE launch: the last CTA folds the partials and finishes the tag
+        if (!c->key_set) return AGCM_E_NO_KEY;
+        if (!d_in || !d_out || (aad_len && !d_aad) || !d_tag || (decrypt && !d_ok)) return AGCM_E_BAD_ARG;
+        if (((n_bytes + 15) >> 4) > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
+        AG_CUDA(c, cudaSetDevice(c->device));
+        FuseFinish ff;
+        ff.aad = aad_len ? d_aad : nullptr;
+        ff.aad_len = aad_len;
+        ff.ct_len = n_bytes;
+        ff.tag_calc = decrypt ? c->d_scratch + SC_TAGCALC : d_tag;
+        ff.tag_expected = decrypt ? d_tag : nullptr;
+        ff.ok = decrypt ? d_ok : nullptr;
+        return run_stream(c, decrypt ? AG_MODE_DEC : AG_MODE_ENC, h_iv12, 0, d_in, d_out, n_bytes, 0, c->d_parts, nullptr,
+                          (cudaStream_t)stream, c->d_counters, &ff);
+    }
     int rc = agcm_stream_part(c, decrypt, h_iv12, 0, d_in, d_out, n_bytes, 0, part, stream);
     if (rc) return rc;
     return agcm_stream_finish(c, decrypt, h_iv12, part, 1, d_aad, aad_len, n_bytes, d_tag, d_ok, stream);
@@ -472,7 +514,7 @@ int agcm_gctr(agcm_ctx* c, const uint8_t h_iv12[12], uint64_t first_block, const
     if (first_block > kMaxBlocks || nb > kMaxBlocks - first_block) return AGCM_E_COUNTER_OVERFLOW;
     AG_CUDA(c, cudaSetDevice(c->device));
     return run_stream(c, AG_MODE_CTR_ONLY, h_iv12, first_block, d_in, d_out, n_bytes, 0, c->d_parts, nullptr,
-                      (cudaStream_t)stream);
+                      (cudaStream_t)stream, c->d_counters);
 }
 
 int agcm_ghash(agcm_ctx* c, const uint8_t* d_in, uint64_t n_bytes, uint8_t* d_y16, void* stream)
@@ -481,7 +523,8 @@ int agcm_ghash(agcm_ctx* c, const uint8_t* d_in, uint64_t n_bytes, uint8_t* d_y1
     if (!c->key_set) return AGCM_E_NO_KEY;
     AG_CUDA(c, cudaSetDevice(c->device));
     const uint8_t iv0[12] = {0};
-    return run_stream(c, AG_MODE_GHASH_ONLY, iv0, 0, d_in, nullptr, n_bytes, 0, c->d_parts, d_y16, (cudaStream_t)stream);
+    return run_stream(c, AG_MODE_GHASH_ONLY, iv0, 0, d_in, nullptr, n_bytes, 0, c->d_parts, d_y16, (cudaStream_t)stream,
+                      c->d_counters);
 }
 
 static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, BatchParams& p, size_t n_msgs, void* stream)
@@ -651,7 +694,7 @@ static int host_pipeline(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uin
         const uint64_t after = nblocks - fb - ((nb + 15) >> 4) + blocks_after0;
         AG_CUDA(c, cudaMemcpyAsync(c->d_stage[s], h_in + off, nb, cudaMemcpyHostToDevice, st));
         int rc = run_stream(c, mode, h_iv12, first_block0 + fb, c->d_stage[s], c->d_stage[s], nb, after,
-                            c->d_stage_parts[s], c->d_chunk_partials + 16 * k, st);
+                            c->d_stage_parts[s], c->d_chunk_partials + 16 * k, st, c->d_counters + 1 + s);
         if (rc) return rc;
         AG_CUDA(c, cudaMemcpyAsync(h_out + off, c->d_stage[s], nb, cudaMemcpyDeviceToHost, st));
     }

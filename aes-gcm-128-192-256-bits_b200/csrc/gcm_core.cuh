@@ -115,6 +115,16 @@ struct StreamParams {
     const KeyDev* key;
     const uint32_t* te0;  // 256-entry Te0 in HBM (per context)
     uint32_t* partials;   // gridDim.x x 4 BE words: per-CTA GHASH partial, last block weighted H^1
+    // fused tail, run by the last CTA to finish (null done_counter = off)
+    uint32_t* done_counter;       // zero before the launch; reset by the kernel
+    uint64_t scale_e;             // partial *= H^scale_e (blocks after this shard)
+    uint8_t* out16;               // scaled partial in natural byte order (may be null)
+    uint32_t fuse_finish;         // also finish the tag (single-shard message, short AAD)
+    const uint8_t* aad;
+    uint64_t aad_len, ct_len;
+    uint8_t* tag_calc;
+    const uint8_t* tag_expected;
+    uint8_t* ok;
 };
 
 // Returns Y_g for global lane g of Gt lanes; the caller multiplies by H^(Gt-g).

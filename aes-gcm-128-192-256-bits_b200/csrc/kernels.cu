@@ -211,94 +211,24 @@ __global__ void __launch_bounds__(256) k_key_setup(KeyDev* kd, const uint32_t* _
     }
 }
 
-// ===========================================================================
-// Single stream: fused GCTR + GHASH, grid-wide strided Horner.
-// grid = kd->ncta CTAs x kd->nt_stream threads; writes one 16 B partial per CTA.
-// ===========================================================================
-template <int NR, int MODE, bool ALIGNED>
-__global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_constant__ StreamParams p)
+// One full warp.  s = xor of the shard partials (natural GHASH domain, BE words).
+struct FinishArgs {
+    const uint32_t* rk;
+    uint32_t nr;
+    const uint32_t* iv;
+    const KeyDev* key;
+    const uint32_t* te0;
+    const uint8_t* aad;
+    uint64_t aad_len, ct_len;
+    uint8_t* tag_calc;
+    const uint8_t* tag_expected;
+    uint8_t* ok;
+};
+
+__device__ void finish_warp(const FinishArgs& p, gf128 s)
 {
-    const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
-    if (MODE != AG_MODE_GHASH_ONLY) fill_aes_tables(p.te0);
-    if (MODE != AG_MODE_CTR_ONLY) fill_gh_tables(p.key->tab[7], nullptr);
-    __syncthreads();
-
-    TeSmem te{ag_smem, lane * 4};
-    GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
-    const uint32_t Gt = gridDim.x * nt;
-    const uint32_t g = blockIdx.x * nt + tid;
-    gf128 y = ag_stream_lane<NR, MODE, ALIGNED>(p, g, Gt, te, gh);
-    if (MODE == AG_MODE_CTR_ONLY) return;
-
-    // lane weight H^(Gt-g) = (H^NT)^(ncta-1-cta) * H^(NT-tid)
-    y = gf_mul(y, p.key->hpow_thread[nt - tid]);
-    y = warp_xor(y);
-    gf128* red = reinterpret_cast<gf128*>(ag_smem + SM_MISC);
-    if (lane == 0) red[tid >> 5] = y;
-    __syncthreads();
-    if (tid < 32) {
-        gf128 v = (tid < (nt >> 5)) ? red[tid] : gf_zero();
-        v = warp_xor(v);
-        if (tid == 0) {
-            v = gf_mul(v, p.key->hpow_cta[gridDim.x - 1 - blockIdx.x]);
-            uint32_t* dst = p.partials + 4 * blockIdx.x;
-            dst[0] = v.w[0]; dst[1] = v.w[1]; dst[2] = v.w[2]; dst[3] = v.w[3];
-        }
-    }
-}
-
-// out16 = (xor of n_in partials) * H^e     (shard pre-scaling)
-__global__ void __launch_bounds__(32) k_reduce_scale(const KeyDev* kd, const uint32_t* __restrict__ parts, uint32_t n_in,
-                                                     uint64_t e, uint8_t* __restrict__ out)
-{
-    const uint32_t lane = threadIdx.x;
-    gf128 s = gf_zero();
-    for (uint32_t j = lane; j < n_in; j += 32) {
-        s.w[0] ^= parts[4 * j + 0]; s.w[1] ^= parts[4 * j + 1]; s.w[2] ^= parts[4 * j + 2]; s.w[3] ^= parts[4 * j + 3];
-    }
-    s = warp_xor(s);
-    if (e) {
-        gf128 he = warp_gf_pow(kd, e);
-        s = gf_mul(s, he);
-    }
-    if (lane == 0) {
-        const uint32_t o[4] = {ag_bswap32(s.w[0]), ag_bswap32(s.w[1]), ag_bswap32(s.w[2]), ag_bswap32(s.w[3])};
-        ag_store_block(out, 16, o);  // natural GHASH byte order
-    }
-}
-
-// out16 = xor of n 16-byte partials (natural byte order in and out)
-__global__ void __launch_bounds__(32) k_xor_parts(const uint8_t* __restrict__ parts, uint32_t n, uint8_t* __restrict__ out)
-{
-    const uint32_t lane = threadIdx.x;
-    gf128 s = gf_zero();
-    for (uint32_t j = lane; j < n; j += 32) {
-        uint32_t x[4];
-        ag_load_block(parts + 16 * j, 16, x);
-        s.w[0] ^= x[0]; s.w[1] ^= x[1]; s.w[2] ^= x[2]; s.w[3] ^= x[3];
-    }
-    s = warp_xor(s);
-    if (lane == 0) ag_store_block(out, 16, s.w);
-}
-
-// Tag finish (gcm_ghash.vhd:257,293 + tb/gcm_model.py:33-51):
-//   S = xor parts (each already aligned so that the last CT block weighs H^1)
-//   QA = sum A_i H^(a-i) over the (short) AAD given here, if any
-//   TAG = ((QA * H^n) xor S xor LEN) * H xor E_K(J0)
-// decrypt: constant-time compare with the expected tag -> ok flag; the computed
-// tag is always written to tag_calc.
-
-__global__ void __launch_bounds__(32) k_stream_finish(const __grid_constant__ FinishParams p)
-{
-    const uint32_t lane = threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
     const KeyDev* kd = p.key;
-    gf128 s = gf_zero();
-    for (uint32_t j = lane; j < p.n_parts; j += 32) {
-        uint32_t x[4];
-        ag_load_block(p.parts + 16 * j, 16, x);
-        s = gf_xor(s, gf_from_le_words(x[0], x[1], x[2], x[3]));
-    }
-    s = warp_xor(s);
     const uint64_t n = (p.ct_len + 15) >> 4;
     if (p.aad && p.aad_len) {  // uniform
         // short AAD (host routes long AAD through k_stream<GHASH_ONLY>): the warp
@@ -341,6 +271,110 @@ __global__ void __launch_bounds__(32) k_stream_finish(const __grid_constant__ Fi
         }
     }
 }
+
+__global__ void __launch_bounds__(32) k_stream_finish(const __grid_constant__ FinishParams p)
+{
+    const uint32_t lane = threadIdx.x;
+    gf128 s = gf_zero();
+    for (uint32_t j = lane; j < p.n_parts; j += 32) {
+        uint32_t x[4];
+        ag_load_block(p.parts + 16 * j, 16, x);
+        s = gf_xor(s, gf_from_le_words(x[0], x[1], x[2], x[3]));
+    }
+    s = warp_xor(s);
+    FinishArgs a{p.rk, p.nr, p.iv, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc, p.tag_expected, p.ok};
+    finish_warp(a, s);
+}
+
+// ===========================================================================
+// Single stream: fused GCTR + GHASH, grid-wide strided Horner.
+// grid = kd->ncta CTAs x kd->nt_stream threads; writes one 16 B partial per CTA.
+// ===========================================================================
+template <int NR, int MODE, bool ALIGNED>
+__global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_constant__ StreamParams p)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+    if (MODE != AG_MODE_GHASH_ONLY) fill_aes_tables(p.te0);
+    if (MODE != AG_MODE_CTR_ONLY) fill_gh_tables(p.key->tab[7], nullptr);
+    __syncthreads();
+
+    TeSmem te{ag_smem, lane * 4};
+    GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
+    const uint32_t Gt = gridDim.x * nt;
+    const uint32_t g = blockIdx.x * nt + tid;
+    gf128 y = ag_stream_lane<NR, MODE, ALIGNED>(p, g, Gt, te, gh);
+    if (MODE == AG_MODE_CTR_ONLY) return;
+
+    // lane weight H^(Gt-g) = (H^NT)^(ncta-1-cta) * H^(NT-tid)
+    y = gf_mul(y, p.key->hpow_thread[nt - tid]);
+    y = warp_xor(y);
+    gf128* red = reinterpret_cast<gf128*>(ag_smem + SM_MISC);
+    if (lane == 0) red[tid >> 5] = y;
+    __syncthreads();
+    if (tid < 32) {
+        gf128 v = (tid < (nt >> 5)) ? red[tid] : gf_zero();
+        v = warp_xor(v);
+        if (tid == 0) {
+            v = gf_mul(v, p.key->hpow_cta[gridDim.x - 1 - blockIdx.x]);
+            uint32_t* dst = p.partials + 4 * blockIdx.x;
+            dst[0] = v.w[0]; dst[1] = v.w[1]; dst[2] = v.w[2]; dst[3] = v.w[3];
+        }
+        // The last CTA to get here folds the per-CTA partials (and, for a single-shard
+        // message, finishes the tag) so that one launch does the whole message.
+        uint32_t ticket = 0;
+        if (p.done_counter) {
+            if (tid == 0) {
+                __threadfence();
+                ticket = atomicAdd(p.done_counter, 1u);
+            }
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            if (ticket == gridDim.x - 1) {
+                __threadfence();
+                gf128 s = gf_zero();
+                for (uint32_t j = tid; j < gridDim.x; j += 32) {
+                    const uint4 q = __ldcg(reinterpret_cast<const uint4*>(p.partials) + j);
+                    s.w[0] ^= q.x; s.w[1] ^= q.y; s.w[2] ^= q.z; s.w[3] ^= q.w;
+                }
+                s = warp_xor(s);
+                if (p.scale_e) {
+                    const gf128 he = warp_gf_pow(p.key, p.scale_e);
+                    s = gf_mul(s, he);
+                }
+                if (p.out16 && tid == 0) {
+                    const uint32_t o[4] = {ag_bswap32(s.w[0]), ag_bswap32(s.w[1]), ag_bswap32(s.w[2]), ag_bswap32(s.w[3])};
+                    ag_store_block(p.out16, 16, o);  // natural GHASH byte order
+                }
+                if (p.fuse_finish) {
+                    FinishArgs a{p.rk, (uint32_t)NR, p.iv, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc,
+                                 p.tag_expected, p.ok};
+                    finish_warp(a, s);
+                }
+                if (tid == 0) *p.done_counter = 0;  // ready for the next launch on this context
+            }
+        }
+    }
+}
+
+// out16 = xor of n 16-byte partials (natural byte order in and out)
+__global__ void __launch_bounds__(32) k_xor_parts(const uint8_t* __restrict__ parts, uint32_t n, uint8_t* __restrict__ out)
+{
+    const uint32_t lane = threadIdx.x;
+    gf128 s = gf_zero();
+    for (uint32_t j = lane; j < n; j += 32) {
+        uint32_t x[4];
+        ag_load_block(parts + 16 * j, 16, x);
+        s.w[0] ^= x[0]; s.w[1] ^= x[1]; s.w[2] ^= x[2]; s.w[3] ^= x[3];
+    }
+    s = warp_xor(s);
+    if (lane == 0) ag_store_block(out, 16, s.w);
+}
+
+// Tag finish (gcm_ghash.vhd:257,293 + tb/gcm_model.py:33-51):
+//   S = xor parts (each already aligned so that the last CT block weighs H^1)
+//   QA = sum A_i H^(a-i) over the (short) AAD given here, if any
+//   TAG = ((QA * H^n) xor S xor LEN) * H xor E_K(J0)
+// decrypt: constant-time compare with the expected tag -> ok flag; the computed
+// tag is always written to tag_calc.
 
 // ===========================================================================
 // Batched messages under one shared key: G lanes per message, persistent grid.
@@ -725,13 +759,6 @@ cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_b
 cudaError_t ag_launch_key_setup(KeyDev* kd, const uint32_t* te0, int nt_stream, int ncta, cudaStream_t st)
 {
     k_key_setup<<<1, 256, 0, st>>>(kd, te0, (uint32_t)nt_stream, (uint32_t)ncta);
-    return cudaGetLastError();
-}
-
-cudaError_t ag_launch_reduce_scale(const KeyDev* kd, const uint32_t* parts, uint32_t n_in, uint64_t e, uint8_t* out,
-                                   cudaStream_t st)
-{
-    k_reduce_scale<<<1, 32, 0, st>>>(kd, parts, n_in, e, out);
     return cudaGetLastError();
 }
 

@@ -28,8 +28,6 @@ cudaError_t ag_launch_batch_perkey(const BatchParams& p, int nr, int decrypt, in
 cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_bytes, const uint32_t* te0,
                                  uint8_t* round_keys, cudaStream_t st);
 cudaError_t ag_launch_key_setup(KeyDev* kd, const uint32_t* te0, int nt_stream, int ncta, cudaStream_t st);
-cudaError_t ag_launch_reduce_scale(const KeyDev* kd, const uint32_t* parts_raw, uint32_t n_in, uint64_t e,
-                                   uint8_t* out16, cudaStream_t st);
 cudaError_t ag_launch_finish(const FinishParams& p, cudaStream_t st);
 cudaError_t ag_launch_xor_parts(const uint8_t* parts16, uint32_t n, uint8_t* out16, cudaStream_t st);
 size_t ag_smem_bytes();
