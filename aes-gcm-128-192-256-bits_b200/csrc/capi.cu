@@ -39,6 +39,8 @@ struct agcm_ctx {
     uint32_t* d_parts = nullptr;  // 2 x AG_MAX_CTA x 4 words: [0] CT partials, [1] AAD partials
     uint8_t* d_scratch = nullptr;
     uint32_t* d_counters = nullptr;  // last-CTA tickets: [0] context scratch, [1+s] pipeline slot s
+    uint32_t* d_pow_n = nullptr;     // cached H^n (4 BE words) for the tag finish
+    uint64_t pow_n = ~0ull;          // exponent it was computed for (~0 = none)
     uint32_t h_rk[60];
     uint8_t h_H[16];
     int nr = 0;
@@ -109,6 +111,16 @@ int timing_drain(agcm_ctx* c)
     return AGCM_OK;
 }
 
+// H^n for the tag finish, computed once per (key, n) on the caller's stream
+int ensure_pow(agcm_ctx* c, uint64_t n_blocks, cudaStream_t st)
+{
+    if (c->pow_n == n_blocks) return AGCM_OK;
+    AG_CUDA(c, ag_launch_pow(c->d_key, n_blocks, c->d_pow_n, st));
+    c->launches++;
+    c->pow_n = n_blocks;
+    return AGCM_OK;
+}
+
 // optional tag finish fused into the stream kernel (single-shard message, short AAD)
 struct FuseFinish {
     const uint8_t* aad;
@@ -152,6 +164,7 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
             p.tag_calc = ff->tag_calc;
             p.tag_expected = ff->tag_expected;
             p.ok = ff->ok;
+            p.hn = c->d_pow_n;
         }
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -211,6 +224,12 @@ int run_finish(agcm_ctx* c, int decrypt, const uint8_t iv[12], const uint8_t* d_
     f.tag_calc = decrypt ? c->d_scratch + SC_TAGCALC : d_tag;
     f.tag_expected = decrypt ? d_tag : nullptr;
     f.ok = decrypt ? d_ok : nullptr;
+    f.hn = nullptr;
+    if (aad_inline) {
+        int rc = ensure_pow(c, n_ct_blocks, st);
+        if (rc) return rc;
+        f.hn = c->d_pow_n;
+    }
     AG_CUDA(c, ag_launch_finish(f, st));
     c->launches++;
     return AGCM_OK;
@@ -299,6 +318,7 @@ int agcm_ctx_create_ex(agcm_ctx** out, int device, int n_cta, int threads)
     if (e == cudaSuccess) e = cudaMemset(c->d_scratch, 0, SC_BYTES);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_counters, sizeof(uint32_t) * (1 + kSlots));
     if (e == cudaSuccess) e = cudaMemset(c->d_counters, 0, sizeof(uint32_t) * (1 + kSlots));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_pow_n, 16);
     if (e == cudaSuccess) {
         uint8_t sbox[256];
         uint32_t te0[256];
@@ -334,6 +354,7 @@ void agcm_ctx_destroy(agcm_ctx* c)
     cudaFree(c->d_parts);
     cudaFree(c->d_scratch);
     cudaFree(c->d_counters);
+    cudaFree(c->d_pow_n);
     delete c;
 }
 
@@ -408,6 +429,7 @@ int agcm_set_key(agcm_ctx* c, int mode, int pre_expanded, const uint8_t* h_key, 
     if (key_len != want) return AGCM_E_BAD_MODE;
     AG_CUDA(c, cudaSetDevice(c->device));
     c->key_set = false;
+    c->pow_n = ~0ull;
     uint8_t* d_rk = reinterpret_cast<uint8_t*>(c->d_key) + offsetof(KeyDev, rk);
     if (pre_expanded) {
         // config/config_aes_kprexp.py:66-95: Nr+1 user-loaded stages, used as they are
@@ -497,6 +519,10 @@ int agcm_stream_crypt(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const 
         ff.tag_calc = decrypt ? c->d_scratch + SC_TAGCALC : d_tag;
         ff.tag_expected = decrypt ? d_tag : nullptr;
         ff.ok = decrypt ? d_ok : nullptr;
+        if (aad_len) {
+            int rc = ensure_pow(c, (n_bytes + 15) >> 4, (cudaStream_t)stream);
+            if (rc) return rc;
+        }
         return run_stream(c, decrypt ? AG_MODE_DEC : AG_MODE_ENC, h_iv12, 0, d_in, d_out, n_bytes, 0, c->d_parts, nullptr,
                           (cudaStream_t)stream, c->d_counters, &ff);
     }

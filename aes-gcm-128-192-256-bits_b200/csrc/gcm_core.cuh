@@ -125,6 +125,7 @@ struct StreamParams {
     uint8_t* tag_calc;
     const uint8_t* tag_expected;
     uint8_t* ok;
+    const uint32_t* hn;           // H^(ct blocks), precomputed (k_pow) or null
 };
 
 // Returns Y_g for global lane g of Gt lanes; the caller multiplies by H^(Gt-g).

@@ -223,6 +223,8 @@ struct FinishArgs {
     uint8_t* tag_calc;
     const uint8_t* tag_expected;
     uint8_t* ok;
+    const uint32_t* hn;   // H^(ct blocks) precomputed by k_pow (4 BE words), or null: compute here
+    bool smem_tables;     // the CTA's shared T-tables are valid (called from k_stream)
 };
 
 __device__ void finish_warp(const FinishArgs& p, gf128 s)
@@ -250,16 +252,26 @@ __device__ void finish_warp(const FinishArgs& p, gf128 s)
         }
         qa = gf_mul(qa, kd->hpow_thread[32 - lane]);
         qa = warp_xor(qa);                     // QA = sum A_i H^(a-i)
-        const gf128 hn = warp_gf_pow(kd, n);
+        gf128 hn;
+        if (p.hn) {
+            hn.w[0] = __ldcg(p.hn + 0); hn.w[1] = __ldcg(p.hn + 1); hn.w[2] = __ldcg(p.hn + 2); hn.w[3] = __ldcg(p.hn + 3);
+        } else {
+            hn = warp_gf_pow(kd, n);
+        }
         if (lane == 0) s = gf_xor(s, gf_mul(qa, hn));
     }
     if (lane == 0) {
         const uint64_t ab = p.aad_len * 8, cb = p.ct_len * 8;
         s.w[0] ^= (uint32_t)(ab >> 32); s.w[1] ^= (uint32_t)ab; s.w[2] ^= (uint32_t)(cb >> 32); s.w[3] ^= (uint32_t)cb;
         s = gf_mul(s, kd->H);
-        TeGlobal te{p.te0};
         uint32_t e[4];
-        aes_encrypt_words(p.rk, (int)p.nr, p.iv[0], p.iv[1], p.iv[2], 0x01000000u, te, e);  // J0 = IV || 00000001
+        if (p.smem_tables) {
+            TeSmem te{ag_smem, 0};
+            aes_encrypt_words(p.rk, (int)p.nr, p.iv[0], p.iv[1], p.iv[2], 0x01000000u, te, e);  // J0 = IV || 00000001
+        } else {
+            TeGlobal te{p.te0};
+            aes_encrypt_words(p.rk, (int)p.nr, p.iv[0], p.iv[1], p.iv[2], 0x01000000u, te, e);
+        }
         uint32_t t[4] = {ag_bswap32(s.w[0]) ^ e[0], ag_bswap32(s.w[1]) ^ e[1], ag_bswap32(s.w[2]) ^ e[2],
                          ag_bswap32(s.w[3]) ^ e[3]};
         ag_store_block(p.tag_calc, 16, t);
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(32) k_stream_finish(const __grid_constant__ Fi
         s = gf_xor(s, gf_from_le_words(x[0], x[1], x[2], x[3]));
     }
     s = warp_xor(s);
-    FinishArgs a{p.rk, p.nr, p.iv, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc, p.tag_expected, p.ok};
+    FinishArgs a{p.rk, p.nr, p.iv, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc, p.tag_expected, p.ok, p.hn, false};
     finish_warp(a, s);
 }
 
@@ -346,13 +358,21 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_con
                 }
                 if (p.fuse_finish) {
                     FinishArgs a{p.rk, (uint32_t)NR, p.iv, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc,
-                                 p.tag_expected, p.ok};
+                                 p.tag_expected, p.ok, p.hn, MODE != AG_MODE_GHASH_ONLY};
                     finish_warp(a, s);
                 }
                 if (tid == 0) *p.done_counter = 0;  // ready for the next launch on this context
             }
         }
     }
+}
+
+// out[0..3] = H^e (BE words); cached per (key, e) by the host so that the tag finish
+// does not recompute it for every message of the same length
+__global__ void __launch_bounds__(32) k_pow(const KeyDev* kd, uint64_t e, uint32_t* __restrict__ out)
+{
+    const gf128 r = warp_gf_pow(kd, e);
+    if (threadIdx.x == 0) { out[0] = r.w[0]; out[1] = r.w[1]; out[2] = r.w[2]; out[3] = r.w[3]; }
 }
 
 // out16 = xor of n 16-byte partials (natural byte order in and out)
@@ -759,6 +779,12 @@ cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_b
 cudaError_t ag_launch_key_setup(KeyDev* kd, const uint32_t* te0, int nt_stream, int ncta, cudaStream_t st)
 {
     k_key_setup<<<1, 256, 0, st>>>(kd, te0, (uint32_t)nt_stream, (uint32_t)ncta);
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_pow(const KeyDev* kd, uint64_t e, uint32_t* out, cudaStream_t st)
+{
+    k_pow<<<1, 32, 0, st>>>(kd, e, out);
     return cudaGetLastError();
 }
 

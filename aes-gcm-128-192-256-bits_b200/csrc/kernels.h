@@ -19,6 +19,7 @@ struct FinishParams {
     uint8_t* tag_calc;            // 16 B out, always written
     const uint8_t* tag_expected;  // 16 B in (decrypt) or null
     uint8_t* ok;                  // 1 B out (decrypt) or null
+    const uint32_t* hn;           // H^(ct blocks) from k_pow, or null
 };
 
 cudaError_t ag_launch_stream(const StreamParams& p, int nr, int mode, int ncta, int nt, cudaStream_t st);
@@ -28,6 +29,7 @@ cudaError_t ag_launch_batch_perkey(const BatchParams& p, int nr, int decrypt, in
 cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_bytes, const uint32_t* te0,
                                  uint8_t* round_keys, cudaStream_t st);
 cudaError_t ag_launch_key_setup(KeyDev* kd, const uint32_t* te0, int nt_stream, int ncta, cudaStream_t st);
+cudaError_t ag_launch_pow(const KeyDev* kd, uint64_t e, uint32_t* out4, cudaStream_t st);
 cudaError_t ag_launch_finish(const FinishParams& p, cudaStream_t st);
 cudaError_t ag_launch_xor_parts(const uint8_t* parts16, uint32_t n, uint8_t* out16, cudaStream_t st);
 size_t ag_smem_bytes();
