@@ -133,6 +133,32 @@ def openssl_speed(cores, seconds=2):
     return None
 
 
+def python_model_rates():
+    """The reference model's calling patterns (tb/gcm_model.py) on one host core with the AES-GCM
+    library that IS installed (`cryptography`/OpenSSL stands in for pycryptodome): whole message,
+    and the testbench's one-<=16-byte-block-per-call streaming.  GB/s each, or None."""
+    try:
+        from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+        from cryptography.hazmat.primitives.ciphers.aead import AESGCM
+    except Exception:
+        return None
+    key, iv, aad = stream_inputs()
+    res = {}
+    pt = np.random.default_rng(1).integers(0, 256, 64 << 20, dtype=np.uint8).tobytes()
+    t0 = time.perf_counter()
+    AESGCM(key).encrypt(iv, pt, aad)
+    res["whole_message_64MiB_1core_GBps"] = round(len(pt) / (time.perf_counter() - t0) / 1e9, 3)
+    n = 1 << 20
+    enc = Cipher(algorithms.AES(key), modes.GCM(iv)).encryptor()
+    enc.authenticate_additional_data(aad)
+    t0 = time.perf_counter()
+    for i in range(0, n, 16):
+        enc.update(pt[i:i + 16])
+    enc.finalize()
+    res["per_16B_call_streaming_1MiB_1core_GBps"] = round(n / (time.perf_counter() - t0) / 1e9, 5)
+    return res
+
+
 def cpu_reference_rate(sample_bytes, threads, steps, warmup):
     """Times the CPU restatement of the reference datapath (oracle/gcm_oracle.c, all host
     threads) on the first `sample_bytes` of the config-2 stream.  -> (GB/s, seconds per step)."""
@@ -178,7 +204,9 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": round(val, 6), "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "first %d MiB of the config-2 stream per step, oracle/gcm_oracle.c with %d threads "
                                    "(pycryptodome, the reference's own backend, is not installed)" % (sample >> 20, cores),
-                         "openssl_speed_evp_aes256gcm_allcores_GBps": ossl},
+                         "openssl_speed_evp_aes256gcm_allcores_GBps": ossl,
+                         "python_cryptography_aesgcm": python_model_rates(),
+                         "pycryptodome": "unavailable (not installed; no network)"},
         "e2e": {"value": round(val, 6), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -345,7 +373,9 @@ def run_ours(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": round(v, 6), "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "first %d MiB of the same stream, 3 passes, oracle/gcm_oracle.c with %d "
                                               "threads (%.1f s per pass)" % (sample >> 20, cores, dt),
-                                    "openssl_speed_evp_aes256gcm_allcores_GBps": openssl_speed(cores)}
+                                    "openssl_speed_evp_aes256gcm_allcores_GBps": openssl_speed(cores),
+                                    "python_cryptography_aesgcm": python_model_rates(),
+                                    "pycryptodome": "unavailable (not installed; no network)"}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
