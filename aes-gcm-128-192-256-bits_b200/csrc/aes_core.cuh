@@ -214,3 +214,58 @@ AG_HD void aes_ctr_block_cached(const uint32_t* rk, const AesCtrConst& cc, AesCt
     out[3] = (te(2, s3, 0) & 0x000000ffu) ^ (te(3, s0, 1) & 0x0000ff00u) ^ (te(0, s1, 2) & 0x00ff0000u) ^
              (te(1, s2, 3) & 0xff000000u) ^ rk[4 * NR + 3];
 }
+
+// ---- counter mode for a lane that walks CONSECUTIVE (or small-stride) counters of one
+// message (the batched kernels): the three upper counter bytes change once per 256 counters,
+// so round-1 columns 1..3 and the twelve round-2 lookups that read them are cached per lane;
+// rounds 1+2 cost 5 lookups instead of 20.  Keyed on the three upper bytes (low 24 bits of
+// s3i = bswap(ctr) ^ rk[3]); a mismatch recomputes (15 lookups).
+struct AesCtrSeqCache {
+    uint32_t key;
+    uint32_t q[4];
+};
+
+template <class TE>
+AG_HD void aes_ctr_seq_fill(const uint32_t* rk, const AesCtrConst& cc, uint32_t s3i, TE&& te, AesCtrSeqCache& c)
+{
+    const uint32_t c1 = cc.k[1] ^ te(2, s3i, 2);  // round-1 column 1
+    const uint32_t c2 = cc.k[2] ^ te(1, s3i, 1);  // round-1 column 2
+    const uint32_t c3 = cc.k[3] ^ te(0, s3i, 0);  // round-1 column 3
+    c.key = s3i & 0x00FFFFFFu;
+    c.q[0] = te(1, c1, 1) ^ te(2, c2, 2) ^ te(3, c3, 3) ^ rk[8];
+    c.q[1] = te(0, c1, 0) ^ te(1, c2, 1) ^ te(2, c3, 2) ^ rk[9];
+    c.q[2] = te(3, c1, 3) ^ te(0, c2, 0) ^ te(1, c3, 1) ^ rk[10];
+    c.q[3] = te(2, c1, 2) ^ te(3, c2, 3) ^ te(0, c3, 0) ^ rk[11];
+}
+
+template <int NR, class TE>
+AG_HD void aes_ctr_block_seq(const uint32_t* rk, const AesCtrConst& cc, AesCtrSeqCache& c, uint32_t ctr, TE&& te,
+                             uint32_t out[4])
+{
+    const uint32_t s3i = ag_bswap32(ctr) ^ rk[3];
+    if ((s3i & 0x00FFFFFFu) != c.key) aes_ctr_seq_fill(rk, cc, s3i, te, c);
+    const uint32_t a = cc.k[0] ^ te(3, s3i, 3);  // round-1 column 0: the only one that moves
+    uint32_t s0 = c.q[0] ^ te(0, a, 0);
+    uint32_t s1 = c.q[1] ^ te(3, a, 3);
+    uint32_t s2 = c.q[2] ^ te(2, a, 2);
+    uint32_t s3 = c.q[3] ^ te(1, a, 1);
+#pragma unroll
+    for (int r = 3; r < NR; ++r) {
+        uint32_t t0 = te(0, s0, 0) ^ te(1, s1, 1) ^ te(2, s2, 2) ^ te(3, s3, 3) ^ rk[4 * r + 0];
+        uint32_t t1 = te(0, s1, 0) ^ te(1, s2, 1) ^ te(2, s3, 2) ^ te(3, s0, 3) ^ rk[4 * r + 1];
+        uint32_t t2 = te(0, s2, 0) ^ te(1, s3, 1) ^ te(2, s0, 2) ^ te(3, s1, 3) ^ rk[4 * r + 2];
+        uint32_t t3 = te(0, s3, 0) ^ te(1, s0, 1) ^ te(2, s1, 2) ^ te(3, s2, 3) ^ rk[4 * r + 3];
+        s0 = t0;
+        s1 = t1;
+        s2 = t2;
+        s3 = t3;
+    }
+    out[0] = (te(2, s0, 0) & 0x000000ffu) ^ (te(3, s1, 1) & 0x0000ff00u) ^ (te(0, s2, 2) & 0x00ff0000u) ^
+             (te(1, s3, 3) & 0xff000000u) ^ rk[4 * NR + 0];
+    out[1] = (te(2, s1, 0) & 0x000000ffu) ^ (te(3, s2, 1) & 0x0000ff00u) ^ (te(0, s3, 2) & 0x00ff0000u) ^
+             (te(1, s0, 3) & 0xff000000u) ^ rk[4 * NR + 1];
+    out[2] = (te(2, s2, 0) & 0x000000ffu) ^ (te(3, s3, 1) & 0x0000ff00u) ^ (te(0, s0, 2) & 0x00ff0000u) ^
+             (te(1, s1, 3) & 0xff000000u) ^ rk[4 * NR + 2];
+    out[3] = (te(2, s3, 0) & 0x000000ffu) ^ (te(3, s0, 1) & 0x0000ff00u) ^ (te(0, s1, 2) & 0x00ff0000u) ^
+             (te(1, s2, 3) & 0xff000000u) ^ rk[4 * NR + 3];
+}

@@ -256,32 +256,32 @@ AG_HD MsgDesc ag_batch_msg(const BatchParams& p, uint64_t m)
 // (gcm_ghash.vhd:259-272 order; length block gcm_ghash.vhd:257).  DEC selects the
 // GHASH source (aes_gcm.vhd:207-211).  Returns Y_t (weight H^(G-t) still to apply).
 template <int NR, bool DEC, class TE, class GH>
-AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, const MsgDesc& d, uint32_t t, uint32_t G, TE&& te,
-                          GH&& gh_g)
+AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, AesCtrSeqCache& cache, const MsgDesc& d, uint32_t t,
+                          uint32_t G, TE&& te, GH&& gh_g)
 {
-    const uint64_t a = (d.aad_len + 15) >> 4, n = (d.len + 15) >> 4;
-    const uint64_t mb = a + n + 1;
-    const uint64_t rows = (mb + G - 1) / G;
-    const uint64_t pad = rows * G - mb;
+    // block counts fit 32 bits (a message is < 2^32 blocks; AAD + payload + 1 likewise)
+    const uint32_t a = (uint32_t)((d.aad_len + 15) >> 4), n = (uint32_t)((d.len + 15) >> 4);
+    const uint32_t mb = a + n + 1;
+    const uint32_t rows = (mb + G - 1) / G;
+    const uint32_t pad = rows * G - mb;   // < G
+    const uint32_t atail = (uint32_t)(d.aad_len & 15), tail = (uint32_t)(d.len & 15);
     gf128 y = gf_zero();
-    for (uint64_t u = 0; u < rows; ++u) {
-        const uint64_t v = u * G + t;
+    uint32_t i = t - pad;                 // wraps while inside the front padding (row 0 only)
+    bool have = t >= pad;
+    for (uint32_t u = 0; u < rows; ++u, i += G, have = true) {
         if (u) y = gf_mul_table(y, gh_g);
-        if (v < pad) continue;
-        const uint64_t i = v - pad;
+        if (!have) continue;
         uint32_t s[4];
         if (i < a) {
-            const uint64_t left = d.aad_len - 16 * i;
-            ag_load_block(d.aad + 16 * i, left < 16 ? (uint32_t)left : 16u, s);
+            ag_load_block(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, s);
         } else if (i < a + n) {
-            const uint64_t j = i - a;
-            const uint64_t left = d.len - 16 * j;
-            const uint32_t nv = left < 16 ? (uint32_t)left : 16u;
+            const uint32_t j = i - a;
+            const uint32_t nv = (j == n - 1 && tail) ? tail : 16u;
             uint32_t x[4], ks[4];
-            ag_load_block(d.in + 16 * j, nv, x);
-            aes_ctr_block<NR>(rk, cc, 2u + (uint32_t)j, te, ks);
+            ag_load_block(d.in + 16 * (uint64_t)j, nv, x);
+            aes_ctr_block_seq<NR>(rk, cc, cache, 2u + j, te, ks);
             uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
-            ag_store_block(d.out + 16 * j, nv, o);
+            ag_store_block(d.out + 16 * (uint64_t)j, nv, o);
             if (DEC) {
                 s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = x[3];
             } else {

@@ -424,6 +424,8 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
         const bool valid = m < p.n_msgs;
         gf128 y = gf_zero();
         AesCtrConst cc;
+        AesCtrSeqCache cache;
+        cache.key = 0xFFFFFFFFu;  // invalid: the key only ever holds 24 bits
         if (valid) {
             const MsgDesc d = ag_batch_msg(p, m);
             const uint8_t* ivp = p.iv + 12 * m;
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
                 }
             }
             cc = aes_ctr_precompute(p.rk, iv0, iv1, iv2, te);
-            y = ag_batch_lane<NR, DEC>(p.rk, cc, d, t, (uint32_t)G, te, gh_g);
+            y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, (uint32_t)G, te, gh_g);
         }
         __syncwarp();
         // R = sum_t Y_t H^(G-t): serial Horner over the group's lanes with T_b = H
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
         }
         if (valid && t == 0) {
             uint32_t e[4];
-            aes_ctr_block<NR>(p.rk, cc, 1u, te, e);  // E_K(J0), J0 = IV || 00000001 (aes_icb.vhd:34,99)
+            aes_ctr_block_seq<NR>(p.rk, cc, cache, 1u, te, e);  // E_K(J0), J0 = IV || 00000001 (aes_icb.vhd:34,99)
             uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
                               ag_bswap32(r.w[3]) ^ e[3]};
             uint8_t* tp = p.tag + 16 * m;
@@ -500,7 +502,9 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
             iv2 |= (uint32_t)ivp[8 + j] << (8 * j);
         }
         const AesCtrConst cc = aes_ctr_precompute(p.rk, iv0, iv1, iv2, te);
-        gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, d, tid, nt, te, gh_g);
+        AesCtrSeqCache cache;
+        cache.key = 0xFFFFFFFFu;
+        gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, tid, nt, te, gh_g);
         y = gf_mul(y, wgt);
         y = warp_xor(y);
         if (lane == 0) red[tid >> 5] = y;
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
             r = warp_xor(r);
             if (tid == 0) {
                 uint32_t e[4];
-                aes_ctr_block<NR>(p.rk, cc, 1u, te, e);
+                aes_ctr_block_seq<NR>(p.rk, cc, cache, 1u, te, e);
                 uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
                                   ag_bswap32(r.w[3]) ^ e[3]};
                 uint8_t* tp = p.tag + 16 * m;

@@ -135,13 +135,15 @@ void batch_nr(const BatchParams& p, uint32_t G, const gf128& H)
         for (int j = 0; j < 12; ++j) iv[j >> 2] |= (uint32_t)ivp[j] << (8 * (j & 3));
         const AesCtrConst cc = aes_ctr_precompute(p.rk, iv[0], iv[1], iv[2], te);
         gf128 r = gf_zero();
+        AesCtrSeqCache cache;
+        cache.key = 0xFFFFFFFFu;
         for (uint32_t t = 0; t < G; ++t) {
-            gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, d, t, G, te, gh_g);
+            gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, G, te, gh_g);
             r = gf_xor(r, y);
             r = gf_mul_table(r, gh_1);
         }
         uint32_t e[4];
-        aes_ctr_block<NR>(p.rk, cc, 1u, te, e);
+        aes_ctr_block_seq<NR>(p.rk, cc, cache, 1u, te, e);
         uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
                           ag_bswap32(r.w[3]) ^ e[3]};
         uint8_t* tp = p.tag + 16 * m;

@@ -73,7 +73,7 @@ def test_batch_lanes(emul, oracle, G):
         for dec in (0, 1):
             nm = 9
             lens = rng.integers(0, 200, nm)
-            lens[0], lens[1], lens[2] = 0, 16, 1500
+            lens[0], lens[1], lens[2], lens[3] = 0, 16, 1500, 16 * 600 + 3   # > 256 blocks: counter byte carries
             alens = rng.integers(0, 70, nm)
             alens[2], alens[3] = 0, 16
             in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
