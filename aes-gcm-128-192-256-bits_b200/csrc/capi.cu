@@ -253,7 +253,7 @@ int ensure_pipeline(agcm_ctx* c)
     return AGCM_OK;
 }
 
-int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len)
+int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, bool aligned16 = true)
 {
     if (lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32) return lanes;
     if (lanes == 1024) return 1024;  // one CTA per message
@@ -261,10 +261,12 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len)
     // long messages that cannot give every warp its own message: one CTA per message
     // (>= 4 rows of the CTA-wide Horner so the per-message lane weights amortise)
     if (avg_len >= (uint64_t)c->nt * 16 * 4 && n_msgs * 32 < (uint64_t)c->ncta * c->nt) return 1024;
-    // enough groups to occupy every lane of the persistent grid, but never more
-    // lanes than blocks in a message
+    // Measured on 2^20 x 1500 B (profiles/r1_kernel_table.md): 2 lanes per message is the best
+    // trade between coalescing (32 B per message per request) and lane-combine cost when the
+    // records are 16-byte aligned, 4 lanes when they are not.  Fewer messages than lanes: widen
+    // until the persistent grid is occupied, but never more lanes than blocks in a message.
     const uint64_t total_lanes = (uint64_t)c->ncta * c->nt;
-    uint64_t g = 1;
+    uint64_t g = aligned16 ? 2 : 4;
     while (g < 32 && n_msgs * g * 2 <= total_lanes) g <<= 1;
     const uint64_t blocks = (avg_len + 15) / 16 + 1;
     while (g > 1 && g > blocks) g >>= 1;
@@ -553,12 +555,13 @@ int agcm_ghash(agcm_ctx* c, const uint8_t* d_in, uint64_t n_bytes, uint8_t* d_y1
                       c->d_counters);
 }
 
-static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, BatchParams& p, size_t n_msgs, void* stream)
+static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, BatchParams& p, size_t n_msgs, void* stream,
+                        bool aligned16 = true)
 {
     if (!c->key_set) return AGCM_E_NO_KEY;
     if (n_msgs == 0) return AGCM_OK;
     if (!p.iv || !p.tag || (decrypt && !p.ok)) return AGCM_E_BAD_ARG;
-    const int g = pick_lanes(c, lanes, n_msgs, avg_len);
+    const int g = pick_lanes(c, lanes, n_msgs, avg_len, aligned16);
     if (g < 0) return AGCM_E_BAD_ARG;
     AG_CUDA(c, cudaSetDevice(c->device));
     memcpy(p.rk, c->h_rk, sizeof(p.rk));
@@ -620,7 +623,8 @@ int agcm_batch_crypt_uniform(agcm_ctx* c, int decrypt, int lanes, const uint8_t*
     p.stride = stride;
     p.aad_len = aad_len;
     p.aad_stride = aad_stride;
-    return batch_common(c, decrypt, lanes, len, p, n_msgs, stream);
+    const bool aligned16 = ((((uintptr_t)d_in | (uintptr_t)d_out) | stride) & 15) == 0;
+    return batch_common(c, decrypt, lanes, len, p, n_msgs, stream, aligned16);
 }
 
 static int perkey_common(agcm_ctx* c, int mode, int decrypt, BatchParams& p, size_t n_msgs, void* stream)

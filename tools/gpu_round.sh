@@ -32,6 +32,9 @@ for s in $STEPS; do
     ncubatch)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch -s 2 -c 2 -f -o $OUT/${TAG}_prof_batch \
         python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_ncubatch_run.log 2>&1; echo "ncubatch rc=$?"; tail -3 $OUT/${TAG}_ncubatch_run.log ;;
+    ncuperkey)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch_perkey -s 1 -c 1 -f -o $OUT/${TAG}_prof_perkey \
+        python tools/bench_variants.py --only perkey --quick > $OUT/${TAG}_ncuperkey_run.log 2>&1; echo "ncuperkey rc=$?"; tail -3 $OUT/${TAG}_ncuperkey_run.log ;;
     sanitize)
       timeout 900 compute-sanitizer --tool memcheck python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_sanitize.log 2>&1; echo "sanitize rc=$?"; tail -8 $OUT/${TAG}_sanitize.log ;;
     scale4|scale8)
