@@ -82,6 +82,79 @@ AG_HD void aes_encrypt_otf(const uint32_t* key, uint32_t s0, uint32_t s1, uint32
              (te(1, s2, 3) & 0xff000000u) ^ k3;
 }
 
+// ---- counter mode with the schedule on the fly, per-message constants hoisted ---------
+// Stage words 0..11 (rounds 0-2) are used once per message: they go into the round-1
+// constants (aes_ctr_precompute), rk[3], and the sequential-counter cache of rounds 1+2
+// (aes_ctr_seq_fill, aes_core.cuh).  Per block the schedule resumes at word 12 from a saved
+// copy of the sliding window, and rounds 1+2 cost 5 lookups.
+template <int NK>
+struct PerKeyCtr {
+    RkStream<NK> at12;     // schedule state after word 11
+    AesCtrConst cc;
+    AesCtrSeqCache cache;
+    uint32_t rk3;
+    uint32_t rk8[4];
+};
+
+template <int NK, class TE, class SB>
+AG_HD void perkey_ctr_init(const uint32_t* key, uint32_t iv0, uint32_t iv1, uint32_t iv2, TE&& te, SB&& sb, PerKeyCtr<NK>& st)
+{
+    RkStream<NK> ks;
+    ks.init(key);
+    uint32_t rk[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) rk[i] = ks.word(i, sb);
+    st.at12 = ks;
+    st.cc = aes_ctr_precompute(rk, iv0, iv1, iv2, te);
+    st.rk3 = rk[3];
+    st.rk8[0] = rk[8]; st.rk8[1] = rk[9]; st.rk8[2] = rk[10]; st.rk8[3] = rk[11];
+    st.cache.key = 0xFFFFFFFFu;
+}
+
+template <int NK, class TE, class SB>
+AG_HD void perkey_ctr_block(PerKeyCtr<NK>& st, uint32_t ctr, TE&& te, SB&& sb, uint32_t out[4])
+{
+    constexpr int NR = NK + 6;
+    const uint32_t s3i = ag_bswap32(ctr) ^ st.rk3;
+    if ((s3i & 0x00FFFFFFu) != st.cache.key) {
+        // aes_ctr_seq_fill reads rk[3] (unused there) and rk[8..11]: hand it a view with those
+        uint32_t rkv[12];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rkv[i] = 0;
+        rkv[8] = st.rk8[0]; rkv[9] = st.rk8[1]; rkv[10] = st.rk8[2]; rkv[11] = st.rk8[3];
+        aes_ctr_seq_fill(rkv, st.cc, s3i, te, st.cache);
+    }
+    const uint32_t a = st.cc.k[0] ^ te(3, s3i, 3);
+    uint32_t s0 = st.cache.q[0] ^ te(0, a, 0);
+    uint32_t s1 = st.cache.q[1] ^ te(3, a, 3);
+    uint32_t s2 = st.cache.q[2] ^ te(2, a, 2);
+    uint32_t s3 = st.cache.q[3] ^ te(1, a, 1);
+    RkStream<NK> ks = st.at12;
+#pragma unroll
+    for (int r = 3; r < NR; ++r) {
+        const uint32_t k0 = ks.word(4 * r + 0, sb), k1 = ks.word(4 * r + 1, sb), k2 = ks.word(4 * r + 2, sb),
+                       k3 = ks.word(4 * r + 3, sb);
+        const uint32_t t0 = te(0, s0, 0) ^ te(1, s1, 1) ^ te(2, s2, 2) ^ te(3, s3, 3) ^ k0;
+        const uint32_t t1 = te(0, s1, 0) ^ te(1, s2, 1) ^ te(2, s3, 2) ^ te(3, s0, 3) ^ k1;
+        const uint32_t t2 = te(0, s2, 0) ^ te(1, s3, 1) ^ te(2, s0, 2) ^ te(3, s1, 3) ^ k2;
+        const uint32_t t3 = te(0, s3, 0) ^ te(1, s0, 1) ^ te(2, s1, 2) ^ te(3, s2, 3) ^ k3;
+        s0 = t0;
+        s1 = t1;
+        s2 = t2;
+        s3 = t3;
+    }
+    const uint32_t k0 = ks.word(4 * NR + 0, sb), k1 = ks.word(4 * NR + 1, sb), k2 = ks.word(4 * NR + 2, sb),
+                   k3 = ks.word(4 * NR + 3, sb);
+    out[0] = (te(2, s0, 0) & 0x000000ffu) ^ (te(3, s1, 1) & 0x0000ff00u) ^ (te(0, s2, 2) & 0x00ff0000u) ^
+             (te(1, s3, 3) & 0xff000000u) ^ k0;
+    out[1] = (te(2, s1, 0) & 0x000000ffu) ^ (te(3, s2, 1) & 0x0000ff00u) ^ (te(0, s3, 2) & 0x00ff0000u) ^
+             (te(1, s0, 3) & 0xff000000u) ^ k1;
+    out[2] = (te(2, s2, 0) & 0x000000ffu) ^ (te(3, s3, 1) & 0x0000ff00u) ^ (te(0, s0, 2) & 0x00ff0000u) ^
+             (te(1, s1, 3) & 0xff000000u) ^ k2;
+    out[3] = (te(2, s3, 0) & 0x000000ffu) ^ (te(3, s0, 1) & 0x0000ff00u) ^ (te(0, s1, 2) & 0x00ff0000u) ^
+             (te(1, s2, 3) & 0xff000000u) ^ k3;
+}
+
 // ---- thread-private 4-bit Shoup table ------------------------------------------
 // T[n] = n*H for the 4-bit polynomial n (bit 3 of n = x^0).  ROWS: object with
 //   void put(int n, uint4 row);   uint4 get(uint32_t be_word, int nibble /*0 = low*/);
@@ -148,7 +221,9 @@ AG_HD void ag_perkey_message(const uint32_t* key, uint32_t iv0, uint32_t iv1, ui
     uint32_t e[4];
     aes_encrypt_otf<NK>(key, 0, 0, 0, 0, te, sb, e);  // H = E_K(0^128)  (gcm_gctr.vhd:141-144)
     gf_build_table4(gf_from_le_words(e[0], e[1], e[2], e[3]), rows);
-    aes_encrypt_otf<NK>(key, iv0, iv1, iv2, 0x01000000u, te, sb, e);  // E_K(J0), J0 = IV || 00000001
+    PerKeyCtr<NK> st;
+    perkey_ctr_init<NK>(key, iv0, iv1, iv2, te, sb, st);
+    perkey_ctr_block<NK>(st, 1u, te, sb, e);  // E_K(J0), J0 = IV || 00000001 (aes_icb.vhd:34,99)
 
     gf128 y = gf_zero();
     const uint64_t a = (d.aad_len + 15) >> 4, n = (d.len + 15) >> 4;
@@ -164,7 +239,7 @@ AG_HD void ag_perkey_message(const uint32_t* key, uint32_t iv0, uint32_t iv1, ui
         const uint32_t nv = left < 16 ? (uint32_t)left : 16u;
         uint32_t x[4], ks[4];
         ag_load_block(d.in + 16 * j, nv, x);
-        aes_encrypt_otf<NK>(key, iv0, iv1, iv2, ag_bswap32(2u + (uint32_t)j), te, sb, ks);
+        perkey_ctr_block<NK>(st, 2u + (uint32_t)j, te, sb, ks);
         uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
         ag_store_block(d.out + 16 * j, nv, o);
         if (DEC) {
