@@ -77,6 +77,17 @@ def engine(engine_lib):
     eng.close()
 
 
+@pytest.fixture(scope="session")
+def engine_small(engine_lib):
+    """A context with a small, odd persistent grid (5 CTAs x 128 threads, stride 640 blocks): many
+    rows at small sizes, and a grid stride that is NOT a multiple of 256, so the counter-byte
+    cache of the stream kernel is refilled on every block."""
+    import aesgcm_b200
+    eng = aesgcm_b200.GcmEngine(0, n_cta=5, threads=128)
+    yield eng
+    eng.close()
+
+
 U8P = ctypes.POINTER(ctypes.c_uint8)
 U64P = ctypes.POINTER(ctypes.c_uint64)
 

@@ -113,41 +113,60 @@ def test_known_answer_vectors_device_api(engine, torch_mod):
 
 
 # ------------------------------------------------------------------- random messages
+def _stream_case(eng, oracle, kb, n, alen, rng):
+    key, iv, aad, pt = _rb(rng, kb), _rb(rng, 12), _rb(rng, alen), _rb(rng, n)
+    eng.set_key(key)
+    want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt, threads=8)
+    ct, tag = eng.encrypt(iv, aad, pt)
+    assert ct == want_ct, (kb, n, alen)
+    assert tag == want_tag, (kb, n, alen)
+    # decrypt + verify, then reject a flipped ciphertext bit and a flipped tag bit
+    assert eng.decrypt(iv, aad, ct, tag) == pt
+    if n:
+        bad = bytearray(ct)
+        bad[n // 2] ^= 0x01
+        _, ok = eng.decrypt(iv, aad, bytes(bad), tag, raise_on_fail=False)
+        assert not ok
+    badtag = bytearray(tag)
+    badtag[15] ^= 0x80
+    _, ok = eng.decrypt(iv, aad, ct, bytes(badtag), raise_on_fail=False)
+    assert not ok
+
+
 @pytest.mark.parametrize("kb", [16, 24, 32])
-def test_stream_random_sizes_vs_oracle(engine, oracle, torch_mod, kb):
-    torch = torch_mod
+def test_stream_random_sizes_vs_oracle(engine, oracle, kb):
+    """Default persistent grid (#SMs x 1024): empty, sub-block, ragged, one partial row, >1 row."""
     rng = np.random.default_rng(100 + kb)
-    sizes = [0, 1, 15, 16, 17, 31, 32, 33, 1500, 4096, 65536 + 3, 1024 * 151552 // 64 + 7, 3 * 16 * 151552 + 16 * 5 + 9]
+    sizes = [0, 1, 15, 16, 17, 31, 32, 33, 1500, 4096, 65536 + 3, 1024 * 151552 // 64 + 7]
+    if kb == 32:
+        sizes.append(3 * 16 * 151552 + 16 * 5 + 9)   # three rows of the 148 x 1024 grid
     for n in sizes:
         for alen in (0, 16, 20):
-            key, iv, aad, pt = _rb(rng, kb), _rb(rng, 12), _rb(rng, alen), _rb(rng, n)
-            engine.set_key(key)
-            want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt, threads=8)
-            ct, tag = engine.encrypt(iv, aad, pt)
-            assert ct == want_ct, (kb, n, alen)
-            assert tag == want_tag, (kb, n, alen)
-            # decrypt + verify, then reject a flipped ciphertext bit and a flipped tag bit
-            assert engine.decrypt(iv, aad, ct, tag) == pt
-            if n:
-                bad = bytearray(ct)
-                bad[n // 2] ^= 0x01
-                _, ok = engine.decrypt(iv, aad, bytes(bad), tag, raise_on_fail=False)
-                assert not ok
-            badtag = bytearray(tag)
-            badtag[15] ^= 0x80
-            _, ok = engine.decrypt(iv, aad, ct, bytes(badtag), raise_on_fail=False)
-            assert not ok
+            _stream_case(engine, oracle, kb, n, alen, rng)
 
 
-def test_stream_unaligned_and_in_place_device_buffers(engine, oracle, torch_mod):
+@pytest.mark.parametrize("kb", [16, 24, 32])
+def test_stream_small_odd_grid_vs_oracle(engine_small, oracle, kb):
+    """5 x 128 grid (stride 640 blocks): many rows, front padding, counter-cache refills."""
+    rng = np.random.default_rng(200 + kb)
+    row = 640 * 16
+    for n in (1, row - 1, row, row + 1, 3 * row + 89, 17 * row + 5, 256 * row // 5 + 3):
+        for alen in (0, 16, 4097):
+            _stream_case(engine_small, oracle, kb, n, alen, rng)
+
+
+@pytest.mark.parametrize("which", ["default", "small"])
+def test_stream_unaligned_and_in_place_device_buffers(engine, engine_small, oracle, torch_mod, which):
     """Device pointers at byte offsets 1 / 4 / 8 (byte and 32-bit paths), different in/out
     alignments, and exact in-place operation."""
     torch = torch_mod
     rng = np.random.default_rng(61)
     key, iv, aad = _rb(rng, 32), _rb(rng, 12), _rb(rng, 16)
+    if which == "small":
+        engine = engine_small
     engine.set_key(key)
     d_aad = _dev(torch, aad)
-    for n in (1, 100, 16 * 151552 + 33, 3 * 16 * 151552 + 5):
+    for n in ((1, 100, 16 * 151552 + 33) if which == "default" else (100, 640 * 16 * 3 + 5, 640 * 16 * 40 + 33)):
         pt = rng.integers(0, 256, n, dtype=np.uint8)
         want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt, threads=8)
         for off_in, off_out in ((1, 1), (4, 4), (8, 0), (0, 3), (16, 16)):

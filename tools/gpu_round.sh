@@ -14,7 +14,7 @@ for s in $STEPS; do
     smoke)
       timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/${TAG}_smoke.log ;;
     tests)
-      timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -15 $OUT/${TAG}_tests.log ;;
+      timeout 1500 python -m pytest tests -m gpu -q -x --timeout 900 --durations=8 > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -22 $OUT/${TAG}_tests.log ;;
     testsall)
       timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > $OUT/${TAG}_tests.log 2>&1; echo "tests rc=$?"; tail -40 $OUT/${TAG}_tests.log ;;
     bench)
