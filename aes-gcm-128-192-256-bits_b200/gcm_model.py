@@ -97,28 +97,30 @@ class gcm:
 
     # ------------------------------------------------------------------
     def get_tag(self, tag):
-        # tb/gcm_model.py:33-51
+        """Close the message (tb/gcm_model.py:33-51 semantics).
+
+        'enc': the engine's tag is appended to ``self.tag`` and compared with the DUT's `tag`
+        (a mismatch is only logged -- the scoreboard does the failing).
+        'dec': the engine verifies `tag`; on success the received tag is appended, on failure
+        its bitwise complement, so that the scoreboard is guaranteed to see a mismatch."""
+        aad, text = bytes(self._aad), bytes(self._text)
         if self.ed == 'enc':
-            ct, model_tag = self.model.encrypt(self._iv, bytes(self._aad), bytes(self._text))
-            if ct != bytes(self._out):
-                raise RuntimeError("fused pass and prefetched keystream disagree")
-            self.tag.append(model_tag)
-            log.info('Model\tTAG ' + '{:032X}'.format(int.from_bytes(model_tag, 'big')))
-            if tag is None:
-                pass  # no DUT tag to compare with (stimulus.replay)
-            elif tag == model_tag:
-                log.info('\33[92m' + "OK:\tTAGs match. " + '\33[00m')
-            else:
-                log.error('ERROR: TAGs mismatch')
+            out, computed = self.model.encrypt(self._iv, aad, text)
+            authentic = True
         else:
-            pt, ok = self.model.decrypt(self._iv, bytes(self._aad), bytes(self._text), bytes(tag), raise_on_fail=False)
-            if pt != bytes(self._out):
-                raise RuntimeError("fused pass and prefetched keystream disagree")
-            if ok:
-                self.tag.append(tag)
-                log.info('\33[92m' + "OK:\tTAGs match. " + '\33[00m' + "the message is authentic!")
-            else:
-                log.error("ERROR:\tKEY or IV incorrect, or message corrupted")
-                # Force TAG error: invert received TAG (tb/gcm_model.py:49-51)
-                not_tag = ~(int.from_bytes(tag, 'big'))
-                self.tag.append((not_tag & ((1 << 128) - 1)).to_bytes(16, 'big'))
+            out, authentic = self.model.decrypt(self._iv, aad, text, bytes(tag), raise_on_fail=False)
+            computed = None
+        if out != bytes(self._out):
+            raise RuntimeError("fused pass and prefetched keystream disagree")
+        if self.ed == 'enc':
+            self.tag.append(computed)
+            log.info("model tag %s", computed.hex().upper())
+            if tag is not None and tag != computed:
+                log.error("tag mismatch: DUT %s", bytes(tag).hex().upper())
+        elif authentic:
+            self.tag.append(tag)
+            log.info("tag verified: message is authentic")
+        else:
+            log.error("tag verification failed (wrong key/IV or corrupted message)")
+            flipped = bytes(b ^ 0xFF for b in bytes(tag))
+            self.tag.append(flipped)
