@@ -523,6 +523,49 @@ def test_counter_overflow_rejected(engine, torch_mod):
         aesgcm_b200.GcmEngine(0).encrypt(bytes(12), b"", b"abc")  # no key
 
 
+def test_error_codes(engine_lib, torch_mod):
+    """Return-code contract of the C ABI (include/aesgcm_b200.h): never throws, negative codes."""
+    torch = torch_mod
+    import ctypes
+    import aesgcm_b200
+    L = engine_lib
+    E = aesgcm_b200._lib
+    ctx = ctypes.c_void_p()
+    assert L.agcm_ctx_create_ex(ctypes.byref(ctx), 0, 300, 1024) == E.E_BAD_ARG      # > 256 CTAs
+    assert L.agcm_ctx_create_ex(ctypes.byref(ctx), 0, 8, 96) == E.E_BAD_ARG          # threads not a power of two
+    assert L.agcm_ctx_create_ex(ctypes.byref(ctx), 99, 0, 0) == E.E_NO_DEVICE
+    assert L.agcm_ctx_create(ctypes.byref(ctx), 0) == 0
+    buf = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    iv = (ctypes.c_uint8 * 12)()
+    ivp = ctypes.addressof(iv)
+    # no key yet
+    assert L.agcm_stream_crypt(ctx, 0, ivp, 0, 0, buf.data_ptr(), buf.data_ptr(), 64, buf.data_ptr(), 0, 0) == E.E_NO_KEY
+    assert L.agcm_gctr(ctx, ivp, 0, buf.data_ptr(), buf.data_ptr(), 64, 0) == E.E_NO_KEY
+    assert L.agcm_get_h(ctx, buf.data_ptr()) == E.E_NO_KEY
+    key = (ctypes.c_uint8 * 32)()
+    kp = ctypes.addressof(key)
+    assert L.agcm_set_key(ctx, 200, 0, kp, 25) == E.E_BAD_MODE
+    assert L.agcm_set_key(ctx, 256, 0, kp, 16) == E.E_BAD_MODE                        # key/mode mismatch
+    assert L.agcm_set_key(ctx, 128, 1, kp, 16) == E.E_BAD_MODE                        # pre-expanded needs 176 B
+    assert L.agcm_set_key(ctx, 256, 0, kp, 32) == 0
+    assert L.agcm_key_expand(ctx, 100, buf.data_ptr(), 1, buf.data_ptr(), 0) == E.E_BAD_MODE
+    # decrypt needs the ok flag; null data with a length; shard rules
+    assert L.agcm_stream_crypt(ctx, 1, ivp, 0, 0, buf.data_ptr(), buf.data_ptr(), 64, buf.data_ptr(), 0, 0) == E.E_BAD_ARG
+    assert L.agcm_stream_crypt(ctx, 0, ivp, 0, 0, 0, 0, 64, buf.data_ptr(), 0, 0) == E.E_BAD_ARG
+    assert L.agcm_stream_crypt(ctx, 0, ivp, 0, 5, buf.data_ptr(), buf.data_ptr(), 64, buf.data_ptr(), 0, 0) == E.E_BAD_ARG
+    assert L.agcm_stream_part(ctx, 0, ivp, 0, buf.data_ptr(), buf.data_ptr(), 60, 3, buf.data_ptr(), 0) == E.E_BAD_LEN   # ragged non-last shard
+    assert L.agcm_stream_part(ctx, 0, ivp, 2 ** 32, buf.data_ptr(), buf.data_ptr(), 64, 0, buf.data_ptr(), 0) == E.E_COUNTER_OVERFLOW
+    assert L.agcm_batch_crypt_uniform(ctx, 0, 3, buf.data_ptr(), 0, 0, 0, buf.data_ptr(), buf.data_ptr(), 16, 16,
+                                      buf.data_ptr(), 0, 2, 0) == E.E_BAD_ARG                                         # lanes = 3
+    assert L.agcm_batch_crypt_uniform(ctx, 0, 0, buf.data_ptr(), 0, 0, 0, buf.data_ptr(), buf.data_ptr(), 32, 16,
+                                      buf.data_ptr(), 0, 2, 0) == E.E_BAD_LEN                                         # stride < len
+    assert L.agcm_batch_crypt_perkey_uniform(ctx, 64, 0, buf.data_ptr(), buf.data_ptr(), 0, 0, 0, buf.data_ptr(),
+                                             buf.data_ptr(), 16, 16, buf.data_ptr(), 0, 1, 0) == E.E_BAD_MODE
+    assert L.agcm_strerror(E.E_NO_KEY) == b"no key set"
+    torch.cuda.synchronize()
+    L.agcm_ctx_destroy(ctx)
+
+
 # ------------------------------------------------------- the gcm_model.py drop-in surface
 @pytest.mark.parametrize("ed", ["enc", "dec"])
 def test_gcm_model_adapter_streaming_callbacks(oracle, ed):
