@@ -235,6 +235,18 @@ int run_finish(agcm_ctx* c, int decrypt, const uint8_t iv[12], const uint8_t* d_
     return AGCM_OK;
 }
 
+// device staging buffer for host-supplied AAD, grown on demand
+int reserve_aad_stage(agcm_ctx* c, uint64_t aad_len)
+{
+    if (aad_len <= c->aad_stage_cap) return AGCM_OK;
+    cudaFree(c->d_aad_stage);
+    c->d_aad_stage = nullptr;
+    c->aad_stage_cap = 0;
+    AG_CUDA(c, cudaMalloc(&c->d_aad_stage, aad_len));
+    c->aad_stage_cap = aad_len;
+    return AGCM_OK;
+}
+
 int ensure_pipeline(agcm_ctx* c)
 {
     if (c->pipeline_ready) return AGCM_OK;
@@ -772,12 +784,9 @@ int agcm_stream_finish_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], 
     int rc = ensure_pipeline(c);
     if (rc) return rc;
     cudaStream_t st = c->hs[0];
-    if (aad_len > c->aad_stage_cap) {
-        cudaFree(c->d_aad_stage);
-        c->d_aad_stage = nullptr;
-        c->aad_stage_cap = 0;
-        AG_CUDA(c, cudaMalloc(&c->d_aad_stage, aad_len));
-        c->aad_stage_cap = aad_len;
+    {
+        int rc_aad = reserve_aad_stage(c, aad_len);
+        if (rc_aad) return rc_aad;
     }
     if (aad_len) AG_CUDA(c, cudaMemcpyAsync(c->d_aad_stage, h_aad, aad_len, cudaMemcpyHostToDevice, st));
     if (n_parts) AG_CUDA(c, cudaMemcpyAsync(c->d_chunk_partials, h_partials16, 16 * (size_t)n_parts, cudaMemcpyHostToDevice, st));
@@ -804,12 +813,9 @@ int agcm_stream_crypt_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], c
     AG_CUDA(c, cudaSetDevice(c->device));
     int rc = ensure_pipeline(c);
     if (rc) return rc;
-    if (aad_len > c->aad_stage_cap) {
-        cudaFree(c->d_aad_stage);
-        c->d_aad_stage = nullptr;
-        c->aad_stage_cap = 0;
-        AG_CUDA(c, cudaMalloc(&c->d_aad_stage, aad_len));
-        c->aad_stage_cap = aad_len;
+    {
+        int rc_aad = reserve_aad_stage(c, aad_len);
+        if (rc_aad) return rc_aad;
     }
     if (aad_len) AG_CUDA(c, cudaMemcpyAsync(c->d_aad_stage, h_aad, aad_len, cudaMemcpyHostToDevice, c->hs[0]));
     uint64_t n_chunks = 0;
