@@ -523,6 +523,75 @@ def test_counter_overflow_rejected(engine, torch_mod):
         aesgcm_b200.GcmEngine(0).encrypt(bytes(12), b"", b"abc")  # no key
 
 
+def test_fuzz_all_paths(engine, engine_small, oracle, torch_mod):
+    """Seeded fuzz over every device entry point: random key size, direction, lengths, AAD lengths,
+    byte alignment, lane counts, shard position (incl. counters that wrap 2^32)."""
+    torch = torch_mod
+    rng = np.random.default_rng(2026)
+    for it in range(60):
+        eng = engine if it % 2 else engine_small
+        kb = int(rng.choice([16, 24, 32]))
+        key, iv = _rb(rng, kb), _rb(rng, 12)
+        eng.set_key(key if it % 3 else oracle.key_expand(key))
+        rk = oracle.key_expand(key)
+        h, _ = oracle.h_ej0(rk, iv)
+        dec = int(rng.integers(0, 2))
+        # --- one shard at a random position of a long message
+        n = int(rng.choice([0, 1, 16, 17, 255, 4096, 40000, 640 * 16 * 3 + 7]))
+        n -= n % 16 if it % 4 == 0 else 0
+        first_block = int(rng.choice([0, 1, 255, 2 ** 24 - 3, 2 ** 32 - 2 - (n + 15) // 16 - 7]))
+        after = 0 if n % 16 else int(rng.choice([0, 1, 5]))
+        off = int(rng.integers(0, 9))
+        data = rng.integers(0, 256, n, dtype=np.uint8)
+        buf_in = torch.zeros(n + 32, dtype=torch.uint8, device="cuda")
+        buf_in[off:off + n] = torch.from_numpy(data).cuda()
+        buf_out = torch.zeros(n + 32, dtype=torch.uint8, device="cuda")
+        part = torch.zeros(16, dtype=torch.uint8, device="cuda")
+        eng.stream_part_device(dec, iv, first_block, buf_in[off:off + n], buf_out[off:off + n], after, part, n_bytes=n)
+        torch.cuda.synchronize()
+        want = oracle.gctr(rk, iv, 2 + first_block, data.tobytes())
+        assert buf_out[off:off + n].cpu().numpy().tobytes() == want, (it, "gctr")
+        ct = data.tobytes() if dec else want
+        want_part = oracle.gfmul(oracle.gf_pow(h, after), oracle.ghash_absorb(h, ct))
+        assert part.cpu().numpy().tobytes() == want_part, (it, "partial")
+        # --- a small ragged batch
+        nm = int(rng.integers(1, 40))
+        lens = rng.integers(0, 5000, nm) if it % 5 else rng.integers(0, 40, nm)
+        alens = rng.integers(0, 100, nm)
+        in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.uint64)
+        msg = rng.integers(0, 256, int(in_off[-1]), dtype=np.uint8)
+        aad = rng.integers(0, 256, int(aad_off[-1]), dtype=np.uint8)
+        ivs = rng.integers(0, 256, 12 * nm, dtype=np.uint8)
+        w_out, w_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), kb, True, ivs, aad, aad_off, msg, in_off,
+                                         decrypt=False, threads=8)
+        lanes = int(rng.choice([0, 1, 2, 4, 8, 16, 32, 1024]))
+        d_out = torch.zeros(max(1, msg.size), dtype=torch.uint8, device="cuda")
+        d_tags = torch.zeros(16 * nm, dtype=torch.uint8, device="cuda")
+        d_io, d_ao = torch.from_numpy(in_off.view(np.int64)).cuda(), torch.from_numpy(aad_off.view(np.int64)).cuda()
+        src = _dev(torch, msg) if msg.size else torch.zeros(1, dtype=torch.uint8, device="cuda")
+        d_aadb = _dev(torch, aad) if aad.size else torch.zeros(1, dtype=torch.uint8, device="cuda")
+        eng.batch_crypt_device(0, _dev(torch, ivs), d_aadb, d_ao, src, d_io, d_out, d_tags, lanes=lanes, avg_len_hint=int(lens.mean()))
+        torch.cuda.synchronize()
+        assert (d_out.cpu().numpy()[:msg.size] == w_out).all(), (it, "batch ct", lanes)
+        assert (d_tags.cpu().numpy() == w_tags).all(), (it, "batch tag", lanes)
+        # --- the same messages, each under its own key, decrypt + verify
+        keys = rng.integers(0, 256, kb * nm, dtype=np.uint8)
+        p_out, p_tags = oracle.gcm_batch(keys, kb, False, ivs, aad, aad_off, msg, in_off, decrypt=False, threads=8)
+        d_back = torch.zeros_like(d_out)
+        d_ok = torch.zeros(nm, dtype=torch.uint8, device="cuda")
+        bad = int(rng.integers(0, nm))
+        tags_in = p_tags.copy()
+        tags_in[16 * bad + 7] ^= 0x08
+        eng.batch_crypt_perkey_device(kb * 8, 1, _dev(torch, keys), _dev(torch, ivs), d_aadb, d_ao,
+                                      _dev(torch, p_out) if p_out.size else src, d_io, d_back, _dev(torch, tags_in), d_ok)
+        torch.cuda.synchronize()
+        assert (d_back.cpu().numpy()[:msg.size] == msg).all(), (it, "perkey pt")
+        exp = np.ones(nm, np.uint8)
+        exp[bad] = 0
+        assert (d_ok.cpu().numpy() == exp).all(), (it, "perkey ok")
+
+
 def test_error_codes(engine_lib, torch_mod):
     """Return-code contract of the C ABI (include/aesgcm_b200.h): never throws, negative codes."""
     torch = torch_mod
