@@ -25,10 +25,10 @@ for s in $STEPS; do
       timeout 900 python tools/bench_variants.py > $OUT/${TAG}_variants.log 2>&1; echo "variants rc=$?"; cat $OUT/${TAG}_variants.log ;;
     launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
-        python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches_run.log 2>&1; echo "launches rc=$?"; tail -3 $OUT/${TAG}_launches_run.log ;;
+        python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > $OUT/${TAG}_launches_run.log 2>&1; echo "launches rc=$?"; tail -3 $OUT/${TAG}_launches_run.log ;;
     ncu)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream -s 3 -c 2 -f -o $OUT/${TAG}_prof \
-        python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_run.log 2>&1; echo "ncu rc=$?"; tail -3 $OUT/${TAG}_ncu_run.log ;;
+        python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $OUT/${TAG}_ncu_run.log 2>&1; echo "ncu rc=$?"; tail -3 $OUT/${TAG}_ncu_run.log ;;
     ncubatch)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch -s 2 -c 2 -f -o $OUT/${TAG}_prof_batch \
         python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_ncubatch_run.log 2>&1; echo "ncubatch rc=$?"; tail -3 $OUT/${TAG}_ncubatch_run.log ;;
