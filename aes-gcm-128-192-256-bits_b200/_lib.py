@@ -41,6 +41,10 @@ SIGNATURES = {
     "agcm_stream_crypt": (c_int, [c_vp, c_int, c_u8p, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u8p, c_u8p, c_vp]),
     "agcm_stream_part": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_vp]),
     "agcm_stream_finish": (c_int, [c_vp, c_int, c_u8p, c_u8p, c_int, c_u8p, c_u64, c_u64, c_u8p, c_u8p, c_vp]),
+    "agcm_peer_setup": (c_int, [c_vp, c_int, c_int, ctypes.POINTER(c_u64)]),
+    "agcm_peer_status": (c_int, [c_vp, ctypes.POINTER(c_int)]),
+    "agcm_stream_crypt_peer": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u64, c_u64, c_u8p,
+                                       c_u8p, c_vp]),
     "agcm_batch_crypt": (c_int, [c_vp, c_int, c_int, c_u64, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
                                  c_sz, c_vp]),
     "agcm_batch_crypt_uniform": (c_int, [c_vp, c_int, c_int, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u8p, c_u64, c_u64,

@@ -41,6 +41,11 @@ struct agcm_ctx {
     uint32_t* d_counters = nullptr;  // last-CTA tickets: [0] context scratch, [1+s] pipeline slot s
     uint32_t* d_pow_n = nullptr;     // cached H^n (4 BE words) for the tag finish
     uint64_t pow_n = ~0ull;          // exponent it was computed for (~0 = none)
+    // peer-memory exchange (multi-GPU)
+    uint8_t** d_peer_bufs = nullptr; // device array of world pointers
+    uint32_t* d_peer_status = nullptr;
+    int peer_rank = 0, peer_world = 0;
+    uint32_t peer_epoch = 0;
     uint32_t h_rk[60];
     uint8_t h_H[16];
     int nr = 0;
@@ -128,6 +133,7 @@ struct FuseFinish {
     uint8_t* tag_calc;
     const uint8_t* tag_expected;
     uint8_t* ok;
+    bool peer = false;  // exchange the partial with the other ranks over peer memory first
 };
 
 // GHASH partial of `n_bytes` at d_in (optionally also CTR) -> 16 B at d_partial16,
@@ -165,6 +171,13 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
             p.tag_expected = ff->tag_expected;
             p.ok = ff->ok;
             p.hn = c->d_pow_n;
+            if (ff->peer) {
+                p.peer_bufs = c->d_peer_bufs;
+                p.peer_rank = (uint32_t)c->peer_rank;
+                p.peer_world = (uint32_t)c->peer_world;
+                p.peer_epoch = ++c->peer_epoch;
+                p.peer_status = c->d_peer_status;
+            }
         }
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -369,6 +382,8 @@ void agcm_ctx_destroy(agcm_ctx* c)
     cudaFree(c->d_scratch);
     cudaFree(c->d_counters);
     cudaFree(c->d_pow_n);
+    cudaFree(c->d_peer_bufs);
+    cudaFree(c->d_peer_status);
     delete c;
 }
 
@@ -543,6 +558,61 @@ int agcm_stream_crypt(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const 
     int rc = agcm_stream_part(c, decrypt, h_iv12, 0, d_in, d_out, n_bytes, 0, part, stream);
     if (rc) return rc;
     return agcm_stream_finish(c, decrypt, h_iv12, part, 1, d_aad, aad_len, n_bytes, d_tag, d_ok, stream);
+}
+
+int agcm_peer_setup(agcm_ctx* c, int rank, int world, const uint64_t* h_peer_ptrs)
+{
+    if (!c || !h_peer_ptrs || world < 1 || world > (int)AG_PEER_MAX || rank < 0 || rank >= world) return AGCM_E_BAD_ARG;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    if (!c->d_peer_bufs) AG_CUDA(c, cudaMalloc(&c->d_peer_bufs, sizeof(uint8_t*) * AG_PEER_MAX));
+    if (!c->d_peer_status) AG_CUDA(c, cudaMalloc(&c->d_peer_status, sizeof(uint32_t)));
+    AG_CUDA(c, cudaMemset(c->d_peer_status, 0, sizeof(uint32_t)));
+    AG_CUDA(c, cudaMemcpy(c->d_peer_bufs, h_peer_ptrs, sizeof(uint64_t) * (size_t)world, cudaMemcpyHostToDevice));
+    // my own buffer starts with all flags clear; the caller barriers before the first exchange
+    AG_CUDA(c, cudaMemset(reinterpret_cast<void*>(h_peer_ptrs[rank]), 0, AG_PEER_BYTES));
+    AG_CUDA(c, cudaDeviceSynchronize());
+    c->peer_rank = rank;
+    c->peer_world = world;
+    c->peer_epoch = 0;
+    return AGCM_OK;
+}
+
+int agcm_peer_status(agcm_ctx* c, int* h_timed_out)
+{
+    if (!c || !h_timed_out) return AGCM_E_BAD_ARG;
+    uint32_t v = 0;
+    if (c->d_peer_status) AG_CUDA(c, cudaMemcpy(&v, c->d_peer_status, sizeof(v), cudaMemcpyDeviceToHost));
+    *h_timed_out = (int)v;
+    return AGCM_OK;
+}
+
+int agcm_stream_crypt_peer(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in,
+                           uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, const uint8_t* d_aad, uint64_t aad_len,
+                           uint64_t total_len, uint8_t* d_tag, uint8_t* d_ok, void* stream)
+{
+    if (!c || !h_iv12 || !d_in || !d_out || !d_tag || (decrypt && !d_ok) || (aad_len && !d_aad)) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (c->peer_world < 1) return AGCM_E_BAD_ARG;                          // agcm_peer_setup first
+    if (n_bytes == 0 || aad_len > kAadInlineMax) return AGCM_E_BAD_LEN;   // every rank must launch; bulk AAD: use the gather path
+    const uint64_t nb = (n_bytes + 15) >> 4, tb = (total_len + 15) >> 4;
+    if (tb > kMaxBlocks || first_block > tb || nb > tb - first_block || blocks_after != tb - first_block - nb)
+        return AGCM_E_BAD_LEN;
+    if (blocks_after && (n_bytes & 15)) return AGCM_E_BAD_LEN;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    FuseFinish ff;
+    ff.aad = aad_len ? d_aad : nullptr;
+    ff.aad_len = aad_len;
+    ff.ct_len = total_len;
+    ff.tag_calc = decrypt ? c->d_scratch + SC_TAGCALC : d_tag;
+    ff.tag_expected = decrypt ? d_tag : nullptr;
+    ff.ok = decrypt ? d_ok : nullptr;
+    ff.peer = true;
+    if (aad_len) {
+        int rc = ensure_pow(c, tb, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return run_stream(c, decrypt ? AG_MODE_DEC : AG_MODE_ENC, h_iv12, first_block, d_in, d_out, n_bytes, blocks_after,
+                      c->d_parts, nullptr, (cudaStream_t)stream, c->d_counters, &ff);
 }
 
 int agcm_gctr(agcm_ctx* c, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,

@@ -126,7 +126,18 @@ struct StreamParams {
     const uint8_t* tag_expected;
     uint8_t* ok;
     const uint32_t* hn;           // H^(ct blocks), precomputed (k_pow) or null
+    // exchange of the shard partials over peer memory (NVLink), fused into the same tail:
+    // peer_bufs[w] = rank w's exchange buffer mapped in this process (AG_PEER_* layout)
+    uint8_t* const* peer_bufs;
+    uint32_t peer_rank, peer_world, peer_epoch;
+    uint32_t* peer_status;        // set to 1 if a peer never showed up (bounded spin)
 };
+
+// Exchange buffer of one rank: two parities (epoch & 1) x AG_PEER_MAX slots of 16 B written by
+// the peers, then the matching 4-byte epoch flags.
+constexpr uint32_t AG_PEER_MAX = 16;
+constexpr uint32_t AG_PEER_FLAGS = 2 * AG_PEER_MAX * 16;
+constexpr uint32_t AG_PEER_BYTES = AG_PEER_FLAGS + 2 * AG_PEER_MAX * 4;
 
 // Returns Y_g for global lane g of Gt lanes; the caller multiplies by H^(Gt-g).
 // Block indices fit 32 bits (a counter range holds < 2^32 blocks).

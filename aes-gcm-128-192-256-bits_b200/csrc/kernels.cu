@@ -356,6 +356,44 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_con
                     const uint32_t o[4] = {ag_bswap32(s.w[0]), ag_bswap32(s.w[1]), ag_bswap32(s.w[2]), ag_bswap32(s.w[3])};
                     ag_store_block(p.out16, 16, o);  // natural GHASH byte order
                 }
+                if (p.peer_world) {
+                    // One tiny all-to-all over NVLink peer memory instead of a collective library
+                    // call: every rank stores its scaled partial into its slot of every peer's
+                    // exchange buffer, raises the slot's epoch flag, waits for the world's flags
+                    // in its own buffer, and XORs the slots.  Two parities make back-to-back steps
+                    // safe (a rank can be at most one step ahead of a peer that still reads).
+                    const uint32_t par = p.peer_epoch & 1u, w = tid;
+                    if (w < p.peer_world) {
+                        uint8_t* dst = p.peer_bufs[w];
+                        *reinterpret_cast<uint4*>(dst + (par * AG_PEER_MAX + p.peer_rank) * 16) =
+                            make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
+                    }
+                    __threadfence_system();
+                    if (w < p.peer_world) {
+                        volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(
+                            p.peer_bufs[w] + AG_PEER_FLAGS + (par * AG_PEER_MAX + p.peer_rank) * 4);
+                        *f = p.peer_epoch;
+                    }
+                    uint8_t* mine = p.peer_bufs[p.peer_rank];
+                    bool arrived = true;
+                    if (w < p.peer_world) {
+                        volatile uint32_t* f =
+                            reinterpret_cast<volatile uint32_t*>(mine + AG_PEER_FLAGS + (par * AG_PEER_MAX + w) * 4);
+                        uint32_t spins = 0;
+                        while (*f != p.peer_epoch) {
+                            __nanosleep(100);
+                            if (++spins > (1u << 25)) { arrived = false; break; }  // ~ seconds: give up, never hang
+                        }
+                    }
+                    __threadfence_system();
+                    gf128 t = gf_zero();
+                    if (w < p.peer_world) {
+                        const uint4 q = __ldcv(reinterpret_cast<const uint4*>(mine + (par * AG_PEER_MAX + w) * 16));
+                        t.w[0] = q.x; t.w[1] = q.y; t.w[2] = q.z; t.w[3] = q.w;
+                    }
+                    s = warp_xor(t);
+                    if (!__all_sync(0xffffffffu, arrived) && tid == 0 && p.peer_status) *p.peer_status = 1;
+                }
                 if (p.fuse_finish) {
                     FinishArgs a{p.rk, (uint32_t)NR, p.iv, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc,
                                  p.tag_expected, p.ok, p.hn, MODE != AG_MODE_GHASH_ONLY};

@@ -232,6 +232,26 @@ class GcmEngine:
                                             _dptr(aad), 0 if aad is None else aad.numel(), int(ct_len), _dptr(tag),
                                             _dptr(ok), _stream(stream)))
 
+    def peer_setup(self, rank, world, peer_ptrs):
+        """peer_ptrs: device addresses (ints) of every rank's exchange buffer, mapped in this process."""
+        arr = (ctypes.c_uint64 * world)(*[int(p) for p in peer_ptrs])
+        self._ck(self._L.agcm_peer_setup(self._ctx, int(rank), int(world), arr))
+
+    def peer_timed_out(self):
+        v = ctypes.c_int()
+        self._ck(self._L.agcm_peer_status(self._ctx, ctypes.byref(v)))
+        return bool(v.value)
+
+    def stream_crypt_peer_device(self, decrypt, iv, first_block, data_in, data_out, blocks_after, aad, total_len, tag, ok=None,
+                                 n_bytes=None, stream=None):
+        """One rank's shard + peer-memory exchange + tag finish in ONE launch (every rank calls it)."""
+        ivb = _np_u8(iv)
+        n = data_in.numel() if n_bytes is None else int(n_bytes)
+        self._ck(self._L.agcm_stream_crypt_peer(self._ctx, int(decrypt), _addr(ivb), int(first_block), _dptr(data_in),
+                                                _dptr(data_out), n, int(blocks_after), _dptr(aad),
+                                                0 if aad is None else aad.numel(), int(total_len), _dptr(tag), _dptr(ok),
+                                                _stream(stream)))
+
     def gctr_device(self, iv, first_block, data_in, data_out, n_bytes=None, stream=None):
         ivb = _np_u8(iv)
         n = data_in.numel() if n_bytes is None else int(n_bytes)

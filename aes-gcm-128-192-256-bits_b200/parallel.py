@@ -74,3 +74,32 @@ def stream_crypt_sharded(engine, decrypt, iv, aad, shard, data_in, data_out, tot
     parts = gather_partials(part, group)
     engine.stream_finish_device(decrypt, iv, parts, parts.shape[0], aad, total_bytes, tag, ok, stream=stream)
     return parts
+
+
+class PeerExchange:
+    """Peer-memory (NVLink) exchange buffers for `GcmEngine.stream_crypt_peer_device`.
+
+    Allocates one small symmetric-memory buffer per rank (torch.distributed._symmetric_memory:
+    CUDA VMM allocations mapped into every process of the node), hands the peer addresses to the
+    engine, and barriers once.  After that a sharded message costs ONE kernel launch per rank and
+    no collective call: the 16-byte partials cross NVLink as plain stores from the kernel's tail.
+    """
+
+    def __init__(self, engine, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        dev = torch.device("cuda", engine.device)
+        self.buf = symm_mem.empty(4096, dtype=torch.uint8, device=dev)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        ptrs = list(self.handle.buffer_ptrs)
+        engine.peer_setup(self.rank, self.world, ptrs)
+        dist.barrier(self.group)   # every buffer is zeroed before anyone stores into it
+        torch.cuda.synchronize(dev)
+        self.engine = engine
+
+    def crypt(self, decrypt, iv, aad, shard, data_in, data_out, total_bytes, tag, ok=None, stream=None):
+        self.engine.stream_crypt_peer_device(decrypt, iv, shard.first_block, data_in, data_out, shard.blocks_after, aad,
+                                             total_bytes, tag, ok, n_bytes=shard.n_bytes, stream=stream)

@@ -217,7 +217,7 @@ def workload_config(n_gpus):
     return {"workload": "BASELINE config 2: AES-256-GCM encrypt+tag, one stream of %d x 2^30 B, %d B AAD, counter-range "
                         "split (2^30 B per GPU)" % (n_gpus, AAD_BYTES),
             "bytes_per_gpu": SHARD_BYTES, "aad_bytes": AAD_BYTES, "key_bits": 256,
-            "parallelism": "counter-range x%d + 16 B/rank all_gather" % n_gpus if n_gpus > 1 else "single GPU",
+            "parallelism": ("counter-range x%d + 16 B/rank exchange (%s)" % (n_gpus, os.environ.get("AGCM_BENCH_EXCHANGE", "peer-memory stores fused in the kernel tail"))) if n_gpus > 1 else "single GPU",
             "l2": "inputs (1 GiB read + 1 GiB written per step) exceed the 126 MB L2; no flush needed"}
 
 
@@ -292,9 +292,19 @@ def run_ours(args, rank, world, local_rank):
     d_part = torch.zeros(16, dtype=torch.uint8, device=dev)
     d_parts = torch.zeros((world, 16), dtype=torch.uint8, device=dev)
 
+    # N > 1: the 16-byte partials cross NVLink as peer-memory stores from the kernel's own tail
+    # (one launch per rank per step); AGCM_BENCH_EXCHANGE=nccl selects part + all_gather + finish
+    exchange = os.environ.get("AGCM_BENCH_EXCHANGE", "peer") if world > 1 else "none"
+    px = None
+    if exchange == "peer":
+        from aesgcm_b200.parallel import PeerExchange
+        px = PeerExchange(eng)
+
     def step():
         if world == 1:
             eng.stream_crypt_device(0, iv, d_aad, d_in, d_out, d_tag)
+        elif px is not None:
+            px.crypt(0, iv, d_aad, shard, d_in, d_out, total, d_tag)
         else:
             eng.stream_part_device(0, iv, shard.first_block, d_in, d_out, shard.blocks_after, d_part)
             dist.all_gather_into_tensor(d_parts.view(-1), d_part)

@@ -111,6 +111,22 @@ int agcm_stream_finish(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], con
                        const uint8_t* d_aad, uint64_t aad_len, uint64_t ct_len, uint8_t* d_tag, uint8_t* d_ok,
                        void* stream);
 
+/* ---- sharded message, partials exchanged over peer memory (NVLink), one launch per rank ----
+ * agcm_peer_setup: h_peer_ptrs[w] = device address, valid in THIS process, of rank w's exchange
+ * buffer (>= 640 bytes, e.g. torch symmetric memory); zeroes this rank's buffer -- barrier before
+ * the first exchange.  world <= 16.
+ * agcm_stream_crypt_peer: agcm_stream_part + the 16-byte all-to-all + agcm_stream_finish fused in
+ * the tail of ONE kernel: the last CTA stores the scaled partial into every peer's buffer, raises
+ * an epoch flag, waits (bounded) for the world's flags in its own buffer, XORs the slots and
+ * finishes the tag on every rank.  All ranks must call it the same number of times; n_bytes > 0 on
+ * every rank; aad_len <= 4096 (else use part + gather + finish).  agcm_peer_status reports a peer
+ * that never arrived. */
+int agcm_peer_setup(agcm_ctx* ctx, int rank, int world, const uint64_t* h_peer_ptrs);
+int agcm_peer_status(agcm_ctx* ctx, int* h_timed_out);
+int agcm_stream_crypt_peer(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in,
+                           uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, const uint8_t* d_aad, uint64_t aad_len,
+                           uint64_t total_len, uint8_t* d_tag, uint8_t* d_ok, void* stream);
+
 /* ---- many independent messages under the shared key ---------------------------
  * Message i: IV d_iv12[12i..], AAD d_aad[aad_off[i]..aad_off[i+1]), payload
  * d_in[in_off[i]..in_off[i+1]) -> d_out at the same offsets, tag at d_tag[16i..]

@@ -489,6 +489,131 @@ def test_counter_range_shards_combine(engine, oracle, torch_mod):
             assert d_tag.cpu().numpy().tobytes() == want_tag, (n, world)
 
 
+def test_peer_exchange_single_gpu_emulation(engine_lib, oracle, torch_mod):
+    """agcm_stream_crypt_peer on ONE GPU: world = 1 (own buffer), and world = 2 emulated with two
+    contexts, two exchange buffers and two streams on the same device (the kernels overlap: the
+    second grid runs on the SMs the first one frees while its last CTA waits for the peer flag)."""
+    torch = torch_mod
+    import aesgcm_b200
+    from aesgcm_b200.parallel import shard_plan
+    rng = np.random.default_rng(88)
+    key, iv, aad = _rb(rng, 32), _rb(rng, 12), _rb(rng, 20)
+    d_aad = _dev(torch, aad)
+    # world = 1
+    e0 = aesgcm_b200.GcmEngine(0)
+    e0.set_key(key)
+    buf0 = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    e0.peer_setup(0, 1, [buf0.data_ptr()])
+    for n in (5, 16 * 151552 + 3):
+        pt = rng.integers(0, 256, n, dtype=np.uint8)
+        want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt, threads=8)
+        d_in = _dev(torch, pt)
+        d_out = torch.zeros_like(d_in)
+        d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+        for rep in range(3):   # epochs 1..3: both parities
+            e0.stream_crypt_peer_device(0, iv, 0, d_in, d_out, 0, d_aad, n, d_tag)
+        torch.cuda.synchronize()
+        assert d_out.cpu().numpy().tobytes() == want_ct and d_tag.cpu().numpy().tobytes() == want_tag
+        assert not e0.peer_timed_out()
+    # world = 2 on one device
+    e1 = aesgcm_b200.GcmEngine(0)
+    e1.set_key(key)
+    buf1 = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    ptrs = [buf0.data_ptr(), buf1.data_ptr()]
+    e0.peer_setup(0, 2, ptrs)
+    e1.peer_setup(1, 2, ptrs)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for n in (16 * 100 + 7, 4 * 16 * 151552 + 11):
+        pt = rng.integers(0, 256, n, dtype=np.uint8)
+        want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt, threads=8)
+        d_in = _dev(torch, pt)
+        for dec in (0, 1):
+            src = d_in if not dec else _dev(torch, np.frombuffer(want_ct, dtype=np.uint8))
+            d_out = torch.zeros_like(d_in)
+            tags = [torch.zeros(16, dtype=torch.uint8, device="cuda") for _ in range(2)]
+            oks = [torch.zeros(1, dtype=torch.uint8, device="cuda") for _ in range(2)]
+            if dec:
+                for t in tags:
+                    t.copy_(torch.from_numpy(np.frombuffer(want_tag, dtype=np.uint8).copy()))
+            torch.cuda.synchronize()
+            plan = shard_plan(n, 2)
+            for r, (eng, st) in enumerate(zip((e0, e1), streams)):
+                sh = plan[r]
+                sl = slice(sh.byte_offset, sh.byte_offset + sh.n_bytes)
+                eng.stream_crypt_peer_device(dec, iv, sh.first_block, src[sl], d_out[sl], sh.blocks_after, d_aad, n, tags[r],
+                                             oks[r], n_bytes=sh.n_bytes, stream=st)
+            torch.cuda.synchronize()
+            assert not e0.peer_timed_out() and not e1.peer_timed_out()
+            assert d_out.cpu().numpy().tobytes() == (pt.tobytes() if dec else want_ct), (n, dec)
+            if dec:
+                assert int(oks[0].item()) == 1 and int(oks[1].item()) == 1
+            else:
+                assert tags[0].cpu().numpy().tobytes() == want_tag and tags[1].cpu().numpy().tobytes() == want_tag
+    e0.close()
+    e1.close()
+
+
+def _peer_worker(rank, world, port, q):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+    import aesgcm_b200
+    from aesgcm_b200.parallel import PeerExchange, shard_plan
+    from oracle import cpu_oracle as o
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    rng = np.random.default_rng(5)
+    key = rng.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    iv = rng.integers(0, 256, 12, dtype=np.uint8).tobytes()
+    aad = rng.integers(0, 256, 16, dtype=np.uint8)
+    n = 3 * 16 * 151552 + 5
+    pt = rng.integers(0, 256, n, dtype=np.uint8)
+    eng = aesgcm_b200.GcmEngine(rank)
+    eng.set_key(key)
+    px = PeerExchange(eng)
+    sh = shard_plan(n, world)[rank]
+    dev = torch.device("cuda", rank)
+    d_in = torch.from_numpy(pt[sh.byte_offset:sh.byte_offset + sh.n_bytes].copy()).to(dev)
+    d_out = torch.zeros_like(d_in)
+    d_tag = torch.zeros(16, dtype=torch.uint8, device=dev)
+    d_aad = torch.from_numpy(aad).to(dev)
+    for _ in range(4):
+        px.crypt(0, iv, d_aad, sh, d_in, d_out, n, d_tag)
+    torch.cuda.synchronize()
+    want_ct, want_tag = o.gcm_crypt(key, iv, aad.tobytes(), pt, threads=4)
+    ok = (d_out.cpu().numpy().tobytes() == want_ct[sh.byte_offset:sh.byte_offset + sh.n_bytes]
+          and d_tag.cpu().numpy().tobytes() == want_tag and not eng.peer_timed_out())
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_exchange_two_gpus(engine_lib, torch_mod):
+    """Real NVLink peer-memory exchange: 2 processes, 2 GPUs, torch symmetric memory buffers."""
+    torch = torch_mod
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+    assert res == [(0, True), (1, True)]
+
+
 def test_gctr_and_ghash_halves(engine, oracle, torch_mod):
     torch = torch_mod
     rng = np.random.default_rng(41)
