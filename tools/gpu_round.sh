@@ -41,6 +41,9 @@ for s in $STEPS; do
       N=${s#scale}
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2953$N \
         bench.py --gpus $N --steps 30 --warmup 5 > $OUT/${TAG}_scale$N.json 2> $OUT/${TAG}_scale$N.err; echo "scale$N rc=$?"; cat $OUT/${TAG}_scale$N.json; tail -3 $OUT/${TAG}_scale$N.err ;;
+    scale8nccl)
+      AGCM_BENCH_EXCHANGE=nccl timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29548 \
+        bench.py --gpus 8 --steps 30 --warmup 5 > $OUT/${TAG}_scale8nccl.json 2> $OUT/${TAG}_scale8nccl.err; echo "scale8nccl rc=$?"; cat $OUT/${TAG}_scale8nccl.json; tail -3 $OUT/${TAG}_scale8nccl.err ;;
     refN8)
       timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29549 \
         bench.py --impl reference --gpus 8 --steps 2 --warmup 1 > $OUT/${TAG}_ref8.json 2> $OUT/${TAG}_ref8.err; echo "ref8 rc=$?"; cat $OUT/${TAG}_ref8.json; tail -3 $OUT/${TAG}_ref8.err ;;
