@@ -297,8 +297,13 @@ def run_ours(args, rank, world, local_rank):
     exchange = os.environ.get("AGCM_BENCH_EXCHANGE", "peer") if world > 1 else "none"
     px = None
     if exchange == "peer":
-        from aesgcm_b200.parallel import PeerExchange
-        px = PeerExchange(eng)
+        try:
+            from aesgcm_b200.parallel import PeerExchange
+            px = PeerExchange(eng)
+        except Exception as ex:  # symmetric memory not available on this node: use the library exchange
+            px = None
+            exchange = "nccl (peer-memory rendezvous failed: %s)" % type(ex).__name__
+            os.environ["AGCM_BENCH_EXCHANGE"] = exchange
 
     def step():
         if world == 1:
