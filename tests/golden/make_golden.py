@@ -105,7 +105,20 @@ def main():
                               "7d17cb8b4c26fc81e3284f2b7fba713d")
     with open(os.path.join(HERE, "kat_vectors.json"), "w") as f:
         json.dump({"generator": "tests/golden/make_golden.py", "vectors": recs}, f, indent=1)
-    print("wrote", len(cases), "key_exp cases and", len(recs), "KATs")
+    # ---- random cases computed by OpenSSL (stand-in for the pycryptodome call of tb/gcm_model.py:18)
+    rv = []
+    for kb in (16, 24, 32):
+        for n, alen in ((0, 0), (1, 0), (15, 7), (16, 16), (17, 20), (33, 64), (100, 1), (255, 33), (256, 0), (511, 100)):
+            key = bytes(rnd.getrandbits(8) for _ in range(kb))
+            iv = bytes(rnd.getrandbits(8) for _ in range(12))
+            aad = bytes(rnd.getrandbits(8) for _ in range(alen))
+            pt = bytes(rnd.getrandbits(8) for _ in range(n))
+            full = AESGCM(key).encrypt(iv, pt, aad)
+            rv.append({"key": key.hex(), "iv": iv.hex(), "aad": aad.hex(), "pt": pt.hex(), "ct": full[:-16].hex(),
+                       "tag": full[-16:].hex()})
+    with open(os.path.join(HERE, "openssl_random_vectors.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_golden.py (cryptography/OpenSSL AESGCM)", "vectors": rv}, f, indent=1)
+    print("wrote", len(cases), "key_exp cases,", len(recs), "KATs and", len(rv), "OpenSSL random vectors")
 
 
 if __name__ == "__main__":

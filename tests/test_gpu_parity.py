@@ -84,6 +84,16 @@ def test_known_answer_vectors_host_api(engine):
         assert engine.decrypt(iv, aad, ct, tag) == pt
 
 
+def test_committed_openssl_vectors_engine(engine):
+    """The engine against the committed OpenSSL-generated fixtures directly (no oracle in the loop)."""
+    for v in _load("openssl_random_vectors.json")["vectors"]:
+        key, iv, aad, pt = (bytes.fromhex(v[k]) for k in ("key", "iv", "aad", "pt"))
+        engine.set_key(key)
+        ct, tag = engine.encrypt(iv, aad, pt)
+        assert ct.hex() == v["ct"] and tag.hex() == v["tag"]
+        assert engine.decrypt(iv, aad, ct, tag) == pt
+
+
 def test_known_answer_vectors_device_api(engine, torch_mod):
     torch = torch_mod
     for v in _load("kat_vectors.json")["vectors"]:

@@ -54,6 +54,17 @@ def test_known_answer_vectors(oracle):
         assert pt2 == pt and tag2 == tag, v["name"]
 
 
+def test_committed_openssl_vectors(oracle):
+    vs = _load("openssl_random_vectors.json")["vectors"]
+    assert len(vs) == 30
+    for v in vs:
+        key, iv, aad, pt = (bytes.fromhex(v[k]) for k in ("key", "iv", "aad", "pt"))
+        ct, tag = oracle.gcm_crypt(key, iv, aad, pt)
+        assert ct.hex() == v["ct"] and tag.hex() == v["tag"]
+        pt2, tag2 = oracle.gcm_crypt(key, iv, aad, ct, decrypt=True)
+        assert pt2 == pt and tag2 == tag
+
+
 def test_readme_intermediates(oracle):
     # H and E_K(J0) of the 802.1AE vectors
     key = bytes.fromhex("AD7A2BD03EAC835A6F620FDCB506B345")
