@@ -317,8 +317,9 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_con
     gf128 y = ag_stream_lane<NR, MODE, ALIGNED>(p, g, Gt, te, gh);
     if (MODE == AG_MODE_CTR_ONLY) return;
 
-    // lane weight H^(Gt-g) = (H^NT)^(ncta-1-cta) * H^(NT-tid)
-    y = gf_mul(y, p.key->hpow_thread[nt - tid]);
+    // lane weight H^(Gt-g) = (H^NT)^(ncta-1-cta) * H^(NT-tid); lanes that absorbed nothing (short
+    // messages leave most of the grid idle) skip the bit-serial product
+    if (__any_sync(0xffffffffu, (y.w[0] | y.w[1] | y.w[2] | y.w[3]) != 0)) y = gf_mul(y, p.key->hpow_thread[nt - tid]);
     y = warp_xor(y);
     gf128* red = reinterpret_cast<gf128*>(ag_smem + SM_MISC);
     if (lane == 0) red[tid >> 5] = y;
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
         AesCtrSeqCache cache;
         cache.key = 0xFFFFFFFFu;
         gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, tid, nt, te, gh_g);
-        y = gf_mul(y, wgt);
+        if (__any_sync(0xffffffffu, (y.w[0] | y.w[1] | y.w[2] | y.w[3]) != 0)) y = gf_mul(y, wgt);
         y = warp_xor(y);
         if (lane == 0) red[tid >> 5] = y;
         __syncthreads();
