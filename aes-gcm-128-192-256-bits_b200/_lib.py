@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libaesgcm_b200.so")
+SO_PATH = os.environ.get("AGCM_LIB_PATH") or os.path.join(_HERE, "libaesgcm_b200.so")  # env: development builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0

@@ -22,7 +22,7 @@
 // registers), so the 64-register budget of the 1024-thread CTA is not blown by
 // the compiler hoisting all sixteen 128-bit loads: a compiler-level memory fence
 // after the second group of four.
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && (!defined(AG_NT_MAX) || AG_NT_MAX > 512)
 #define AG_LOOKUP_FENCE(r) do { if ((r) == 1) asm volatile("" ::: "memory"); } while (0)
 #else
 #define AG_LOOKUP_FENCE(r) do { } while (0)
