@@ -1,6 +1,6 @@
 // sm_100a kernels of the AES-GCM engine.
 //
-// Shared-memory plan (one persistent 1024-thread CTA per SM, 194 KB of the 227 KB):
+// Shared-memory plan (one persistent 512-thread CTA per SM, 194 KB of the 227 KB):
 //
 //   [0      , 64 KB)  AES_A : 256 entries x 256 B; entry x = 32 lane-private copies
 //                     of Te0[x] (128 B) then 32 copies of Te1[x] (128 B)

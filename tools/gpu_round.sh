@@ -27,10 +27,10 @@ for s in $STEPS; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
         python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > $OUT/${TAG}_launches_run.log 2>&1; echo "launches rc=$?"; tail -3 $OUT/${TAG}_launches_run.log ;;
     ncu)
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream -s 3 -c 2 -f -o $OUT/${TAG}_prof \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream -s 3 -c 1 -f -o $OUT/${TAG}_prof \
         python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $OUT/${TAG}_ncu_run.log 2>&1; echo "ncu rc=$?"; tail -3 $OUT/${TAG}_ncu_run.log ;;
     ncubatch)
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch -s 2 -c 2 -f -o $OUT/${TAG}_prof_batch \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch -s 2 -c 1 -f -o $OUT/${TAG}_prof_batch \
         python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_ncubatch_run.log 2>&1; echo "ncubatch rc=$?"; tail -3 $OUT/${TAG}_ncubatch_run.log ;;
     ncuperkey)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch_perkey -s 1 -c 1 -f -o $OUT/${TAG}_prof_perkey \
