@@ -273,7 +273,7 @@ AG_HD MsgDesc ag_batch_msg(const BatchParams& p, uint64_t m)
 // GHASH source (aes_gcm.vhd:207-211).  Returns Y_t (weight H^(G-t) still to apply).
 template <int NR, bool DEC, class TE, class GH>
 AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, AesCtrSeqCache& cache, const MsgDesc& d, uint32_t t,
-                          uint32_t G, TE&& te, GH&& gh_g)
+                          uint32_t G, TE&& te, GH&& gh_g, uint32_t ej0[4])
 {
     // block counts fit 32 bits (a message is < 2^32 blocks; AAD + payload + 1 likewise)
     const uint32_t a = (uint32_t)((d.aad_len + 15) >> 4), n = (uint32_t)((d.len + 15) >> 4);
@@ -290,12 +290,27 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, AesCtrSeqCa
         uint32_t s[4];
         if (i < a) {
             ag_load_block(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, s);
-        } else if (i < a + n) {
+        } else {
+            // The length block always lands on lane G-1 of the last row.  That lane has no payload
+            // block in this row, so it spends the row's AES pass on E_K(J0) (counter 1,
+            // src/aes_icb.vhd:34,99): the tag mask costs no pass of its own.
+            const bool is_len = (i == a + n);
             const uint32_t j = i - a;
+            uint32_t ks[4];
+            aes_ctr_block_seq<NR>(rk, cc, cache, is_len ? 1u : 2u + j, te, ks);
+            if (is_len) {
+                ej0[0] = ks[0]; ej0[1] = ks[1]; ej0[2] = ks[2]; ej0[3] = ks[3];
+                // [len(A)]64 || [len(C)]64 in bits, big-endian (gcm_ghash.vhd:257)
+                const uint64_t ab = d.aad_len * 8, cb = d.len * 8;
+                y.w[0] ^= (uint32_t)(ab >> 32);
+                y.w[1] ^= (uint32_t)ab;
+                y.w[2] ^= (uint32_t)(cb >> 32);
+                y.w[3] ^= (uint32_t)cb;
+                continue;
+            }
             const uint32_t nv = (j == n - 1 && tail) ? tail : 16u;
-            uint32_t x[4], ks[4];
+            uint32_t x[4];
             ag_load_block(d.in + 16 * (uint64_t)j, nv, x);
-            aes_ctr_block_seq<NR>(rk, cc, cache, 2u + j, te, ks);
             uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
             ag_store_block(d.out + 16 * (uint64_t)j, nv, o);
             if (DEC) {
@@ -304,14 +319,6 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, AesCtrSeqCa
                 if (nv != 16) ag_mask_block(o, nv);
                 s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
             }
-        } else {
-            // [len(A)]64 || [len(C)]64 in bits, big-endian (gcm_ghash.vhd:257)
-            const uint64_t ab = d.aad_len * 8, cb = d.len * 8;
-            y.w[0] ^= (uint32_t)(ab >> 32);
-            y.w[1] ^= (uint32_t)ab;
-            y.w[2] ^= (uint32_t)(cb >> 32);
-            y.w[3] ^= (uint32_t)cb;
-            continue;
         }
         y.w[0] ^= ag_bswap32(s[0]);
         y.w[1] ^= ag_bswap32(s[1]);

@@ -465,6 +465,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
         AesCtrConst cc;
         AesCtrSeqCache cache;
         cache.key = 0xFFFFFFFFu;  // invalid: the key only ever holds 24 bits
+        uint32_t e[4] = {0, 0, 0, 0};  // E_K(J0): produced by lane G-1 (the one that meets the length block)
         if (valid) {
             const MsgDesc d = ag_batch_msg(p, m);
             const uint8_t* ivp = p.iv + 12 * m;
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
                 }
             }
             cc = aes_ctr_precompute(p.rk, iv0, iv1, iv2, te);
-            y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, (uint32_t)G, te, gh_g);
+            y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, (uint32_t)G, te, gh_g, e);
         }
         __syncwarp();
         // R = sum_t Y_t H^(G-t): serial Horner over the group's lanes with T_b = H
@@ -495,9 +496,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
             r = gf_xor(r, yk);
             r = gf_mul_table(r, gh_1);
         }
-        if (valid && t == 0) {
-            uint32_t e[4];
-            aes_ctr_block_seq<NR>(p.rk, cc, cache, 1u, te, e);  // E_K(J0), J0 = IV || 00000001 (aes_icb.vhd:34,99)
+        if (valid && t == G - 1) {
             uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
                               ag_bswap32(r.w[3]) ^ e[3]};
             uint8_t* tp = p.tag + 16 * m;
@@ -543,7 +542,12 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
         const AesCtrConst cc = aes_ctr_precompute(p.rk, iv0, iv1, iv2, te);
         AesCtrSeqCache cache;
         cache.key = 0xFFFFFFFFu;
-        gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, tid, nt, te, gh_g);
+        uint32_t e[4] = {0, 0, 0, 0};
+        gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, tid, nt, te, gh_g, e);
+        if (tid == nt - 1) {   // the lane that met the length block also produced E_K(J0)
+            uint32_t* ej = reinterpret_cast<uint32_t*>(ag_smem + SM_MISC + 1024);
+            ej[0] = e[0]; ej[1] = e[1]; ej[2] = e[2]; ej[3] = e[3];
+        }
         if (__any_sync(0xffffffffu, (y.w[0] | y.w[1] | y.w[2] | y.w[3]) != 0)) y = gf_mul(y, wgt);
         y = warp_xor(y);
         if (lane == 0) red[tid >> 5] = y;
@@ -552,8 +556,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
             gf128 r = (tid < (nt >> 5)) ? red[tid] : gf_zero();
             r = warp_xor(r);
             if (tid == 0) {
-                uint32_t e[4];
-                aes_ctr_block_seq<NR>(p.rk, cc, cache, 1u, te, e);
+                const uint32_t* e = reinterpret_cast<const uint32_t*>(ag_smem + SM_MISC + 1024);
                 uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
                                   ag_bswap32(r.w[3]) ^ e[3]};
                 uint8_t* tp = p.tag + 16 * m;

@@ -137,13 +137,14 @@ void batch_nr(const BatchParams& p, uint32_t G, const gf128& H)
         gf128 r = gf_zero();
         AesCtrSeqCache cache;
         cache.key = 0xFFFFFFFFu;
+        uint32_t e[4] = {0, 0, 0, 0};
         for (uint32_t t = 0; t < G; ++t) {
-            gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, G, te, gh_g);
+            uint32_t el[4] = {0, 0, 0, 0};
+            gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, G, te, gh_g, el);
+            if (t == G - 1) { e[0] = el[0]; e[1] = el[1]; e[2] = el[2]; e[3] = el[3]; }
             r = gf_xor(r, y);
             r = gf_mul_table(r, gh_1);
         }
-        uint32_t e[4];
-        aes_ctr_block_seq<NR>(p.rk, cc, cache, 1u, te, e);
         uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
                           ag_bswap32(r.w[3]) ^ e[3]};
         uint8_t* tp = p.tag + 16 * m;
