@@ -296,7 +296,9 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, AesCtrSeqCa
             // src/aes_icb.vhd:34,99): the tag mask costs no pass of its own.
             const bool is_len = (i == a + n);
             const uint32_t j = i - a;
-            uint32_t ks[4];
+            const uint32_t nv = (j == n - 1 && tail) ? tail : 16u;
+            uint32_t x[4] = {0, 0, 0, 0}, ks[4];
+            if (!is_len) ag_load_block(d.in + 16 * (uint64_t)j, nv, x);   // in flight during the AES rounds
             aes_ctr_block_seq<NR>(rk, cc, cache, is_len ? 1u : 2u + j, te, ks);
             if (is_len) {
                 ej0[0] = ks[0]; ej0[1] = ks[1]; ej0[2] = ks[2]; ej0[3] = ks[3];
@@ -308,9 +310,6 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, AesCtrSeqCa
                 y.w[3] ^= (uint32_t)cb;
                 continue;
             }
-            const uint32_t nv = (j == n - 1 && tail) ? tail : 16u;
-            uint32_t x[4];
-            ag_load_block(d.in + 16 * (uint64_t)j, nv, x);
             uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
             ag_store_block(d.out + 16 * (uint64_t)j, nv, o);
             if (DEC) {
