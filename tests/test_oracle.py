@@ -65,6 +65,24 @@ def test_committed_openssl_vectors(oracle):
         assert pt2 == pt and tag2 == tag
 
 
+def test_reference_model_traces(oracle):
+    """Traces recorded from the reference's own tb/gcm_model.py (tests/golden/make_model_traces.py):
+    the oracle reproduces its per-call outputs and tags, and the forced-mismatch tag is the
+    bitwise complement of the received one (tb/gcm_model.py:47-51)."""
+    cases = _load("gcm_model_traces.json")["cases"]
+    assert len(cases) == 15
+    for c in cases:
+        key = bytes.fromhex(c["key"]["data"])
+        iv = bytes.fromhex(c["iv"]["data"])
+        aad, pt = bytes.fromhex(c["aad"]), bytes.fromhex(c["pt"])
+        ct, tag = oracle.gcm_crypt(key, iv, aad, pt)
+        assert "".join(c["enc_data_out"]) == ct.hex() and c["enc_tag"] == [tag.hex()]
+        assert all(len(x) <= 32 for x in c["enc_data_out"])            # one <=16-byte block per call
+        assert "".join(c["dec_good"]["data_out"]) == pt.hex() and c["dec_good"]["tag"] == [tag.hex()]
+        rx = bytes.fromhex(c["dec_bad"]["rx_tag"])
+        assert c["dec_bad"]["tag"] == [bytes(b ^ 0xFF for b in rx).hex()]
+
+
 def test_readme_intermediates(oracle):
     # SURVEY appendix: H and E_K(J0) of the 802.1AE vectors
     key = bytes.fromhex("AD7A2BD03EAC835A6F620FDCB506B345")
