@@ -185,8 +185,11 @@ def replay(config, model_factory, rng=None, pre_expanded=False, expand_key=None)
     pre_expanded: hand the model the Nr+1 stages instead of the raw key (the -x / rmexp flow,
     tb/gcm_test.py:103-106); expand_key(key_hex, size_str) -> list[int] is then required.
     Returns a dict with the resolved data, the word lists and the model outputs."""
+    # one RNG stream, consumed in the reference's order: config_data, then the AAD words, then the
+    # data words (tb/gcm_gctr.py:229-332, 337-437)
+    if rng is None:
+        rng = random.Random(config.get('seed', 0))
     cfg, data = resolve_config(config, rng)
-    rng = rng or random.Random(cfg.get('seed', 0) + 1)
     key = dict(data['key'])
     if pre_expanded:
         exp = bytes(expand_key(key['data'], str(cfg.get('aes_mode', '128'))))

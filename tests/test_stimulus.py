@@ -120,3 +120,40 @@ def test_replay_with_oracle_backed_model(tmp_path, oracle):
                       expand_key=lambda k, s: list(oracle.key_expand(bytes.fromhex(k))))
         assert b"".join(r['dec_words']) == b"".join(r['pt_words'])
         assert r['dec_tag'] == r['tag']
+
+
+def _traces():
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "stimulus_traces.json")) as f:
+        return json.load(f)["cases"]
+
+
+def test_resolve_config_matches_reference_gcm_gctr():
+    """tests/golden/stimulus_traces.json was recorded from the reference's own tb/gcm_gctr.py
+    (config_data + encrypt_data driven alone): same seed -> same key / IV / counts / delays and
+    the same AAD / data word lists."""
+    cases = _traces()
+    assert len(cases) == 6
+    for c in cases:
+        rng = random.Random(c["config_in"]["seed"])
+        cfg, d = st.resolve_config(c["config_in"], rng)
+        assert d["key"] == c["data"]["key"] and d["iv"] == c["data"]["iv"], c["config_in"]["seed"]
+        assert d["aad_n_bytes"] == c["data"]["aad_n_bytes"] and d["pt_n_bytes"] == c["data"]["pt_n_bytes"]
+        assert d["delays"] == c["data"]["delays"]
+        assert cfg["aes_mode"] == c["config_out"]["aes_mode"] and cfg["key"] == c["config_out"]["key"]
+        aad_words = st.split_words(cfg["aad"], d["aad_n_bytes"], rng)
+        pt_words = st.split_words(cfg["data"], d["pt_n_bytes"], rng)
+        assert [w.hex() for w in aad_words] == c["aad_words"]
+        assert [w.hex() for w in pt_words] == c["pt_words"]
+
+
+def test_key_pin_encodings_match_reference_gcm_gctr(oracle):
+    """load_key / load_pre_exp_key pin writes of the reference (tb/gcm_gctr.py:144-214)."""
+    for c in _traces():
+        key = c["data"]["key"]
+        mode = c["config_out"]["aes_mode"]
+        assert c["load_key"] == [[st.key_mode_val(mode), "%064X" % st.pack_key_word(key)]]
+        exp = oracle.key_expand(bytes.fromhex(key["data"]))
+        want = [[v, "%064X" % w] for v, w in st.pack_pre_expanded_key(exp)]
+        assert c["load_pre_exp_key"] == want
