@@ -28,7 +28,7 @@ _KS_WINDOW = 1 << 16  # bytes of keystream fetched per device call
 
 
 class gcm:
-    def __init__(self, key, icb, ed, device=0, engine=None):
+    def __init__(self, key, icb, ed, device=0, engine=None, prefetch=True):
         # tb/gcm_model.py:8-18
         self.ed = ed
         self.data_out = []
@@ -49,6 +49,9 @@ class gcm:
         self._ks_base = 0                 # ... covering message bytes [_ks_base, _ks_base + len(_ks))
         self._zeros = None
         self._ksbuf = None
+        # prefetch=False: no keystream window; every callback is its own device GCTR call
+        # (H2D of the block, agcm_gctr, D2H): the XOR itself then also happens on the GPU
+        self._prefetch = bool(prefetch)
 
     # ------------------------------------------------------------------
     def _keystream(self, pos, n):
@@ -74,10 +77,27 @@ class gcm:
             n -= take
         return bytes(out)
 
+    def _crypt_on_device(self, pos, data):
+        import numpy as np
+        import torch
+        lead = pos % 16                       # keep the counter block-aligned for a mid-block call
+        buf = np.zeros(lead + len(data), dtype=np.uint8)
+        buf[lead:] = np.frombuffer(data, dtype=np.uint8)
+        with torch.cuda.device(self.model.device):
+            d = torch.from_numpy(buf).cuda()
+            o = torch.empty_like(d)
+            self.model.gctr_device(self._iv, pos // 16, d, o)
+            return o.cpu().numpy()[lead:].tobytes()
+
     def _crypt(self, data):
         data = bytes(data)
-        ks = self._keystream(len(self._text), len(data))
-        res = (int.from_bytes(data, 'big') ^ int.from_bytes(ks, 'big')).to_bytes(len(data), 'big') if data else b""
+        if not data:
+            res = b""
+        elif self._prefetch:
+            ks = self._keystream(len(self._text), len(data))
+            res = (int.from_bytes(data, 'big') ^ int.from_bytes(ks, 'big')).to_bytes(len(data), 'big')
+        else:
+            res = self._crypt_on_device(len(self._text), data)
         self._text += data
         self._out += res
         return res

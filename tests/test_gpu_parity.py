@@ -825,6 +825,25 @@ def test_adapter_reproduces_reference_model_traces():
             assert [t.hex() for t in d.tag] == c[label]["tag"], label
 
 
+def test_adapter_without_prefetch_matches(oracle):
+    """prefetch=False: every callback is its own device GCTR call (no host-side XOR); odd call sizes."""
+    from aesgcm_b200 import gcm_model
+    rng = np.random.default_rng(66)
+    key, iv, aad, pt = _rb(rng, 24), _rb(rng, 12), _rb(rng, 30), _rb(rng, 200)
+    want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt)
+    for prefetch in (False, True):
+        m = gcm_model.gcm({'data': key.hex(), 'n_bytes': 24}, {'data': iv.hex(), 'n_bytes': 12}, 'enc', prefetch=prefetch)
+        m.load_aad(aad)
+        pos = 0
+        for step in (16, 16, 5, 11, 16, 1, 40, 95):          # byte-granular streaming like pycryptodome's encrypt()
+            m.load_plain_text(pt[pos:pos + step])
+            assert m.data_out[-1] == want_ct[pos:pos + step]
+            pos += step
+        assert pos == len(pt)
+        m.get_tag(want_tag)
+        assert m.tag == [want_tag]
+
+
 def test_readme_vectors_through_adapter():
     """The two command lines of README.md:251,257 (802.1AE vectors), via the model surface."""
     from aesgcm_b200 import gcm_model
