@@ -374,6 +374,11 @@ void agcm_ctx_destroy(agcm_ctx* c)
     }
     for (cudaEvent_t e : c->tev)
         if (e) cudaEventDestroy(e);
+    // key hygiene: wipe the stage keys, H, its powers and tables, and the host copy
+    if (c->d_key) cudaMemset(c->d_key, 0, sizeof(KeyDev));
+    if (c->d_scratch) cudaMemset(c->d_scratch, 0, SC_BYTES);
+    memset(c->h_rk, 0, sizeof(c->h_rk));
+    memset(c->h_H, 0, sizeof(c->h_H));
     cudaFree(c->d_chunk_partials);
     cudaFree(c->d_aad_stage);
     cudaFree(c->d_te0);
