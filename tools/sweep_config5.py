@@ -42,7 +42,7 @@ def main():
                 d_aad = torch.randint(0, 256, (max(1, n_msgs * astride),), dtype=torch.uint8, device="cuda")
                 d_iv = torch.randint(0, 256, (n_msgs * 12,), dtype=torch.uint8, device="cuda")
                 d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
-                use_stream = size >= (32 << 20)
+                use_stream = per >= (32 << 20)   # few huge messages (payload + AAD): one stream call each
 
                 def run():
                     if use_stream:
