@@ -51,3 +51,22 @@ def test_fails_loudly_without_device(engine_lib):
 def test_strerror(engine_lib):
     assert engine_lib.agcm_strerror(0) == b"ok"
     assert b"2^32-2" in engine_lib.agcm_strerror(-3)
+
+
+def test_header_is_plain_c_and_example_links(engine_lib, tmp_path):
+    """include/aesgcm_b200.h compiles as C99 and a gcc-only client links against the library."""
+    import shutil
+    import subprocess
+    import aesgcm_b200
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    pkg = os.path.dirname(aesgcm_b200._lib.SO_PATH)
+    exe = str(tmp_path / "abi_example")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi_example.c"), "-L", pkg, "-laesgcm_b200", "-Wl,-rpath," + pkg,
+                           "-o", exe])
+    import torch
+    if torch.cuda.is_available():
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and "abi_example ok" in out.stdout, out.stdout + out.stderr

@@ -727,6 +727,24 @@ def test_fuzz_all_paths(engine, engine_small, oracle, torch_mod):
         assert (d_ok.cpu().numpy() == exp).all(), (it, "perkey ok")
 
 
+def test_plain_c_client(engine_lib, tmp_path):
+    """tests/abi_example.c: a gcc-only C99 program drives the C ABI (802.1AE vector of README.md:251)."""
+    import shutil
+    import subprocess
+    import aesgcm_b200
+    from conftest import ROOT
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    pkg = os.path.dirname(aesgcm_b200._lib.SO_PATH)
+    exe = str(tmp_path / "abi_example")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi_example.c"), "-L", pkg, "-laesgcm_b200", "-Wl,-rpath," + pkg,
+                           "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "abi_example ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_error_codes(engine_lib, torch_mod):
     """Return-code contract of the C ABI (include/aesgcm_b200.h): never throws, negative codes."""
     torch = torch_mod
