@@ -79,6 +79,22 @@ def main():
                 print(json.dumps(r), flush=True)
                 res.append(r)
             del d_buf, d_out
+    if args.only in ("", "keys"):
+        # aes_kexp on the device: 2^20 distinct keys -> round keys (tb/key_exp.py:118 semantics), and set_key latency
+        import time
+        for kb in (16, 24, 32):
+            n_keys = 1 << 20
+            d_keys = torch.randint(0, 256, (n_keys * kb,), dtype=torch.uint8, device="cuda")
+            d_rk = torch.empty((n_keys, 4 * kb + 112), dtype=torch.uint8, device="cuda")
+            ms = timeit(lambda: eng.expand_keys_device(kb * 8, d_keys, d_rk), iters)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                eng.set_key(bytes(range(kb)))
+            sk_us = (time.perf_counter() - t0) / 20 * 1e6
+            r = {"path": "k_key_expand, 2^20 keys", "aes": kb * 8, "op": "key schedule", "ms": round(ms, 4),
+                 "GBps": round(n_keys * (4 * kb + 112) / ms / 1e6, 1), "Mkeys_per_s": round(n_keys / ms / 1e3, 1),
+                 "set_key_us": round(sk_us, 1)}
+            print(json.dumps(r), flush=True)
     if args.only in ("", "perkey"):
         # BASELINE config 4: AES-256 decrypt+verify, distinct key per message, 64 B AAD
         alen = 64
