@@ -24,6 +24,12 @@
  *     src/aes_icb.vhd:65,114,119).
  *   - There is no CPU fallback.  Every call needs a CUDA device of compute
  *     capability 10.x.
+ *   - Limits: payload per IV <= (2^32-2) x 16 bytes (the 32-bit block counter); a batched
+ *     message holds fewer than 2^32 blocks of AAD + payload; agcm_stream_finish takes up to
+ *     1024 shard partials; agcm_peer_setup up to 16 ranks; the host-buffer stream call up to
+ *     1024 x 64 MiB per call.  AAD of any length (bytes 4097.. run through the grid-wide GHASH).
+ *   - Device buffers may have any byte alignment; 16-byte alignment selects the 128-bit
+ *     load/store path (4-byte alignment a 32-bit path, anything else bytes).
  */
 #ifndef AESGCM_B200_H
 #define AESGCM_B200_H
