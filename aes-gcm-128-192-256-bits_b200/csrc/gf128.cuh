@@ -18,10 +18,10 @@
 #define AG_HD inline
 #endif
 
-// Keeps at most 8 of the 16 row lookups of one table product in flight (32
-// registers), so the 64-register budget of the 1024-thread CTA is not blown by
-// the compiler hoisting all sixteen 128-bit loads: a compiler-level memory fence
-// after the second group of four.
+// Only for builds with 1024-thread CTAs (AG_NT_MAX > 512, 64 registers per thread): keeps at
+// most 8 of the 16 row lookups of one table product in flight (32 registers) with a
+// compiler-level memory fence after the second group of four.  The default 512-thread build has
+// 128 registers and lets the compiler hoist all sixteen 128-bit loads.
 #if defined(__CUDA_ARCH__) && (!defined(AG_NT_MAX) || AG_NT_MAX > 512)
 #define AG_LOOKUP_FENCE(r) do { if ((r) == 1) asm volatile("" ::: "memory"); } while (0)
 #else

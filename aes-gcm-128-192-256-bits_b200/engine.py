@@ -2,7 +2,7 @@
 
 `GcmEngine` owns one `agcm_ctx` on one GPU.  Two families of calls:
 
-* host-buffer calls (`encrypt`, `decrypt`, `encrypt_batch_uniform`, ...) take
+* host-buffer calls (`encrypt`, `decrypt`, `crypt_batch_uniform_host`, `stream_part_host`, ...) take
   bytes / numpy arrays / pinned torch CPU tensors and go through the library's
   chunked H2D -> kernel -> D2H pipeline: this is the call a user of the reference
   model makes (tb/gcm_model.py:8-51 semantics, whole message at a time);
@@ -10,6 +10,9 @@
   `stream_finish_device`) take torch CUDA uint8 tensors already resident in HBM.
 
 All arithmetic runs in the CUDA library; nothing here computes AES or GHASH.
+
+A context owns scratch buffers (per-CTA partials, tickets, the cached H^n): issue the calls of one
+engine on ONE CUDA stream at a time; use one engine per concurrently active stream.
 """
 import ctypes
 
