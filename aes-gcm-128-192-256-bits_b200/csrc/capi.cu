@@ -466,25 +466,23 @@ int agcm_set_key(agcm_ctx* c, int mode, int pre_expanded, const uint8_t* h_key, 
     AG_CUDA(c, cudaSetDevice(c->device));
     c->key_set = false;
     c->pow_n = ~0ull;
-    uint8_t* d_rk = reinterpret_cast<uint8_t*>(c->d_key) + offsetof(KeyDev, rk);
-    if (pre_expanded) {
-        // config/config_aes_kprexp.py:66-95: Nr+1 user-loaded stages, used as they are
-        AG_CUDA(c, cudaMemcpy(d_rk, h_key, key_len, cudaMemcpyHostToDevice));
-    } else {
-        uint8_t* d_raw = c->d_scratch + SC_KEY;
-        AG_CUDA(c, cudaMemcpy(d_raw, h_key, key_len, cudaMemcpyHostToDevice));
-        AG_CUDA(c, ag_launch_key_expand(d_raw, 1, mode / 8, c->d_te0, d_rk, nullptr));
-        c->launches++;
-    }
-    const uint32_t nr_u = (uint32_t)nr;
-    AG_CUDA(c, cudaMemcpy(reinterpret_cast<uint8_t*>(c->d_key) + offsetof(KeyDev, nr), &nr_u, 4, cudaMemcpyHostToDevice));
-    AG_CUDA(c, ag_launch_key_setup(c->d_key, c->d_te0, c->nt, c->ncta, nullptr));
-    c->launches++;
+    KeyIn in;
+    memset(&in, 0, sizeof(in));
+    memcpy(in.w, h_key, key_len);   // LE words == the byte string
+    in.key_bytes = (uint32_t)mode / 8;
+    in.nr = (uint32_t)nr;
+    in.pre_expanded = pre_expanded ? 1u : 0u;
+    // no kernel of an earlier call may still be reading the key material this launch overwrites
     AG_CUDA(c, cudaDeviceSynchronize());
+    AG_CUDA(c, ag_launch_key_setup(c->d_key, in, c->d_te0, c->nt, c->ncta, nullptr));
+    c->launches++;
+    // one readback: rk[60] | nr, nt, ncta, pad | H are the first 272 bytes of KeyDev
+    static_assert(offsetof(KeyDev, rk) == 0 && offsetof(KeyDev, H) == 256, "KeyDev head layout");
+    uint32_t head[68];
+    AG_CUDA(c, cudaMemcpy(head, c->d_key, sizeof(head), cudaMemcpyDeviceToHost));
     memset(c->h_rk, 0, sizeof(c->h_rk));
-    AG_CUDA(c, cudaMemcpy(c->h_rk, d_rk, (size_t)16 * (nr + 1), cudaMemcpyDeviceToHost));
-    uint32_t hw[4];
-    AG_CUDA(c, cudaMemcpy(hw, reinterpret_cast<uint8_t*>(c->d_key) + offsetof(KeyDev, H), 16, cudaMemcpyDeviceToHost));
+    memcpy(c->h_rk, head, (size_t)16 * (nr + 1));
+    const uint32_t* hw = head + 64;
     for (int i = 0; i < 4; ++i) {
         c->h_H[4 * i + 0] = (uint8_t)(hw[i] >> 24);
         c->h_H[4 * i + 1] = (uint8_t)(hw[i] >> 16);

@@ -149,26 +149,40 @@ __global__ void k_key_expand(const uint8_t* __restrict__ keys, uint64_t n_keys, 
 }
 
 // ===========================================================================
-// Per-key setup: H, H^(2^k), per-thread / per-CTA weights, Shoup tables.
-// One CTA of 256 threads; kd->rk / kd->nr must already be filled.
+// Per-key setup: stage keys, H, H^(2^k), per-thread / per-CTA weights, Shoup
+// tables.  One CTA of 256 threads, one launch per agcm_set_key: the key (raw,
+// or the Nr+1 user-loaded stages of config/config_aes_kprexp.py:66-95) rides
+// in the kernel parameters, so the host does no H2D copy.
 // ===========================================================================
-__global__ void __launch_bounds__(256) k_key_setup(KeyDev* kd, const uint32_t* __restrict__ te0, uint32_t nt_stream,
-                                                   uint32_t ncta)
+__global__ void __launch_bounds__(256) k_key_setup(KeyDev* kd, const __grid_constant__ KeyIn in,
+                                                   const uint32_t* __restrict__ te0, uint32_t nt_stream, uint32_t ncta)
 {
     const uint32_t tid = threadIdx.x;
     __shared__ gf128 s_pow2[64];
+    __shared__ uint32_t s_rk[60];
+    if (in.pre_expanded) {
+        if (tid < 4 * (in.nr + 1)) s_rk[tid] = in.w[tid];
+    } else if (tid == 0) {
+        uint8_t key[32];
+        for (uint32_t j = 0; j < in.key_bytes; ++j) key[j] = (uint8_t)(in.w[j >> 2] >> (8 * (j & 3)));
+        auto sb = [&](uint32_t b) { return (__ldg(te0 + (b & 0xff)) >> 8) & 0xff; };
+        aes_key_expand_words(key, (int)in.key_bytes, sb, s_rk);
+    }
+    __syncthreads();
+    if (tid < 60) kd->rk[tid] = tid < 4 * (in.nr + 1) ? s_rk[tid] : 0u;
     if (tid == 0) {
         TeGlobal te{te0};
         uint32_t h[4];
-        aes_encrypt_words(kd->rk, (int)kd->nr, 0, 0, 0, 0, te, h);  // H = E_K(0^128), gcm_gctr.vhd:141-144
+        aes_encrypt_words(s_rk, (int)in.nr, 0, 0, 0, 0, te, h);  // H = E_K(0^128), gcm_gctr.vhd:141-144
         gf128 p = gf_from_le_words(h[0], h[1], h[2], h[3]);
         kd->H = p;
+        kd->nr = in.nr;
         kd->nt_stream = nt_stream;
         kd->ncta = ncta;
         for (int k = 0; k < 64; ++k) {
             s_pow2[k] = p;
             kd->pow2[k] = p;
-            p = gf_mul(p, p);
+            p = gf_sqr(p);
         }
         kd->hpow_thread[0] = gf_one();
         kd->hpow_thread[1] = s_pow2[0];
@@ -822,9 +836,10 @@ cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_b
     return cudaGetLastError();
 }
 
-cudaError_t ag_launch_key_setup(KeyDev* kd, const uint32_t* te0, int nt_stream, int ncta, cudaStream_t st)
+cudaError_t ag_launch_key_setup(KeyDev* kd, const KeyIn& in, const uint32_t* te0, int nt_stream, int ncta,
+                                cudaStream_t st)
 {
-    k_key_setup<<<1, 256, 0, st>>>(kd, te0, (uint32_t)nt_stream, (uint32_t)ncta);
+    k_key_setup<<<1, 256, 0, st>>>(kd, in, te0, (uint32_t)nt_stream, (uint32_t)ncta);
     return cudaGetLastError();
 }
 

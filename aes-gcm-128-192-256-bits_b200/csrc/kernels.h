@@ -28,7 +28,15 @@ cudaError_t ag_launch_batch_cta(const BatchParams& p, int nr, int decrypt, int n
 cudaError_t ag_launch_batch_perkey(const BatchParams& p, int nr, int decrypt, int max_cta, cudaStream_t st);
 cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_bytes, const uint32_t* te0,
                                  uint8_t* round_keys, cudaStream_t st);
-cudaError_t ag_launch_key_setup(KeyDev* kd, const uint32_t* te0, int nt_stream, int ncta, cudaStream_t st);
+// The key as k_key_setup takes it: raw key bytes, or the Nr+1 pre-expanded stages, as LE words.
+struct KeyIn {
+    uint32_t w[60];
+    uint32_t key_bytes;     // 16 / 24 / 32 (raw key length; unused when pre_expanded)
+    uint32_t nr;            // 10 / 12 / 14
+    uint32_t pre_expanded;  // w holds 4*(nr+1) stage-key words, used as they are
+};
+cudaError_t ag_launch_key_setup(KeyDev* kd, const KeyIn& in, const uint32_t* te0, int nt_stream, int ncta,
+                                cudaStream_t st);
 cudaError_t ag_launch_pow(const KeyDev* kd, uint64_t e, uint32_t* out4, cudaStream_t st);
 cudaError_t ag_launch_finish(const FinishParams& p, cudaStream_t st);
 cudaError_t ag_launch_xor_parts(const uint8_t* parts16, uint32_t n, uint8_t* out16, cudaStream_t st);

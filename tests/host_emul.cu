@@ -294,6 +294,8 @@ void emul_gf_mul_table(const uint8_t x[16], const uint8_t c[16], uint8_t out[16]
     gf_to_bytes(gf_mul_table(gf_from_bytes(x), gh), out);
 }
 
+void emul_gf_sqr(const uint8_t a[16], uint8_t out[16]) { gf_to_bytes(gf_sqr(gf_from_bytes(a)), out); }
+
 void emul_sbox(uint8_t out[256]) { memcpy(out, tables().sbox, 256); }
 
 }  // extern "C"

@@ -36,6 +36,8 @@ def test_gf_multiplies(emul, oracle):
         assert out.tobytes() == want
         emul.emul_gf_mul_table(u8p(a), u8p(b), u8p(out))  # Shoup-table path of the hot loop
         assert out.tobytes() == want
+        emul.emul_gf_sqr(u8p(a), u8p(out))                 # linear squaring used by the key setup
+        assert out.tobytes() == oracle.gfmul(a.tobytes(), a.tobytes())
 
 
 @pytest.mark.parametrize("kb", [16, 24, 32])
