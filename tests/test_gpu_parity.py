@@ -998,6 +998,58 @@ def test_large_stream_8GiB_properties(engine, oracle, torch_mod):
     torch.cuda.empty_cache()
 
 
+def test_maximum_length_stream_in_place(engine, oracle, torch_mod):
+    """The longest message the 32-bit counter allows (src/aes_icb.vhd:99-100,118: the counter
+    halts at 0xFFFFFFFF): 2^32-2 blocks = 68 719 476 704 bytes, encrypted IN PLACE in HBM.  CT
+    windows (including the very last block, counter 0xFFFFFFFF) vs the oracle's GCTR; the tag must
+    equal the 8-shard combine; the sharded decrypt restores the plaintext (64-bit word checksum)."""
+    torch = torch_mod
+    n = ((1 << 32) - 2) * 16
+    free, _ = torch.cuda.mem_get_info()
+    if free < n + (6 << 30):
+        pytest.skip("not enough free HBM")
+    from aesgcm_b200.parallel import shard_plan
+    rng = np.random.default_rng(64)
+    key, iv, aad = _rb(rng, 32), _rb(rng, 12), _rb(rng, 20)
+    engine.set_key(key)
+    rk = oracle.key_expand(key)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(64)
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    step = 1 << 32
+    for off in range(0, n, step):                      # fill by pieces: no 64 GiB temporaries
+        m = min(step, n - off)
+        d[off:off + m] = torch.randint(0, 256, (m,), dtype=torch.uint8, device="cuda", generator=gen)
+    def checksum():
+        v = d.view(torch.int64)
+        return [int(v[i::4].sum().item()) for i in range(4)]   # wraps mod 2^64; any restore error shows
+    before = checksum()
+    offs = (0, (1 << 32) - 512, (1 << 35) + 16 * 1001, n - 1024)
+    w = 1024
+    keep = {off: d[off:off + w].cpu().numpy().tobytes() for off in offs}
+    d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    d_aad = _dev(torch, aad)
+    engine.stream_crypt_device(0, iv, d_aad, d, d, d_tag)
+    torch.cuda.synchronize()
+    for off in offs:
+        assert d[off:off + w].cpu().numpy().tobytes() == oracle.gctr(rk, iv, 2 + off // 16, keep[off]), off
+    assert checksum() != before
+    parts = torch.zeros((8, 16), dtype=torch.uint8, device="cuda")
+    for s in shard_plan(n, 8):
+        sl = slice(s.byte_offset, s.byte_offset + s.n_bytes)
+        engine.stream_part_device(1, iv, s.first_block, d[sl], d[sl], s.blocks_after, parts[s.rank])
+    d_ok = torch.zeros(1, dtype=torch.uint8, device="cuda")
+    engine.stream_finish_device(1, iv, parts, 8, d_aad, n, d_tag, d_ok)
+    torch.cuda.synchronize()
+    assert int(d_ok.item()) == 1
+    assert checksum() == before
+    # one more block does not fit the counter
+    with pytest.raises(Exception):
+        engine.stream_part_device(0, iv, 16, d, d, 0, parts[0])      # first_block 16 + 2^32-2 blocks
+    del d
+    torch.cuda.empty_cache()
+
+
 def test_config3_full_size_roundtrip(engine, oracle, torch_mod):
     """BASELINE config 3 at full size: 2^20 x 1500 B at a 1504 B stride, AES-192, shared
     pre-expanded key.  Sampled messages vs the oracle; full decrypt round trip; ok flags all 1."""
