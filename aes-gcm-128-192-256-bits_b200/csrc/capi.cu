@@ -286,15 +286,18 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, 
     // long messages that cannot give every warp its own message: one CTA per message
     // (>= 4 rows of the CTA-wide Horner so the per-message lane weights amortise)
     if (avg_len >= (uint64_t)c->nt * 16 * 4 && n_msgs * 32 < (uint64_t)c->ncta * c->nt) return 1024;
-    // Measured on 2^20 x 1500 B (profiles/r1_kernel_table.md): 2 lanes per message is the best
-    // trade between coalescing (32 B per message per request) and lane-combine cost when the
-    // records are 16-byte aligned, 4 lanes when they are not.  Fewer messages than lanes: widen
-    // until the persistent grid is occupied, but never more lanes than blocks in a message.
+    // Measured (tools/sweep_lanes.py, profiles/r1_lane_sweep.md): the best lane count grows like
+    // sqrt(blocks)/4 -- 1 below 16 blocks (64 B: 370 vs 290 GB/s for 2 lanes), 2 at 1-1.5 KB, 4 at
+    // 4 KB, 8 at 16 KB, 32 from 64 KB -- the trade between coalescing (16*G contiguous bytes per
+    // message per request) and the per-message lane combine and front padding.  Records that are
+    // not 16-byte aligned want at least 4 lanes.  Fewer messages than lanes: widen until the
+    // persistent grid is occupied, but never more lanes than blocks in a message.
     const uint64_t total_lanes = (uint64_t)c->ncta * c->nt;
     const uint64_t blocks = (avg_len + 15) / 16 + 1;
-    // tiny messages (< 16 blocks): one lane each -- the lane combine and the front padding would
-    // cost more than the coalescing wins (64 B messages: 343 vs 290 GB/s)
-    uint64_t g = blocks < 16 ? 1 : (aligned16 ? 2 : 4);
+    uint64_t g = 1;
+    while (g < 32 && (8 * g) * (8 * g) <= 2 * blocks) g <<= 1;
+    if (blocks >= 4096) g = 32;
+    if (!aligned16 && blocks >= 16 && g < 4) g = 4;
     while (g < 32 && n_msgs * g * 2 <= total_lanes) g <<= 1;
     while (g > 1 && g > blocks) g >>= 1;
     return (int)g;
