@@ -16,6 +16,9 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device
  *     entry points are asynchronous on that stream.  A context owns scratch
  *     buffers: use one context per concurrently active stream.
+ *   - The library keeps no global mutable state.  A context is not locked internally: one
+ *     host thread at a time per context; distinct contexts (same or different devices) may be
+ *     used from different threads at the same time.
  *   - Return 0 on success, a negative AGCM_E_* otherwise.  Nothing throws.
  *   - mode = key size in bits: 128 / 192 / 256 (src/aes_pkg.vhd:31-33 Nr=10/12/14).
  *   - IV is always 96 bits; the counter block is IV || cnt32, cnt = 1 for J0 and

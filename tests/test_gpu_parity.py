@@ -998,6 +998,60 @@ def test_large_stream_8GiB_properties(engine, oracle, torch_mod):
     torch.cuda.empty_cache()
 
 
+def test_two_contexts_two_threads_no_crosstalk(engine_lib, oracle, torch_mod):
+    """The boundary contract: no global mutable state, distinct contexts are independent.  Two
+    host threads, each with its own context, key and CUDA stream, interleave stream and batch
+    calls (ctypes drops the GIL during a call); every result must match the oracle."""
+    import threading
+    import aesgcm_b200
+    torch = torch_mod
+    errors = []
+
+    def worker(seed, kb):
+        try:
+            rng = np.random.default_rng(seed)
+            eng = aesgcm_b200.GcmEngine(0)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for it in range(12):
+                    key = _rb(rng, kb)
+                    eng.set_key(key)
+                    iv, aad = _rb(rng, 12), _rb(rng, int(rng.integers(0, 40)))
+                    n = int(rng.integers(1, 300000))
+                    pt = _rb(rng, n)
+                    d_pt, d_aad = _dev(torch, pt), (_dev(torch, aad) if aad else None)
+                    d_ct = torch.empty_like(d_pt)
+                    d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+                    eng.stream_crypt_device(0, iv, d_aad, d_pt, d_ct, d_tag, stream=st.cuda_stream)
+                    # a batch of short messages under the same key on the same stream
+                    m, ln = 257, 208
+                    ivs = _rb(rng, 12 * m)
+                    bpt = _rb(rng, m * ln)
+                    d_iv, d_bpt = _dev(torch, ivs), _dev(torch, bpt)
+                    d_bct = torch.empty_like(d_bpt)
+                    d_tags = torch.zeros(16 * m, dtype=torch.uint8, device="cuda")
+                    eng.batch_crypt_uniform_device(0, d_iv, None, 0, 0, d_bpt, d_bct, ln, ln, d_tags, n_msgs=m,
+                                                   stream=st.cuda_stream)
+                    st.synchronize()
+                    want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt)
+                    assert d_ct.cpu().numpy().tobytes() == want_ct, (seed, it)
+                    assert d_tag.cpu().numpy().tobytes() == want_tag, (seed, it)
+                    got_ct, got_tags = d_bct.cpu().numpy().tobytes(), d_tags.cpu().numpy().tobytes()
+                    for i in (0, 100, m - 1):
+                        c, t = oracle.gcm_crypt(key, ivs[12 * i:12 * i + 12], b"", bpt[ln * i:ln * i + ln])
+                        assert got_ct[ln * i:ln * i + ln] == c and got_tags[16 * i:16 * i + 16] == t, (seed, it, i)
+            eng.close()
+        except BaseException as e:   # noqa: BLE001 - reported by the main thread
+            errors.append((seed, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(900 + i, kb)) for i, kb in enumerate((16, 32, 24))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_maximum_length_stream_in_place(engine, oracle, torch_mod):
     """The longest message the 32-bit counter allows (src/aes_icb.vhd:99-100,118: the counter
     halts at 0xFFFFFFFF): 2^32-2 blocks = 68 719 476 704 bytes, encrypted IN PLACE in HBM.  CT
