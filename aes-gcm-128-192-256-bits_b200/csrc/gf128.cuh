@@ -109,8 +109,7 @@ AG_HD gf128 gf_mul(const gf128& x, gf128 v)
 }
 
 // Squaring is GF(2)-linear: (sum a_i x^i)^2 = sum a_i x^(2i).  Spread the 128-bit string with
-// zeros (bit at string offset k -> offset 2k), then fold degrees 128..254 back with
-// x^128 = 1 + x + x^2 + x^7 (two folds: the first leaves at most 7 overflow bits).  ~130 integer
+// zeros (bit at string offset k -> offset 2k), then fold degrees 128..254 back (gf_fold256).  ~130 integer
 // ops instead of the ~1500 of the bit-serial product; used for the H^(2^k) chain of k_key_setup.
 AG_HD uint32_t ag_spread16(uint32_t x)   // bit j of the low 16 bits -> bit 2j
 {
@@ -122,6 +121,26 @@ AG_HD uint32_t ag_spread16(uint32_t x)   // bit j of the low 16 bits -> bit 2j
     return x;
 }
 
+// Reduce an unreduced 256-bit product (words 0..7, word 0 bit 31 = x^0, degrees up to 255) with
+// x^128 = 1 + x + x^2 + x^7: one fold of words 4..7, then a fold of the (at most 7) bits the
+// first one pushed past degree 255.
+AG_HD gf128 gf_fold256(const uint32_t z[8])
+{
+    uint32_t e[5];
+    e[0] = z[4] ^ (z[4] >> 1) ^ (z[4] >> 2) ^ (z[4] >> 7);
+#pragma unroll
+    for (int m = 1; m < 4; ++m)
+        e[m] = z[4 + m] ^ ag_funnel_r(z[4 + m], z[3 + m], 1) ^ ag_funnel_r(z[4 + m], z[3 + m], 2) ^
+               ag_funnel_r(z[4 + m], z[3 + m], 7);
+    const uint32_t u = (z[7] << 31) ^ (z[7] << 30) ^ (z[7] << 25);   // degrees 128..134 of the first fold
+    gf128 o;
+    o.w[0] = z[0] ^ e[0] ^ u ^ (u >> 1) ^ (u >> 2) ^ (u >> 7);
+    o.w[1] = z[1] ^ e[1];
+    o.w[2] = z[2] ^ e[2];
+    o.w[3] = z[3] ^ e[3];
+    return o;
+}
+
 AG_HD gf128 gf_sqr(const gf128& a)
 {
     uint32_t z[8];
@@ -131,22 +150,7 @@ AG_HD gf128 gf_sqr(const gf128& a)
         z[2 * q] = ag_spread16(a.w[q] >> 16) << 1;
         z[2 * q + 1] = ag_spread16(a.w[q]) << 1;
     }
-    // first fold: E = V ^ V>>1 ^ V>>2 ^ V>>7 over 5 words (V = z[4..7], degrees 128..254)
-    uint32_t e[5];
-    e[0] = z[4] ^ (z[4] >> 1) ^ (z[4] >> 2) ^ (z[4] >> 7);
-#pragma unroll
-    for (int m = 1; m < 4; ++m)
-        e[m] = z[4 + m] ^ ag_funnel_r(z[4 + m], z[3 + m], 1) ^ ag_funnel_r(z[4 + m], z[3 + m], 2) ^
-               ag_funnel_r(z[4 + m], z[3 + m], 7);
-    e[4] = (z[7] << 31) ^ (z[7] << 30) ^ (z[7] << 25);   // the bits pushed past degree 255 by >>1, >>2, >>7
-    // second fold of the (at most 7) overflow bits in e[4], which sit at degrees 128..134
-    const uint32_t u = e[4];
-    gf128 o;
-    o.w[0] = z[0] ^ e[0] ^ u ^ (u >> 1) ^ (u >> 2) ^ (u >> 7);
-    o.w[1] = z[1] ^ e[1];
-    o.w[2] = z[2] ^ e[2];
-    o.w[3] = z[3] ^ e[3];
-    return o;
+    return gf_fold256(z);
 }
 
 // 16 bytes as loaded little-endian (uint4 of LE words, the AES state layout)

@@ -598,7 +598,8 @@ namespace {
 
 constexpr uint32_t PK_NT = 512;
 constexpr uint32_t PK_GH4 = 65536;          // + up to 2 KB alignment pad
-constexpr uint32_t PK_SMEM = PK_GH4 + 2048 + PK_NT * 256;
+constexpr uint32_t PK_SUBC = 12 * PK_NT * 4;   // SubWord outputs of the schedule: 12 words per thread, [j][tid]
+constexpr uint32_t PK_SMEM = PK_GH4 + 2048 + PK_NT * 256 + PK_SUBC;
 
 struct TeSmem2 {
     const uint8_t* base;
@@ -644,6 +645,21 @@ struct Rows4Smem {
     }
 };
 
+// thread-private word column: word j at base + j * (4 * PK_NT) (a warp reads 128 consecutive bytes)
+struct SubCacheSmem {
+    uint32_t base;  // 32-bit shared address of this thread's word 0
+    __device__ __forceinline__ void put(int j, uint32_t v) const
+    {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + j * (4 * PK_NT)), "r"(v) : "memory");
+    }
+    __device__ __forceinline__ uint32_t get(int j) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + j * (4 * PK_NT)) : "memory");
+        return v;
+    }
+};
+
 __device__ __forceinline__ void load_words(const uint8_t* p, int n_words, uint32_t* w)
 {
     if (((uintptr_t)p & 3) == 0) {
@@ -680,6 +696,7 @@ __global__ void __launch_bounds__(PK_NT, 1) k_batch_perkey(const __grid_constant
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(ag_smem) + PK_GH4;
     const uint32_t s_al = (s0 + 2047u) & ~2047u;
     Rows4Smem rows{s_al + (tid >> 3) * 2048u + (tid & 7) * 16u};
+    SubCacheSmem subc{s_al + PK_NT * 256u + tid * 4u};
 
     for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + tid; m < p.n_msgs; m += (uint64_t)gridDim.x * blockDim.x) {
         const MsgDesc d = ag_batch_msg(p, m);
@@ -687,7 +704,7 @@ __global__ void __launch_bounds__(PK_NT, 1) k_batch_perkey(const __grid_constant
         load_words(p.keys + m * (uint64_t)(4 * NK), NK, key);
         load_words(p.iv + 12 * m, 3, iv);
         uint32_t tg[4];
-        ag_perkey_message<NK, DEC>(key, iv[0], iv[1], iv[2], d, te, sb, rows, tg);
+        ag_perkey_message<NK, DEC>(key, iv[0], iv[1], iv[2], d, te, sb, rows, subc, tg);
         uint8_t* tp = p.tag + 16 * m;
         if (DEC) {
             uint32_t x[4];

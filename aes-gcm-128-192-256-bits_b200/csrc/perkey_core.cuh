@@ -8,6 +8,11 @@
 // recurrence Y <- (Y xor X)*H of src/gcm_ghash.vhd:269-272 -- with one message
 // per thread the recurrence IS the parallel form: 2^20 independent chains.
 //
+// The only non-linear part of the schedule is SubWord, applied to 8 / 7 / 12 words past word 11
+// (AES-128 / 192 / 256).  Those SubWord outputs are computed once per message and parked in
+// a 12-word thread-private shared-memory column (SUBC: put(j, v) / get(j)); per block the
+// schedule is then 12 word loads and XORs instead of 48 S-box byte lookups.
+//
 // Host+device, exercised on the CPU by tests/host_emul.cu.
 #pragma once
 #include "gcm_core.cuh"
@@ -82,6 +87,27 @@ AG_HD void aes_encrypt_otf(const uint32_t* key, uint32_t s0, uint32_t s1, uint32
              (te(1, s2, 3) & 0xff000000u) ^ k3;
 }
 
+// SubWord functors for RkStream::word past word 11: record the outputs once, replay them per block.
+// After unrolling, j is a compile-time constant at every call.
+template <class SB, class SUBC>
+struct SubRecord {
+    SB& sb;
+    SUBC& c;
+    int j;
+    AG_HD uint32_t operator()(uint32_t w)
+    {
+        const uint32_t v = sb(w);
+        c.put(j++, v);
+        return v;
+    }
+};
+template <class SUBC>
+struct SubReplay {
+    SUBC& c;
+    int j;
+    AG_HD uint32_t operator()(uint32_t) { return c.get(j++); }
+};
+
 // ---- counter mode with the schedule on the fly, per-message constants hoisted ---------
 // Stage words 0..11 (rounds 0-2) are used once per message: they go into the round-1
 // constants (aes_ctr_precompute), rk[3], and the sequential-counter cache of rounds 1+2
@@ -96,8 +122,9 @@ struct PerKeyCtr {
     uint32_t rk8[4];
 };
 
-template <int NK, class TE, class SB>
-AG_HD void perkey_ctr_init(const uint32_t* key, uint32_t iv0, uint32_t iv1, uint32_t iv2, TE&& te, SB&& sb, PerKeyCtr<NK>& st)
+template <int NK, class TE, class SB, class SUBC>
+AG_HD void perkey_ctr_init(const uint32_t* key, uint32_t iv0, uint32_t iv1, uint32_t iv2, TE&& te, SB&& sb, SUBC&& subc,
+                           PerKeyCtr<NK>& st)
 {
     RkStream<NK> ks;
     ks.init(key);
@@ -105,16 +132,24 @@ AG_HD void perkey_ctr_init(const uint32_t* key, uint32_t iv0, uint32_t iv1, uint
 #pragma unroll
     for (int i = 0; i < 12; ++i) rk[i] = ks.word(i, sb);
     st.at12 = ks;
+    {   // run the rest of the schedule once, parking every SubWord output
+        SubRecord<SB, SUBC> rec{sb, subc, 0};
+        uint32_t sink = 0;
+#pragma unroll
+        for (int i = 12; i < 4 * (NK + 7); ++i) sink ^= ks.word(i, rec);
+        (void)sink;
+    }
     st.cc = aes_ctr_precompute(rk, iv0, iv1, iv2, te);
     st.rk3 = rk[3];
     st.rk8[0] = rk[8]; st.rk8[1] = rk[9]; st.rk8[2] = rk[10]; st.rk8[3] = rk[11];
     st.cache.key = 0xFFFFFFFFu;
 }
 
-template <int NK, class TE, class SB>
-AG_HD void perkey_ctr_block(PerKeyCtr<NK>& st, uint32_t ctr, TE&& te, SB&& sb, uint32_t out[4])
+template <int NK, class TE, class SUBC>
+AG_HD void perkey_ctr_block(PerKeyCtr<NK>& st, uint32_t ctr, TE&& te, SUBC&& subc, uint32_t out[4])
 {
     constexpr int NR = NK + 6;
+    SubReplay<SUBC> sb{subc, 0};
     const uint32_t s3i = ag_bswap32(ctr) ^ st.rk3;
     if ((s3i & 0x00FFFFFFu) != st.cache.key) {
         // aes_ctr_seq_fill reads rk[3] (unused there) and rk[8..11]: hand it a view with those
@@ -181,49 +216,50 @@ AG_HD void gf_build_table4(const gf128& h, ROWS&& rows)
     }
 }
 
-// X*H by Horner over the 32 nibbles of X, last nibble first:
-//   Z <- Z*x^4 xor T[n_j];   Z*x^4 = (Z >> 4) xor R[dropped nibble],
-//   R[d] = d (x) (x^128 mod P) = (d<<28) ^ (d<<27) ^ (d<<26) ^ (d<<21) in word 0.
+// X*H with the reduction deferred to the end.  X = sum over (word q, nibble k) of
+// n(q,k) * x^(32q) * x^(4(7-k))  (k = 7 is the top nibble of a BE word = its lowest degrees), so
+//   X*H = sum_k x^(4(7-k)) * A_k,   A_k = sum_q T[n(q,k)] * x^(32q):
+// x^(32q) is a move by q words (free), and the outer sum is a Horner in x^4 over an unreduced
+// 8-word accumulator: 7 shifts by one nibble and ONE fold (gf_fold256) instead of a shift and a
+// reduction per nibble (about 270 integer operations per product instead of about 500).
 template <class ROWS>
 AG_HD gf128 gf_mul_table4(const gf128& x, ROWS&& rows)
 {
-    uint32_t z0 = 0, z1 = 0, z2 = 0, z3 = 0;
+    uint32_t z[8];
 #pragma unroll
-    for (int q = 3; q >= 0; --q) {
+    for (int m = 0; m < 8; ++m) z[m] = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // nibble k of BE word q, k = 0 is the last (highest-degree) nibble
-            if (!(q == 3 && k == 0)) {
-                const uint32_t d = z3 & 0xfu;
-                z3 = ag_funnel_r(z3, z2, 4);
-                z2 = ag_funnel_r(z2, z1, 4);
-                z1 = ag_funnel_r(z1, z0, 4);
-                z0 = (z0 >> 4) ^ (d * ((1u << 28) | (1u << 21))) ^ (d << 27) ^ (d << 26);
-            }
+    for (int k = 0; k < 8; ++k) {
+        if (k) {
+#pragma unroll
+            for (int m = 7; m >= 1; --m) z[m] = ag_funnel_r(z[m], z[m - 1], 4);
+            z[0] >>= 4;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
             const uint4 t = rows.get(x.w[q], k);
-            z0 ^= t.x;
-            z1 ^= t.y;
-            z2 ^= t.z;
-            z3 ^= t.w;
+            z[q] ^= t.x;
+            z[q + 1] ^= t.y;
+            z[q + 2] ^= t.z;
+            z[q + 3] ^= t.w;
         }
     }
-    gf128 o;
-    o.w[0] = z0; o.w[1] = z1; o.w[2] = z2; o.w[3] = z3;
-    return o;
+    return gf_fold256(z);
 }
 
 // ---- one whole message ------------------------------------------------------------
 // key: NK little-endian words of the raw key.  Returns the computed tag words (LE) and
 // writes the payload.  Unified order AAD | CT | length block (gcm_ghash.vhd:259-272,257).
-template <int NK, bool DEC, class TE, class SB, class ROWS>
+template <int NK, bool DEC, class TE, class SB, class ROWS, class SUBC>
 AG_HD void ag_perkey_message(const uint32_t* key, uint32_t iv0, uint32_t iv1, uint32_t iv2, const MsgDesc& d, TE&& te,
-                             SB&& sb, ROWS&& rows, uint32_t tag[4])
+                             SB&& sb, ROWS&& rows, SUBC&& subc, uint32_t tag[4])
 {
     uint32_t e[4];
     aes_encrypt_otf<NK>(key, 0, 0, 0, 0, te, sb, e);  // H = E_K(0^128)  (gcm_gctr.vhd:141-144)
     gf_build_table4(gf_from_le_words(e[0], e[1], e[2], e[3]), rows);
     PerKeyCtr<NK> st;
-    perkey_ctr_init<NK>(key, iv0, iv1, iv2, te, sb, st);
-    perkey_ctr_block<NK>(st, 1u, te, sb, e);  // E_K(J0), J0 = IV || 00000001 (aes_icb.vhd:34,99)
+    perkey_ctr_init<NK>(key, iv0, iv1, iv2, te, sb, subc, st);
+    perkey_ctr_block<NK>(st, 1u, te, subc, e);  // E_K(J0), J0 = IV || 00000001 (aes_icb.vhd:34,99)
 
     gf128 y = gf_zero();
     const uint64_t a = (d.aad_len + 15) >> 4, n = (d.len + 15) >> 4;
@@ -239,7 +275,7 @@ AG_HD void ag_perkey_message(const uint32_t* key, uint32_t iv0, uint32_t iv1, ui
         const uint32_t nv = left < 16 ? (uint32_t)left : 16u;
         uint32_t x[4], ks[4];
         ag_load_block(d.in + 16 * j, nv, x);
-        perkey_ctr_block<NK>(st, 2u + (uint32_t)j, te, sb, ks);
+        perkey_ctr_block<NK>(st, 2u + (uint32_t)j, te, subc, ks);
         uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
         ag_store_block(d.out + 16 * j, nv, o);
         if (DEC) {

@@ -40,6 +40,12 @@ struct SubWordHost {
     }
 };
 
+struct SubCacheHost {
+    uint32_t v[12];
+    void put(int j, uint32_t x) { v[j] = x; }
+    uint32_t get(int j) const { return v[j]; }
+};
+
 struct Rows4Host {
     uint4 r[16];
     __host__ __device__ void put(int n, uint4 v) { r[n] = v; }
@@ -171,8 +177,9 @@ void perkey_nk(const BatchParams& p)
         const uint8_t* ivp = p.iv + 12 * m;
         for (int j = 0; j < 12; ++j) iv[j >> 2] |= (uint32_t)ivp[j] << (8 * (j & 3));
         Rows4Host rows;
+        SubCacheHost subc;
         uint32_t tg[4];
-        ag_perkey_message<NK, DEC>(key, iv[0], iv[1], iv[2], d, te, sb, rows, tg);
+        ag_perkey_message<NK, DEC>(key, iv[0], iv[1], iv[2], d, te, sb, rows, subc, tg);
         uint8_t* tp = p.tag + 16 * m;
         if (DEC) {
             uint32_t x[4];
