@@ -190,7 +190,13 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
         ev1 = c->tev[2 * c->tev_pending + 1];
         AG_CUDA(c, cudaEventRecord(ev0, st));
     }
-    AG_CUDA(c, ag_launch_stream(p, c->nr, mode, c->ncta, c->nt, st));
+    // An input of at most one grid row (blocks <= ncta * nt) needs only the CTAs its blocks land in:
+    // the lane and CTA weights are relative to the launched grid, and the row constant H^(nt*ncta)
+    // is never applied.  A short message then pays for filling one CTA's tables, not 148.
+    int ncta = c->ncta;
+    const uint64_t blocks = (n_bytes + 15) >> 4;
+    if (blocks <= (uint64_t)c->ncta * (uint64_t)c->nt) ncta = (int)((blocks + (uint64_t)c->nt - 1) / (uint64_t)c->nt);
+    AG_CUDA(c, ag_launch_stream(p, c->nr, mode, ncta, c->nt, st));
     c->launches++;
     if (c->timing) {
         AG_CUDA(c, cudaEventRecord(ev1, st));

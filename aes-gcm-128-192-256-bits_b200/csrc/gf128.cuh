@@ -88,26 +88,6 @@ AG_HD gf128 gf_mulx(const gf128& v)
     return r;
 }
 
-// Generic bit-serial product X*V (ghash_gfmul.vhd:42-63).  ~128 x 12 integer
-// ops; used only off the per-block path (key setup, per-thread/-CTA weights,
-// tag finish).
-AG_HD gf128 gf_mul(const gf128& x, gf128 v)
-{
-    gf128 z = gf_zero();
-    for (int q = 0; q < 4; ++q) {
-        uint32_t xw = x.w[q];
-        for (int b = 31; b >= 0; --b) {
-            uint32_t m = 0u - ((xw >> b) & 1u);
-            z.w[0] ^= v.w[0] & m;
-            z.w[1] ^= v.w[1] & m;
-            z.w[2] ^= v.w[2] & m;
-            z.w[3] ^= v.w[3] & m;
-            v = gf_mulx(v);
-        }
-    }
-    return z;
-}
-
 // Squaring is GF(2)-linear: (sum a_i x^i)^2 = sum a_i x^(2i).  Spread the 128-bit string with
 // zeros (bit at string offset k -> offset 2k), then fold degrees 128..254 back (gf_fold256).  ~130 integer
 // ops instead of the ~1500 of the bit-serial product; used for the H^(2^k) chain of k_key_setup.
@@ -149,6 +129,40 @@ AG_HD gf128 gf_sqr(const gf128& a)
         // string offset k of word q (k = 0 is bit 31) -> offset 2k of the 64-bit pair (z[2q], z[2q+1])
         z[2 * q] = ag_spread16(a.w[q] >> 16) << 1;
         z[2 * q + 1] = ag_spread16(a.w[q]) << 1;
+    }
+    return gf_fold256(z);
+}
+
+// Generic product X*V (the function of ghash_gfmul.vhd:42-63), off the per-block path (key setup,
+// per-thread / per-CTA weights, tag finish).  Instead of the serial "V <- V*x with reduction" chain
+// of Algorithm 1 (128 dependent steps), the product is accumulated UNREDUCED: the bit of X at
+// degree 32q + j adds V * x^j (V moved j bits along the string, 5 words) at word offset q of an
+// 8-word accumulator, and one gf_fold256 reduces at the end.  32 steps of about 33 independent
+// integer operations: roughly 2.5x faster than the bit-serial form on one thread.
+AG_HD gf128 gf_mul(const gf128& x, const gf128& v)
+{
+    uint32_t z[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) z[m] = 0;
+    uint32_t s0 = v.w[0], s1 = v.w[1], s2 = v.w[2], s3 = v.w[3], s4 = 0;   // V * x^j
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j < 32; ++j) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t m = 0u - ((x.w[q] >> (31 - j)) & 1u);
+            z[q] ^= s0 & m;
+            z[q + 1] ^= s1 & m;
+            z[q + 2] ^= s2 & m;
+            z[q + 3] ^= s3 & m;
+            z[q + 4] ^= s4 & m;
+        }
+        s4 = ag_funnel_r(s4, s3, 1);
+        s3 = ag_funnel_r(s3, s2, 1);
+        s2 = ag_funnel_r(s2, s1, 1);
+        s1 = ag_funnel_r(s1, s0, 1);
+        s0 >>= 1;
     }
     return gf_fold256(z);
 }
