@@ -88,7 +88,9 @@ int agcm_key_expand_host(agcm_ctx* ctx, int mode, const uint8_t* h_key, uint8_t*
  * key_len = mode/8 when pre_expanded == 0, (Nr+1)*16 otherwise.
  * Derives on the device H = E_K(0^128) (src/gcm_gctr.vhd:141-144,
  * src/gcm_ghash.vhd:128-139), its powers and the Shoup tables; H stays valid
- * until the next agcm_set_key (src/gcm_ghash.vhd:123).  Synchronous. */
+ * until the next agcm_set_key (src/gcm_ghash.vhd:123).  Synchronous: it first waits for all
+ * work queued on the device (no earlier call may still read the old key), runs one kernel and
+ * reads the stage keys and H back; about 75 us. */
 int agcm_set_key(agcm_ctx* ctx, int mode, int pre_expanded, const uint8_t* h_key, size_t key_len);
 int agcm_get_round_keys(const agcm_ctx* ctx, uint8_t* h_round_keys, size_t cap); /* returns byte count */
 int agcm_get_h(const agcm_ctx* ctx, uint8_t h_h16[16]);
