@@ -269,3 +269,17 @@ AG_HD void aes_ctr_block_seq(const uint32_t* rk, const AesCtrConst& cc, AesCtrSe
     out[3] = (te(2, s3, 0) & 0x000000ffu) ^ (te(3, s0, 1) & 0x0000ff00u) ^ (te(0, s1, 2) & 0x00ff0000u) ^
              (te(1, s2, 3) & 0xff000000u) ^ rk[4 * NR + 3];
 }
+
+// One name for both per-lane caches, selected by the cache type the caller keeps.
+template <int NR, class TE>
+AG_HD void aes_ctr_block_auto(const uint32_t* rk, const AesCtrConst& cc, AesCtrSeqCache& c, uint32_t ctr, TE&& te,
+                              uint32_t out[4])
+{
+    aes_ctr_block_seq<NR>(rk, cc, c, ctr, te, out);
+}
+template <int NR, class TE>
+AG_HD void aes_ctr_block_auto(const uint32_t* rk, const AesCtrConst& cc, AesCtrCache& c, uint32_t ctr, TE&& te,
+                              uint32_t out[4])
+{
+    aes_ctr_block_cached<NR>(rk, cc, c, ctr, te, out);
+}

@@ -289,9 +289,6 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, 
     if (lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32) return lanes;
     if (lanes == 1024) return 1024;  // one CTA per message
     if (lanes != 0) return -1;
-    // long messages that cannot give every warp its own message: one CTA per message
-    // (>= 4 rows of the CTA-wide Horner so the per-message lane weights amortise)
-    if (avg_len >= (uint64_t)c->nt * 16 * 4 && n_msgs * 32 < (uint64_t)c->ncta * c->nt) return 1024;
     // Measured (tools/sweep_lanes.py, profiles/r1_lane_sweep.md): the best lane count grows like
     // sqrt(blocks)/4 -- 1 below 16 blocks (64 B: 370 vs 290 GB/s for 2 lanes), 2 at 1-1.5 KB, 4 at
     // 4 KB, 8 at 16 KB, 32 from 64 KB -- the trade between coalescing (16*G contiguous bytes per
@@ -306,6 +303,17 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, 
     if (!aligned16 && blocks >= 16 && g < 4) g = 4;
     while (g < 32 && n_msgs * g * 2 <= total_lanes) g <<= 1;
     while (g > 1 && g > blocks) g >>= 1;
+    // Long messages: one CTA per message (k_batch_cta) when that finishes sooner.  Both layouts
+    // assign whole messages statically, so the step count is quantised: rounds x (rows per lane +
+    // per-message overhead), in block-times of one lane; the overheads (2 rows for a lane group,
+    // 2.5 rows for a CTA: lane weights, two barriers) are fitted to profiles/r1_lane_sweep.md.
+    if (avg_len >= (uint64_t)c->nt * 16 * 4) {
+        const uint64_t groups = total_lanes / g;
+        const double t_g = (double)((n_msgs + groups - 1) / groups) * ((double)blocks / (double)g + 2.0);
+        const double t_cta = (double)((n_msgs + (uint64_t)c->ncta - 1) / (uint64_t)c->ncta) *
+                             ((double)blocks / (double)c->nt + 2.5);
+        if (t_cta < t_g) return 1024;
+    }
     return (int)g;
 }
 

@@ -271,8 +271,10 @@ AG_HD MsgDesc ag_batch_msg(const BatchParams& p, uint64_t m)
 // Lane t of G over the unified sequence [AAD blocks | CT blocks | length block]
 // (gcm_ghash.vhd:259-272 order; length block gcm_ghash.vhd:257).  DEC selects the
 // GHASH source (aes_gcm.vhd:207-211).  Returns Y_t (weight H^(G-t) still to apply).
-template <int NR, bool DEC, class TE, class GH>
-AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, AesCtrSeqCache& cache, const MsgDesc& d, uint32_t t,
+// CACHE: AesCtrSeqCache when G is small (a lane's counters are near-consecutive), AesCtrCache when
+// G is a multiple of 256 (one CTA per message: the lane's low counter byte never changes).
+template <int NR, bool DEC, class CACHE, class TE, class GH>
+AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cache, const MsgDesc& d, uint32_t t,
                           uint32_t G, TE&& te, GH&& gh_g, uint32_t ej0[4])
 {
     // block counts fit 32 bits (a message is < 2^32 blocks; AAD + payload + 1 likewise)
@@ -299,7 +301,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, AesCtrSeqCa
             const uint32_t nv = (j == n - 1 && tail) ? tail : 16u;
             uint32_t x[4] = {0, 0, 0, 0}, ks[4];
             if (!is_len) ag_load_block(d.in + 16 * (uint64_t)j, nv, x);   // in flight during the AES rounds
-            aes_ctr_block_seq<NR>(rk, cc, cache, is_len ? 1u : 2u + j, te, ks);
+            aes_ctr_block_auto<NR>(rk, cc, cache, is_len ? 1u : 2u + j, te, ks);
             if (is_len) {
                 ej0[0] = ks[0]; ej0[1] = ks[1]; ej0[2] = ks[2]; ej0[3] = ks[3];
                 // [len(A)]64 || [len(C)]64 in bits, big-endian (gcm_ghash.vhd:257)

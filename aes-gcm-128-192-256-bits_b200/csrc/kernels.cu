@@ -468,6 +468,8 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
 
     const uint32_t t = lane & (G - 1);
     const uint32_t gbase = lane & ~(uint32_t)(G - 1);
+    gf128 lane_weight = gf_one();
+    if (G >= 16) lane_weight = p.key->hpow_thread[G - t];   // H^(G-t), G <= nt_stream
     const uint64_t groups_per_cta = nt / G;
     const uint64_t n_groups = (uint64_t)gridDim.x * groups_per_cta;
     const uint64_t gid = (uint64_t)blockIdx.x * groups_per_cta + tid / G;
@@ -498,17 +500,32 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
             y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, (uint32_t)G, te, gh_g, e);
         }
         __syncwarp();
-        // R = sum_t Y_t H^(G-t): serial Horner over the group's lanes with T_b = H
+        // R = sum_t Y_t H^(G-t)
         gf128 r = gf_zero();
+        if (G >= 16) {
+            // wide groups: every lane applies its own weight with one generic product (integer
+            // pipe only), then a butterfly XOR -- G-1 serial table products would keep the lookup
+            // pipe, the binding one, busy for G x 64 wavefronts per warp
+            r = gf_mul(y, lane_weight);
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                r.w[0] ^= __shfl_xor_sync(0xffffffffu, r.w[0], o);
+                r.w[1] ^= __shfl_xor_sync(0xffffffffu, r.w[1], o);
+                r.w[2] ^= __shfl_xor_sync(0xffffffffu, r.w[2], o);
+                r.w[3] ^= __shfl_xor_sync(0xffffffffu, r.w[3], o);
+            }
+        } else {
+            // narrow groups: serial Horner over the group's lanes with T_b = H
 #pragma unroll 1
-        for (int k = 0; k < G; ++k) {
-            gf128 yk;
-            yk.w[0] = __shfl_sync(0xffffffffu, y.w[0], gbase + k);
-            yk.w[1] = __shfl_sync(0xffffffffu, y.w[1], gbase + k);
-            yk.w[2] = __shfl_sync(0xffffffffu, y.w[2], gbase + k);
-            yk.w[3] = __shfl_sync(0xffffffffu, y.w[3], gbase + k);
-            r = gf_xor(r, yk);
-            r = gf_mul_table(r, gh_1);
+            for (int k = 0; k < G; ++k) {
+                gf128 yk;
+                yk.w[0] = __shfl_sync(0xffffffffu, y.w[0], gbase + k);
+                yk.w[1] = __shfl_sync(0xffffffffu, y.w[1], gbase + k);
+                yk.w[2] = __shfl_sync(0xffffffffu, y.w[2], gbase + k);
+                yk.w[3] = __shfl_sync(0xffffffffu, y.w[3], gbase + k);
+                r = gf_xor(r, yk);
+                r = gf_mul_table(r, gh_1);
+            }
         }
         if (valid && t == G - 1) {
             uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
@@ -554,8 +571,9 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
             iv2 |= (uint32_t)ivp[8 + j] << (8 * j);
         }
         const AesCtrConst cc = aes_ctr_precompute(p.rk, iv0, iv1, iv2, te);
-        AesCtrSeqCache cache;
-        cache.key = 0xFFFFFFFFu;
+        // lanes step their counter by nt (512: a multiple of 256): the stream kernel's cache fits
+        AesCtrCache cache;
+        cache.key = 0x00FFFF00u;  // invalid: a valid key has those bits clear
         uint32_t e[4] = {0, 0, 0, 0};
         gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, tid, nt, te, gh_g, e);
         if (tid == nt - 1) {   // the lane that met the length block also produced E_K(J0)
