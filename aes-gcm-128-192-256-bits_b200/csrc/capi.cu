@@ -37,6 +37,8 @@ struct agcm_ctx {
     uint32_t* d_te0 = nullptr;
     KeyDev* d_key = nullptr;
     uint32_t* d_parts = nullptr;  // 2 x AG_MAX_CTA x 4 words: [0] CT partials, [1] AAD partials
+    uint32_t* d_seg_parts = nullptr;  // split batch layout: n_msgs x (split + 1) x 16 B, grown on demand
+    size_t seg_parts_bytes = 0;
     uint8_t* d_scratch = nullptr;
     uint32_t* d_counters = nullptr;  // last-CTA tickets: [0] context scratch, [1+s] pipeline slot s
     uint32_t* d_pow_n = nullptr;     // cached H^n (4 BE words) for the tag finish
@@ -288,6 +290,7 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, 
 {
     if (lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32) return lanes;
     if (lanes == 1024) return 1024;  // one CTA per message
+    if (lanes > 1024 && lanes <= 1024 + 256 && ((lanes - 1024) & (lanes - 1025)) == 0) return lanes;  // ... per 1/S of a message
     if (lanes != 0) return -1;
     // Measured (tools/sweep_lanes.py, profiles/r1_lane_sweep.md): the best lane count grows like
     // sqrt(blocks)/4 -- 1 below 16 blocks (64 B: 370 vs 290 GB/s for 2 lanes), 2 at 1-1.5 KB, 4 at
@@ -312,7 +315,22 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, 
         const double t_g = (double)((n_msgs + groups - 1) / groups) * ((double)blocks / (double)g + 2.0);
         const double t_cta = (double)((n_msgs + (uint64_t)c->ncta - 1) / (uint64_t)c->ncta) *
                              ((double)blocks / (double)c->nt + 2.5);
-        if (t_cta < t_g) return 1024;
+        if (t_cta < t_g) {
+            // few long messages: cut each into S counter-range segments so that the last round
+            // of CTAs is full too (a segment pays about 1.5 more rows for its H^after scaling)
+            int best = 1024;
+            double t_best = t_cta;
+            for (uint64_t S = 2; S <= 256; S <<= 1) {
+                const double rows = (double)blocks / (double)(S * (uint64_t)c->nt);
+                if (rows < 8.0) break;
+                const double t = (double)((n_msgs * S + (uint64_t)c->ncta - 1) / (uint64_t)c->ncta) * (rows + 4.0);
+                if (t < 0.97 * t_best) {
+                    t_best = t;
+                    best = 1024 + (int)S;
+                }
+            }
+            return best;
+        }
     }
     return (int)g;
 }
@@ -403,6 +421,7 @@ void agcm_ctx_destroy(agcm_ctx* c)
     cudaFree(c->d_te0);
     cudaFree(c->d_key);
     cudaFree(c->d_parts);
+    cudaFree(c->d_seg_parts);
     cudaFree(c->d_scratch);
     cudaFree(c->d_counters);
     cudaFree(c->d_pow_n);
@@ -672,10 +691,23 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
     p.key = c->d_key;
     p.te0 = c->d_te0;
     p.n_msgs = n_msgs;
-    if (g == 1024) {
-        const int ncta_m = (int)(n_msgs < (uint64_t)c->ncta ? n_msgs : (uint64_t)c->ncta);
+    if (g >= 1024) {
+        p.split = g == 1024 ? 1u : (uint32_t)(g - 1024);
+        const uint64_t n_units = (uint64_t)n_msgs * p.split;
+        if (p.split > 1) {
+            const size_t need = (size_t)(n_units + n_msgs) * 16;
+            if (need > c->seg_parts_bytes) {
+                AG_CUDA(c, cudaFree(c->d_seg_parts));
+                c->d_seg_parts = nullptr;
+                c->seg_parts_bytes = 0;
+                AG_CUDA(c, cudaMalloc(&c->d_seg_parts, need));
+                c->seg_parts_bytes = need;
+            }
+            p.seg_parts = c->d_seg_parts;
+        }
+        const int ncta_m = (int)(n_units < (uint64_t)c->ncta ? n_units : (uint64_t)c->ncta);
         AG_CUDA(c, ag_launch_batch_cta(p, c->nr, decrypt, ncta_m, c->nt, (cudaStream_t)stream));
-        c->launches++;
+        c->launches += p.split > 1 ? 2 : 1;
         return AGCM_OK;
     }
     // no more CTAs than there is work for
@@ -728,7 +760,8 @@ int agcm_batch_crypt_uniform(agcm_ctx* c, int decrypt, int lanes, const uint8_t*
     p.aad_len = aad_len;
     p.aad_stride = aad_stride;
     const bool aligned16 = ((((uintptr_t)d_in | (uintptr_t)d_out) | stride) & 15) == 0;
-    return batch_common(c, decrypt, lanes, len, p, n_msgs, stream, aligned16);
+    // work estimate for the layout choice: an AAD block costs about a quarter of a payload block (no AES)
+    return batch_common(c, decrypt, lanes, len + (d_aad ? aad_len / 4 : 0), p, n_msgs, stream, aligned16);
 }
 
 static int perkey_common(agcm_ctx* c, int mode, int decrypt, BatchParams& p, size_t n_msgs, void* stream)

@@ -245,13 +245,21 @@ struct BatchParams {
     uint8_t* ok;               // n_msgs, dec only: 1 = authentic
     uint64_t n_msgs;
     uint64_t len, stride, aad_len, aad_stride;  // uniform layout
+    // k_batch_cta only: every message is cut into `split` counter-range segments, one CTA each
+    // (1 = whole messages); seg_parts holds n_msgs x split scaled partials then n_msgs x E_K(J0)
+    uint32_t split;
+    uint32_t* seg_parts;
 };
 
+// One message, or one counter-range segment of it (ag_batch_segment).
 struct MsgDesc {
     const uint8_t* in;
     uint8_t* out;
     const uint8_t* aad;
-    uint64_t len, aad_len;
+    uint64_t len, aad_len;              // what THIS unit reads: payload bytes, AAD bytes
+    uint64_t total_len, total_aad_len;  // the whole message (the length block, gcm_ghash.vhd:257)
+    uint32_t ctr_off;                   // payload block index of the unit's first block (counter = 2 + ctr_off + j)
+    uint32_t last;                      // the unit ends the message: it absorbs the length block and makes E_K(J0)
 };
 
 AG_HD MsgDesc ag_batch_msg(const BatchParams& p, uint64_t m)
@@ -265,6 +273,43 @@ AG_HD MsgDesc ag_batch_msg(const BatchParams& p, uint64_t m)
     if (p.aad_off) { o = p.aad_off[m]; l = p.aad_off[m + 1] - o; } else { o = m * p.aad_stride; l = p.aad_len; }
     d.aad = p.aad ? p.aad + o : nullptr;
     d.aad_len = p.aad ? l : 0;
+    d.total_len = d.len;
+    d.total_aad_len = d.aad_len;
+    d.ctr_off = 0;
+    d.last = 1;
+    return d;
+}
+
+// Segment `seg` of S of message w, the single-GPU form of the counter-range shards of
+// parallel.py: a contiguous range of the unified sequence AAD | CT (so bulk AAD is shared out
+// too), the length block and E_K(J0) with segment S-1.  *after = blocks of the
+// unified sequence that follow the segment: its GHASH partial is scaled by H^after before the
+// S partials are XORed.  AAD and CT are each zero-padded to whole blocks by the reference
+// (gcm_ghash.vhd:228-244), so cutting at block boundaries changes nothing.
+AG_HD MsgDesc ag_batch_segment(const MsgDesc& w, uint32_t seg, uint32_t S, uint64_t* after)
+{
+    const uint64_t a = (w.aad_len + 15) >> 4, n = (w.len + 15) >> 4, tot = a + n;
+    // equal WORK per segment, not equal blocks: an AAD block (GHASH only) weighs 1, a payload
+    // block (AES + GHASH) 4; boundary k sits at weight k * per of the total a + 4n
+    const uint64_t W = a + 4 * n, per = (W + S - 1) / S;
+    uint64_t w0 = (uint64_t)seg * per, w1 = w0 + per;
+    if (w0 > W) w0 = W;
+    if (w1 > W) w1 = W;
+    uint64_t u0 = w0 <= a ? w0 : a + (w0 - a + 3) / 4;
+    uint64_t u1 = w1 <= a ? w1 : a + (w1 - a + 3) / 4;
+    if (u0 > tot) u0 = tot;
+    if (u1 > tot || seg == S - 1) u1 = tot;
+    const uint64_t a0 = u0 < a ? u0 : a, a1 = u1 < a ? u1 : a;          // AAD blocks [a0, a1)
+    const uint64_t c0 = (u0 > a ? u0 : a) - a, c1 = (u1 > a ? u1 : a) - a;  // CT blocks [c0, c1)
+    MsgDesc d = w;
+    d.aad = (a1 > a0) ? w.aad + 16 * a0 : nullptr;
+    d.aad_len = (a1 > a0) ? ((a1 == a) ? w.aad_len - 16 * a0 : 16 * (a1 - a0)) : 0;
+    d.in = w.in + 16 * c0;
+    d.out = w.out + 16 * c0;
+    d.len = (c1 > c0) ? ((c1 == n) ? w.len - 16 * c0 : 16 * (c1 - c0)) : 0;
+    d.ctr_off = (uint32_t)c0;
+    d.last = (seg == S - 1) ? 1u : 0u;
+    *after = d.last ? 0 : (tot - u1) + 1;
     return d;
 }
 
@@ -273,39 +318,48 @@ AG_HD MsgDesc ag_batch_msg(const BatchParams& p, uint64_t m)
 // GHASH source (aes_gcm.vhd:207-211).  Returns Y_t (weight H^(G-t) still to apply).
 // CACHE: AesCtrSeqCache when G is small (a lane's counters are near-consecutive), AesCtrCache when
 // G is a multiple of 256 (one CTA per message: the lane's low counter byte never changes).
+// An AAD row has no AES pass to hide its load behind, so the AAD block of row u+1 is fetched
+// before row u is processed (one row of software prefetch); a payload block is loaded at the top
+// of its own row and consumed after the AES rounds.
 template <int NR, bool DEC, class CACHE, class TE, class GH>
 AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cache, const MsgDesc& d, uint32_t t,
                           uint32_t G, TE&& te, GH&& gh_g, uint32_t ej0[4])
 {
     // block counts fit 32 bits (a message is < 2^32 blocks; AAD + payload + 1 likewise)
     const uint32_t a = (uint32_t)((d.aad_len + 15) >> 4), n = (uint32_t)((d.len + 15) >> 4);
-    const uint32_t mb = a + n + 1;
+    const uint32_t mb = a + n + (d.last ? 1u : 0u);
     const uint32_t rows = (mb + G - 1) / G;
     const uint32_t pad = rows * G - mb;   // < G
     const uint32_t atail = (uint32_t)(d.aad_len & 15), tail = (uint32_t)(d.len & 15);
     gf128 y = gf_zero();
     uint32_t i = t - pad;                 // wraps while inside the front padding (row 0 only)
     bool have = t >= pad;
-    for (uint32_t u = 0; u < rows; ++u, i += G, have = true) {
+    uint32_t nxt[4] = {0, 0, 0, 0};
+    if (rows && have && i < a) ag_load_block(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt);
+    for (uint32_t u = 0; u < rows; ++u) {
+        const uint32_t ic = i;
+        const bool hv = have;
+        uint32_t s[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
+        i += G;
+        have = true;
+        if (u + 1 < rows && i < a) ag_load_block(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt);
         if (u) y = gf_mul_table(y, gh_g);
-        if (!have) continue;
-        uint32_t s[4];
-        if (i < a) {
-            ag_load_block(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, s);
-        } else {
+        if (!hv) continue;
+        if (ic >= a) {
             // The length block always lands on lane G-1 of the last row.  That lane has no payload
             // block in this row, so it spends the row's AES pass on E_K(J0) (counter 1,
             // src/aes_icb.vhd:34,99): the tag mask costs no pass of its own.
-            const bool is_len = (i == a + n);
-            const uint32_t j = i - a;
+            const bool is_len = d.last && (ic == a + n);
+            const uint32_t j = ic - a;
             const uint32_t nv = (j == n - 1 && tail) ? tail : 16u;
-            uint32_t x[4] = {0, 0, 0, 0}, ks[4];
+            uint32_t x[4] = {0, 0, 0, 0};
             if (!is_len) ag_load_block(d.in + 16 * (uint64_t)j, nv, x);   // in flight during the AES rounds
-            aes_ctr_block_auto<NR>(rk, cc, cache, is_len ? 1u : 2u + j, te, ks);
+            uint32_t ks[4];
+            aes_ctr_block_auto<NR>(rk, cc, cache, is_len ? 1u : 2u + d.ctr_off + j, te, ks);
             if (is_len) {
                 ej0[0] = ks[0]; ej0[1] = ks[1]; ej0[2] = ks[2]; ej0[3] = ks[3];
                 // [len(A)]64 || [len(C)]64 in bits, big-endian (gcm_ghash.vhd:257)
-                const uint64_t ab = d.aad_len * 8, cb = d.len * 8;
+                const uint64_t ab = d.total_aad_len * 8, cb = d.total_len * 8;
                 y.w[0] ^= (uint32_t)(ab >> 32);
                 y.w[1] ^= (uint32_t)ab;
                 y.w[2] ^= (uint32_t)(cb >> 32);

@@ -561,8 +561,18 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
     GhSmem gh_g{ag_smem + SM_GH, (lane & 7) * 16};
     gf128* red = reinterpret_cast<gf128*>(ag_smem + SM_MISC);
     const gf128 wgt = p.key->hpow_thread[nt - tid];
-    for (uint64_t m = blockIdx.x; m < p.n_msgs; m += gridDim.x) {
-        const MsgDesc d = ag_batch_msg(p, m);
+    // One unit per CTA pass: a whole message, or (split > 1) one counter-range segment of it --
+    // a few long messages would otherwise leave the grid idle in the last round (256 messages on
+    // 148 CTAs: 2 rounds, 86 % busy).  A segment's partial is scaled by H^(blocks after it), the
+    // S partials and E_K(J0) go to seg_parts, and k_batch_split_finish XORs them into the tag.
+    const uint32_t S = p.split;
+    const uint64_t n_units = p.n_msgs * S;
+    for (uint64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const uint64_t m = u / S;
+        const uint32_t seg = (uint32_t)(u - m * S);
+        uint64_t after = 0;
+        MsgDesc d = ag_batch_msg(p, m);
+        if (S > 1) d = ag_batch_segment(d, seg, S, &after);
         const uint8_t* ivp = p.iv + 12 * m;
         uint32_t iv0 = 0, iv1 = 0, iv2 = 0;
         for (int j = 0; j < 4; ++j) {
@@ -587,10 +597,23 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
         if (tid < 32) {
             gf128 r = (tid < (nt >> 5)) ? red[tid] : gf_zero();
             r = warp_xor(r);
-            if (tid == 0) {
-                const uint32_t* e = reinterpret_cast<const uint32_t*>(ag_smem + SM_MISC + 1024);
-                uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
-                                  ag_bswap32(r.w[3]) ^ e[3]};
+            const uint32_t* ej = reinterpret_cast<const uint32_t*>(ag_smem + SM_MISC + 1024);
+            if (S > 1) {
+                if (after) {  // uniform
+                    const gf128 ha = warp_gf_pow(p.key, after);
+                    r = gf_mul(r, ha);
+                }
+                if (tid == 0) {
+                    uint32_t* dst = p.seg_parts + 4 * u;
+                    dst[0] = r.w[0]; dst[1] = r.w[1]; dst[2] = r.w[2]; dst[3] = r.w[3];
+                    if (d.last) {
+                        uint32_t* de = p.seg_parts + 4 * (n_units + m);
+                        de[0] = ej[0]; de[1] = ej[1]; de[2] = ej[2]; de[3] = ej[3];
+                    }
+                }
+            } else if (tid == 0) {
+                uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ ej[0], ag_bswap32(r.w[1]) ^ ej[1], ag_bswap32(r.w[2]) ^ ej[2],
+                                  ag_bswap32(r.w[3]) ^ ej[3]};
                 uint8_t* tp = p.tag + 16 * m;
                 if (DEC) {
                     uint32_t x[4];
@@ -603,6 +626,32 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
             }
         }
         __syncthreads();
+    }
+}
+
+// Tag finish of the split layout: one thread per message XORs its S scaled partials
+// (linearity of GHASH in its input, the same algebra as gcm_ghash.vhd:330-332) and E_K(J0).
+template <bool DEC>
+__global__ void k_batch_split_finish(const __grid_constant__ BatchParams p)
+{
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= p.n_msgs) return;
+    const uint32_t S = p.split;
+    uint32_t r[4] = {0, 0, 0, 0};
+    for (uint32_t k = 0; k < S; ++k) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p.seg_parts + 4 * (m * S + k));
+        r[0] ^= q.x; r[1] ^= q.y; r[2] ^= q.z; r[3] ^= q.w;
+    }
+    const uint4 e = *reinterpret_cast<const uint4*>(p.seg_parts + 4 * (p.n_msgs * S + m));
+    uint32_t tg[4] = {ag_bswap32(r[0]) ^ e.x, ag_bswap32(r[1]) ^ e.y, ag_bswap32(r[2]) ^ e.z, ag_bswap32(r[3]) ^ e.w};
+    uint8_t* tp = p.tag + 16 * m;
+    if (DEC) {
+        uint32_t x[4];
+        ag_load_block(tp, 16, x);
+        const uint32_t diff = (x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3]);
+        p.ok[m] = diff ? 0 : 1;
+    } else {
+        ag_store_block(tp, 16, tg);
     }
 }
 
@@ -838,6 +887,9 @@ static cudaError_t launch_batch_cta_t(const BatchParams& p, int ncta, int nt, cu
     cudaError_t e = cudaFuncSetAttribute(k_batch_cta<NR, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     k_batch_cta<NR, DEC><<<ncta, nt, kSmemBytes, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || p.split <= 1) return e;
+    k_batch_split_finish<DEC><<<(unsigned)((p.n_msgs + 127) / 128), 128, 0, st>>>(p);
     return cudaGetLastError();
 }
 

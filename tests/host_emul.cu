@@ -127,7 +127,7 @@ void stream_nr(const StreamParams& p, int mode, uint64_t ncta, uint64_t nt, cons
 }
 
 template <int NR, bool DEC>
-void batch_nr(const BatchParams& p, uint32_t G, const gf128& H)
+void batch_nr(const BatchParams& p, uint32_t G, const gf128& H, uint32_t S = 1)
 {
     std::vector<uint4> tab_g, tab_1;
     build_table(gf_pow(H, G), tab_g);
@@ -135,22 +135,32 @@ void batch_nr(const BatchParams& p, uint32_t G, const gf128& H)
     TeHost te{tables().te0};
     GhHost gh_g{tab_g.data()}, gh_1{tab_1.data()};
     for (uint64_t m = 0; m < p.n_msgs; ++m) {
-        const MsgDesc d = ag_batch_msg(p, m);
+        const MsgDesc whole = ag_batch_msg(p, m);
         const uint8_t* ivp = p.iv + 12 * m;
         uint32_t iv[3] = {0, 0, 0};
         for (int j = 0; j < 12; ++j) iv[j >> 2] |= (uint32_t)ivp[j] << (8 * (j & 3));
         const AesCtrConst cc = aes_ctr_precompute(p.rk, iv[0], iv[1], iv[2], te);
-        gf128 r = gf_zero();
-        AesCtrSeqCache cache;
-        cache.key = 0xFFFFFFFFu;
+        gf128 total = gf_zero();
         uint32_t e[4] = {0, 0, 0, 0};
-        for (uint32_t t = 0; t < G; ++t) {
-            uint32_t el[4] = {0, 0, 0, 0};
-            gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, G, te, gh_g, el);
-            if (t == G - 1) { e[0] = el[0]; e[1] = el[1]; e[2] = el[2]; e[3] = el[3]; }
-            r = gf_xor(r, y);
-            r = gf_mul_table(r, gh_1);
+        // S > 1: the message as S counter-range segments (k_batch_cta's split layout), each partial
+        // scaled by H^after and XORed, as k_batch_split_finish does
+        for (uint32_t seg = 0; seg < S; ++seg) {
+            uint64_t after = 0;
+            const MsgDesc d = S > 1 ? ag_batch_segment(whole, seg, S, &after) : whole;
+            gf128 r = gf_zero();
+            AesCtrSeqCache cache;
+            cache.key = 0xFFFFFFFFu;
+            for (uint32_t t = 0; t < G; ++t) {
+                uint32_t el[4] = {0, 0, 0, 0};
+                gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, G, te, gh_g, el);
+                if (t == G - 1 && d.last) { e[0] = el[0]; e[1] = el[1]; e[2] = el[2]; e[3] = el[3]; }
+                r = gf_xor(r, y);
+                r = gf_mul_table(r, gh_1);
+            }
+            if (after) r = gf_mul(r, gf_pow(H, after));
+            total = gf_xor(total, r);
         }
+        const gf128 r = total;
         uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ e[0], ag_bswap32(r.w[1]) ^ e[1], ag_bswap32(r.w[2]) ^ e[2],
                           ag_bswap32(r.w[3]) ^ e[3]};
         uint8_t* tp = p.tag + 16 * m;
@@ -249,9 +259,20 @@ int emul_stream(const uint8_t* rk_bytes, int nr, const uint8_t iv[12], uint32_t 
     return 0;
 }
 
+int emul_batch_split(const uint8_t* rk_bytes, int nr, int decrypt, int G, int S, const uint8_t* iv, const uint8_t* aad,
+                     const uint64_t* aad_off, const uint8_t* in, const uint64_t* in_off, uint8_t* out, uint8_t* tag,
+                     uint8_t* ok, uint64_t n_msgs);
+
 int emul_batch(const uint8_t* rk_bytes, int nr, int decrypt, int G, const uint8_t* iv, const uint8_t* aad,
                const uint64_t* aad_off, const uint8_t* in, const uint64_t* in_off, uint8_t* out, uint8_t* tag, uint8_t* ok,
                uint64_t n_msgs)
+{
+    return emul_batch_split(rk_bytes, nr, decrypt, G, 1, iv, aad, aad_off, in, in_off, out, tag, ok, n_msgs);
+}
+
+int emul_batch_split(const uint8_t* rk_bytes, int nr, int decrypt, int G, int S, const uint8_t* iv, const uint8_t* aad,
+                     const uint64_t* aad_off, const uint8_t* in, const uint64_t* in_off, uint8_t* out, uint8_t* tag,
+                     uint8_t* ok, uint64_t n_msgs)
 {
     BatchParams p;
     memset(&p, 0, sizeof(p));
@@ -270,9 +291,9 @@ int emul_batch(const uint8_t* rk_bytes, int nr, int decrypt, int G, const uint8_
     aes_encrypt_words(p.rk, nr, 0, 0, 0, 0, te, h);
     const gf128 H = gf_from_le_words(h[0], h[1], h[2], h[3]);
     switch (nr) {
-        case 10: decrypt ? batch_nr<10, true>(p, G, H) : batch_nr<10, false>(p, G, H); break;
-        case 12: decrypt ? batch_nr<12, true>(p, G, H) : batch_nr<12, false>(p, G, H); break;
-        case 14: decrypt ? batch_nr<14, true>(p, G, H) : batch_nr<14, false>(p, G, H); break;
+        case 10: decrypt ? batch_nr<10, true>(p, G, H, S) : batch_nr<10, false>(p, G, H, S); break;
+        case 12: decrypt ? batch_nr<12, true>(p, G, H, S) : batch_nr<12, false>(p, G, H, S); break;
+        case 14: decrypt ? batch_nr<14, true>(p, G, H, S) : batch_nr<14, false>(p, G, H, S); break;
         default: return -1;
     }
     return 0;

@@ -291,7 +291,9 @@ def test_batch_ragged_offsets_all_lane_counts(engine, oracle, torch_mod, kb):
 
 
 def test_batch_cta_per_message(engine, oracle, torch_mod):
-    """Few long messages: one CTA per message (lanes=1024), ragged lengths, AAD longer than the payload."""
+    """Few long messages: one CTA per message (lanes=1024) or per 1/S of a message (lanes=1024+S:
+    counter-range segments, scaled partials XORed by k_batch_split_finish), ragged lengths, AAD
+    longer than the payload, messages shorter than S blocks."""
     torch = torch_mod
     rng = np.random.default_rng(77)
     key = _rb(rng, 32)
@@ -307,7 +309,7 @@ def test_batch_cta_per_message(engine, oracle, torch_mod):
     want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), 32, True, ivs, aad, aad_off, data, in_off, threads=8)
     d_in_off, d_aad_off = torch.from_numpy(in_off.view(np.int64)).cuda(), torch.from_numpy(aad_off.view(np.int64)).cuda()
     d_data, d_aad, d_ivs = _dev(torch, data), _dev(torch, aad), _dev(torch, ivs)
-    for lanes in (1024, 0, 32):
+    for lanes in (1024, 0, 32, 1026, 1028, 1032, 1040):
         d_ct = torch.zeros_like(d_data)
         d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
         engine.batch_crypt_device(0, d_ivs, d_aad, d_aad_off, d_data, d_in_off, d_ct, d_tags, lanes=lanes,
@@ -324,6 +326,50 @@ def test_batch_cta_per_message(engine, oracle, torch_mod):
         torch.cuda.synchronize()
         assert (d_pt.cpu().numpy() == data).all(), lanes
         assert list(d_ok.cpu().numpy()) == [1, 1, 0, 1, 1, 1, 1], lanes
+
+
+def test_batch_few_long_messages_auto_split(engine, oracle, torch_mod):
+    """The shape the split layout exists for: more long messages than fit one round of CTAs but
+    fewer than two (the library picks lanes = 1024 + S on its own).  Uniform layout, in place,
+    sampled messages vs the oracle, full decrypt round trip with one corrupted tag."""
+    torch = torch_mod
+    rng = np.random.default_rng(78)
+    key = _rb(rng, 16)
+    engine.set_key(key)
+    ncta = engine.n_cta
+    n_msgs, length, alen = ncta + ncta // 2 + 3, 4 << 20, 48
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(78)
+    d_pt = torch.randint(0, 256, (n_msgs * length,), dtype=torch.uint8, device="cuda", generator=gen)
+    d_iv = torch.randint(0, 256, (n_msgs * 12,), dtype=torch.uint8, device="cuda", generator=gen)
+    d_aad = torch.randint(0, 256, (n_msgs * alen,), dtype=torch.uint8, device="cuda", generator=gen)
+    d_ct = torch.empty_like(d_pt)
+    d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+    before = engine.launch_count
+    engine.batch_crypt_uniform_device(0, d_iv, d_aad, alen, alen, d_pt, d_ct, length, length, d_tags, n_msgs=n_msgs)
+    torch.cuda.synchronize()
+    assert engine.launch_count - before == 2              # k_batch_cta (split) + k_batch_split_finish
+    for i in (0, 1, n_msgs // 2, n_msgs - 1):
+        pt = d_pt[i * length:(i + 1) * length].cpu().numpy().tobytes()
+        iv = d_iv[12 * i:12 * i + 12].cpu().numpy().tobytes()
+        aad = d_aad[alen * i:alen * (i + 1)].cpu().numpy().tobytes()
+        want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt)
+        assert d_ct[i * length:(i + 1) * length].cpu().numpy().tobytes() == want_ct, i
+        assert d_tags[16 * i:16 * i + 16].cpu().numpy().tobytes() == want_tag, i
+    # the same tags from the unsplit layout
+    d_tags1 = torch.zeros_like(d_tags)
+    d_ct1 = torch.empty_like(d_pt)
+    engine.batch_crypt_uniform_device(0, d_iv, d_aad, alen, alen, d_pt, d_ct1, length, length, d_tags1, n_msgs=n_msgs, lanes=1024)
+    torch.cuda.synchronize()
+    assert torch.equal(d_tags, d_tags1) and torch.equal(d_ct, d_ct1)
+    del d_ct1
+    d_tags[16 * 5 + 2] ^= 0x08
+    d_ok = torch.zeros(n_msgs, dtype=torch.uint8, device="cuda")
+    engine.batch_crypt_uniform_device(1, d_iv, d_aad, alen, alen, d_ct, d_ct, length, length, d_tags, d_ok, n_msgs=n_msgs)
+    torch.cuda.synchronize()
+    assert torch.equal(d_ct, d_pt)
+    ok = d_ok.cpu().numpy()
+    assert ok[5] == 0 and int(ok.sum()) == n_msgs - 1
 
 
 def test_config3_shape_strided_packets(engine, oracle, torch_mod):

@@ -103,6 +103,44 @@ def test_batch_lanes(emul, oracle, G):
                 assert (tag == et).all(), (kb, G)
 
 
+@pytest.mark.parametrize("S", [2, 4, 16])
+def test_batch_split_segments(emul, oracle, S):
+    """Messages cut into S counter-range segments (the split layout of k_batch_cta): AAD with
+    segment 0, length block with segment S-1, partials scaled by H^after and XORed.  Includes
+    messages shorter than S blocks (empty segments), ragged tails and empty payloads."""
+    rng = np.random.default_rng(300 + S)
+    for kb, G in ((16, 4), (32, 32), (24, 8)):
+        for dec in (0, 1):
+            nm = 8
+            lens = rng.integers(0, 400, nm)
+            lens[0], lens[1], lens[2], lens[3], lens[4] = 0, 16, 16 * 300 + 5, 33, 16 * S * 7
+            alens = rng.integers(0, 70, nm)
+            alens[2], alens[3] = 0, 16
+            in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+            aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.uint64)
+            data = rng.integers(0, 256, int(in_off[-1]) + 1, dtype=np.uint8)
+            aad = rng.integers(0, 256, int(aad_off[-1]) + 1, dtype=np.uint8)
+            ivs = rng.integers(0, 256, 12 * nm, dtype=np.uint8)
+            key = rng.integers(0, 256, kb, dtype=np.uint8)
+            rk = np.frombuffer(oracle.key_expand(key.tobytes()), dtype=np.uint8).copy()
+            nr = len(rk) // 16 - 1
+            eo, et = oracle.gcm_batch(key, kb, True, ivs, aad, aad_off, data[:int(in_off[-1])], in_off, decrypt=bool(dec))
+            out = np.zeros_like(data)
+            tag = np.zeros(16 * nm, np.uint8)
+            ok = np.zeros(nm, np.uint8)
+            if dec:
+                tag[:] = et
+                tag[16 * 2 + 9] ^= 0x01
+            rc = emul.emul_batch_split(u8p(rk), nr, dec, G, S, u8p(ivs), u8p(aad), u64p(aad_off), u8p(data), u64p(in_off),
+                                       u8p(out), u8p(tag), u8p(ok), ctypes.c_uint64(nm))
+            assert rc == 0
+            assert (out[:int(in_off[-1])] == eo).all(), (kb, G, dec)
+            if dec:
+                assert list(ok) == [1, 1, 0, 1, 1, 1, 1, 1]
+            else:
+                assert (tag == et).all(), (kb, G)
+
+
 @pytest.mark.parametrize("kb", [16, 24, 32])
 def test_perkey_messages(emul, oracle, kb):
     """One distinct key per message: on-the-fly key schedule + private 4-bit GHASH table."""
