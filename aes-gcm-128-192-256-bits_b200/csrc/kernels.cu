@@ -66,11 +66,23 @@ struct TeGlobal {
     }
 };
 
-__device__ __forceinline__ void fill_aes_tables(const uint32_t* __restrict__ te0)
+// Te0 (1 KB) is staged once through the reduction scratch with one coalesced load per thread, so
+// the 16 expansion passes read shared memory instead of paying a global-load latency each: the
+// table fill is most of a short message's kernel time.  Order at the call sites: stage_te0 and
+// fill_gh_tables (their global loads overlap), __syncthreads, expand_aes_tables, __syncthreads.
+__device__ __forceinline__ void stage_te0(const uint32_t* __restrict__ te0)
 {
+    uint32_t* stage = reinterpret_cast<uint32_t*>(ag_smem + SM_MISC);
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) stage[i] = __ldg(te0 + i);
+}
+
+__device__ __forceinline__ void expand_aes_tables()
+{
+    const uint32_t* stage = reinterpret_cast<const uint32_t*>(ag_smem + SM_MISC);
+#pragma unroll 4
     for (uint32_t idx = threadIdx.x; idx < 256 * 32; idx += blockDim.x) {
         const uint32_t x = idx >> 5, l = idx & 31;
-        const uint32_t t = __ldg(te0 + x);
+        const uint32_t t = stage[x];
         uint32_t* a = reinterpret_cast<uint32_t*>(ag_smem + SM_AES_A + x * 256 + l * 4);
         uint32_t* b = reinterpret_cast<uint32_t*>(ag_smem + SM_AES_B + x * 256 + l * 4);
         a[0] = t;
@@ -82,6 +94,7 @@ __device__ __forceinline__ void fill_aes_tables(const uint32_t* __restrict__ te0
 
 __device__ __forceinline__ void fill_gh_tables(const uint4* __restrict__ ta, const uint4* __restrict__ tb)
 {
+#pragma unroll 4
     for (uint32_t idx = threadIdx.x; idx < 256 * 8; idx += blockDim.x) {
         const uint32_t b = idx >> 3, r = idx & 7;
         uint4* d = reinterpret_cast<uint4*>(ag_smem + SM_GH + b * 256 + r * 16);
@@ -320,8 +333,10 @@ template <int NR, int MODE, bool ALIGNED>
 __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_constant__ StreamParams p)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
-    if (MODE != AG_MODE_GHASH_ONLY) fill_aes_tables(p.te0);
+    if (MODE != AG_MODE_GHASH_ONLY) stage_te0(p.te0);
     if (MODE != AG_MODE_CTR_ONLY) fill_gh_tables(p.key->tab[7], nullptr);
+    __syncthreads();
+    if (MODE != AG_MODE_GHASH_ONLY) expand_aes_tables();
     __syncthreads();
 
     TeSmem te{ag_smem, lane * 4};
@@ -458,8 +473,10 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
     constexpr int LG = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : 5;
-    fill_aes_tables(p.te0);
+    stage_te0(p.te0);
     fill_gh_tables(p.key->tab[LG], p.key->tab[0]);
+    __syncthreads();
+    expand_aes_tables();
     __syncthreads();
 
     TeSmem te{ag_smem, lane * 4};
@@ -554,8 +571,10 @@ template <int NR, bool DEC>
 __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_constant__ BatchParams p)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
-    fill_aes_tables(p.te0);
+    stage_te0(p.te0);
     fill_gh_tables(p.key->tab[6], nullptr);
+    __syncthreads();
+    expand_aes_tables();
     __syncthreads();
     TeSmem te{ag_smem, lane * 4};
     GhSmem gh_g{ag_smem + SM_GH, (lane & 7) * 16};
