@@ -1,0 +1,22 @@
+#!/usr/bin/env python
+"""Probe: one AAD-heavy batch point of config 5 (16 KiB payload + 256 KiB AAD per message, ~1 GiB) through
+agcm_batch_crypt_uniform, for an ncu capture of the lane-group kernel on GHASH-dominated work."""
+import sys, os
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch, aesgcm_b200
+eng = aesgcm_b200.GcmEngine(0); eng.set_key(bytes(range(32)))
+size, alen = 16384, 262144
+n = (1 << 30) // (size + alen)
+d_in = torch.randint(0, 256, (n * size,), dtype=torch.uint8, device="cuda"); d_out = torch.empty_like(d_in)
+d_aad = torch.randint(0, 256, (n * alen,), dtype=torch.uint8, device="cuda")
+d_iv = torch.randint(0, 256, (n * 12,), dtype=torch.uint8, device="cuda"); d_tags = torch.zeros(16 * n, dtype=torch.uint8, device="cuda")
+for _ in range(3):
+    eng.batch_crypt_uniform_device(0, d_iv, d_aad, alen, alen, d_in, d_out, size, size, d_tags, n_msgs=n)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    eng.batch_crypt_uniform_device(0, d_iv, d_aad, alen, alen, d_in, d_out, size, size, d_tags, n_msgs=n)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 5
+print("n", n, "ms", ms, "total GB/s", n * (size + alen) / ms / 1e6)
