@@ -312,18 +312,18 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, 
     // 2.5 rows for a CTA: lane weights, two barriers) are fitted to profiles/r1_lane_sweep.md.
     if (avg_len >= (uint64_t)c->nt * 16 * 4) {
         const uint64_t groups = total_lanes / g;
-        const double t_g = (double)((n_msgs + groups - 1) / groups) * ((double)blocks / (double)g + 2.0);
+        const double t_g = (double)((n_msgs + groups - 1) / groups) * ((double)blocks / (double)g + 3.0);
         const double t_cta = (double)((n_msgs + (uint64_t)c->ncta - 1) / (uint64_t)c->ncta) *
-                             ((double)blocks / (double)c->nt + 2.5);
+                             ((double)blocks / (double)c->nt + 3.5);
         if (t_cta < t_g) {
             // few long messages: cut each into S counter-range segments so that the last round
-            // of CTAs is full too (a segment pays about 1.5 more rows for its H^after scaling)
+            // of CTAs is full too
             int best = 1024;
             double t_best = t_cta;
             for (uint64_t S = 2; S <= 256; S <<= 1) {
                 const double rows = (double)blocks / (double)(S * (uint64_t)c->nt);
                 if (rows < 8.0) break;
-                const double t = (double)((n_msgs * S + (uint64_t)c->ncta - 1) / (uint64_t)c->ncta) * (rows + 4.0);
+                const double t = (double)((n_msgs * S + (uint64_t)c->ncta - 1) / (uint64_t)c->ncta) * (rows + 5.0);
                 if (t < 0.97 * t_best) {
                     t_best = t;
                     best = 1024 + (int)S;
@@ -997,8 +997,11 @@ int agcm_batch_crypt_uniform_host(agcm_ctx* c, int decrypt, int lanes, const uin
     if (m_chunk > m_aux) m_chunk = m_aux;
     if (m_chunk == 0) return AGCM_E_BAD_LEN;  // one record larger than the staging granule: use the stream API
     // fix the lane count once so every chunk runs the same kernel
-    const int g = pick_lanes(c, lanes, n_msgs < m_chunk ? n_msgs : m_chunk, len);
+    int g = pick_lanes(c, lanes, n_msgs < m_chunk ? n_msgs : m_chunk, len);
     if (g < 0) return AGCM_E_BAD_ARG;
+    // the chunks run concurrently on the pipeline's streams and the segment layout keeps its
+    // partials in one scratch buffer per context: whole-message layouts only on this path
+    if (g > 1024) g = 1024;
     uint64_t k = 0;
     for (uint64_t m0 = 0; m0 < n_msgs; m0 += m_chunk, ++k) {
         const int s = (int)(k % kSlots);

@@ -580,6 +580,13 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
     GhSmem gh_g{ag_smem + SM_GH, (lane & 7) * 16};
     gf128* red = reinterpret_cast<gf128*>(ag_smem + SM_MISC);
     const gf128 wgt = p.key->hpow_thread[nt - tid];
+    // H^after cache of the split layout, 4 direct-mapped entries (key 0 = empty): with equal-length
+    // messages a CTA meets at most a few distinct exponents, and one exponentiation by a single
+    // warp (seven dependent generic products, the rest of the CTA waiting) costs ~20 us
+    uint64_t* pow_keys = reinterpret_cast<uint64_t*>(ag_smem + SM_MISC + 1056);
+    gf128* pow_vals = reinterpret_cast<gf128*>(ag_smem + SM_MISC + 1088);
+    if (tid < 4) pow_keys[tid] = 0;
+    __syncthreads();
     // One unit per CTA pass: a whole message, or (split > 1) one counter-range segment of it --
     // a few long messages would otherwise leave the grid idle in the last round (256 messages on
     // 148 CTAs: 2 rounds, 86 % busy).  A segment's partial is scaled by H^(blocks after it), the
@@ -619,7 +626,19 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
             const uint32_t* ej = reinterpret_cast<const uint32_t*>(ag_smem + SM_MISC + 1024);
             if (S > 1) {
                 if (after) {  // uniform
-                    const gf128 ha = warp_gf_pow(p.key, after);
+                    const uint32_t slot = seg & 3u;
+                    gf128 ha;
+                    if (pow_keys[slot] == after) {
+                        ha = pow_vals[slot];
+                    } else {
+                        ha = warp_gf_pow(p.key, after);
+                        __syncwarp();
+                        if (tid == 0) {
+                            pow_vals[slot] = ha;
+                            pow_keys[slot] = after;
+                        }
+                        __syncwarp();
+                    }
                     r = gf_mul(r, ha);
                 }
                 if (tid == 0) {

@@ -147,7 +147,9 @@ int agcm_stream_crypt_peer(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12],
  * 1024+S, S a power of two up to 256 = one CTA per 1/S of a message: counter-range segments whose
  * scaled GHASH partials a second launch XORs into the tag, for so few long messages
  * that whole messages would leave CTAs idle) or 0 = choose from n_msgs and
- * avg_len_hint.  Every choice produces the same bytes. */
+ * avg_len_hint.  Every choice produces the same bytes.  The segment layout keeps its
+ * partials in a per-context scratch buffer (grown on demand, which synchronises the
+ * device the first time): one such call in flight per context. */
 int agcm_batch_crypt(agcm_ctx* ctx, int decrypt, int lanes, uint64_t avg_len_hint, const uint8_t* d_iv12,
                      const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
                      uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);

@@ -10,13 +10,14 @@ n = (1 << 30) // (size + alen)
 d_in = torch.randint(0, 256, (n * size,), dtype=torch.uint8, device="cuda"); d_out = torch.empty_like(d_in)
 d_aad = torch.randint(0, 256, (n * alen,), dtype=torch.uint8, device="cuda")
 d_iv = torch.randint(0, 256, (n * 12,), dtype=torch.uint8, device="cuda"); d_tags = torch.zeros(16 * n, dtype=torch.uint8, device="cuda")
-for _ in range(3):
-    eng.batch_crypt_uniform_device(0, d_iv, d_aad, alen, alen, d_in, d_out, size, size, d_tags, n_msgs=n)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(5):
-    eng.batch_crypt_uniform_device(0, d_iv, d_aad, alen, alen, d_in, d_out, size, size, d_tags, n_msgs=n)
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / 5
-print("n", n, "ms", ms, "total GB/s", n * (size + alen) / ms / 1e6)
+for lanes in [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["0"])]:
+    for _ in range(3):
+        eng.batch_crypt_uniform_device(0, d_iv, d_aad, alen, alen, d_in, d_out, size, size, d_tags, n_msgs=n, lanes=lanes)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        eng.batch_crypt_uniform_device(0, d_iv, d_aad, alen, alen, d_in, d_out, size, size, d_tags, n_msgs=n, lanes=lanes)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print("lanes", lanes, "n", n, "ms", round(ms, 4), "total GB/s", round(n * (size + alen) / ms / 1e6, 1), flush=True)
