@@ -50,6 +50,9 @@ struct agcm_ctx {
     uint32_t peer_epoch = 0;
     uint32_t h_rk[60];
     uint8_t h_H[16];
+    uint8_t h_key_in[240];           // the key as it was loaded, to recognise a reload of the same key
+    size_t key_in_len = 0;
+    int key_in_mode = 0, key_in_pre = 0;
     int nr = 0;
     bool key_set = false;
     cudaError_t last_err = cudaSuccess;
@@ -416,6 +419,7 @@ void agcm_ctx_destroy(agcm_ctx* c)
     if (c->d_scratch) cudaMemset(c->d_scratch, 0, SC_BYTES);
     memset(c->h_rk, 0, sizeof(c->h_rk));
     memset(c->h_H, 0, sizeof(c->h_H));
+    memset(c->h_key_in, 0, sizeof(c->h_key_in));
     cudaFree(c->d_chunk_partials);
     cudaFree(c->d_aad_stage);
     cudaFree(c->d_te0);
@@ -499,6 +503,11 @@ int agcm_set_key(agcm_ctx* c, int mode, int pre_expanded, const uint8_t* h_key, 
     if (!nr) return AGCM_E_BAD_MODE;
     const size_t want = pre_expanded ? (size_t)16 * (nr + 1) : (size_t)mode / 8;
     if (key_len != want) return AGCM_E_BAD_MODE;
+    // the same key again: H, its powers and the tables are still valid (the IP keeps H until a
+    // NEW key arrives, src/gcm_ghash.vhd:123-139)
+    if (c->key_set && c->key_in_mode == mode && c->key_in_pre == (pre_expanded ? 1 : 0) && c->key_in_len == key_len &&
+        memcmp(c->h_key_in, h_key, key_len) == 0)
+        return AGCM_OK;
     AG_CUDA(c, cudaSetDevice(c->device));
     c->key_set = false;
     c->pow_n = ~0ull;
@@ -526,6 +535,10 @@ int agcm_set_key(agcm_ctx* c, int mode, int pre_expanded, const uint8_t* h_key, 
         c->h_H[4 * i + 3] = (uint8_t)hw[i];
     }
     c->nr = nr;
+    memcpy(c->h_key_in, h_key, key_len);
+    c->key_in_len = key_len;
+    c->key_in_mode = mode;
+    c->key_in_pre = pre_expanded ? 1 : 0;
     c->key_set = true;
     return AGCM_OK;
 }

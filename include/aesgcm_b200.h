@@ -90,7 +90,8 @@ int agcm_key_expand_host(agcm_ctx* ctx, int mode, const uint8_t* h_key, uint8_t*
  * src/gcm_ghash.vhd:128-139), its powers and the Shoup tables; H stays valid
  * until the next agcm_set_key (src/gcm_ghash.vhd:123).  Synchronous: it first waits for all
  * work queued on the device (no earlier call may still read the old key), runs one kernel and
- * reads the stage keys and H back; about 75 us. */
+ * reads the stage keys and H back; about 75 us.  Loading the key that is already
+ * loaded returns at once: H is kept until a NEW key arrives, as in the IP. */
 int agcm_set_key(agcm_ctx* ctx, int mode, int pre_expanded, const uint8_t* h_key, size_t key_len);
 int agcm_get_round_keys(const agcm_ctx* ctx, uint8_t* h_round_keys, size_t cap); /* returns byte count */
 int agcm_get_h(const agcm_ctx* ctx, uint8_t h_h16[16]);

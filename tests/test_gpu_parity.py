@@ -68,6 +68,20 @@ def test_set_key_raw_and_preexpanded(engine, oracle):
         assert engine.hash_subkey() == h
         engine.set_key(rk)  # pre-expanded stages, used as they are
         assert engine.round_keys() == rk and engine.hash_subkey() == h
+        # the same key again keeps H and the tables (src/gcm_ghash.vhd:123-139): no kernel runs;
+        # a different key, or the same bytes in the other format, is a new load
+        n0 = engine.launch_count
+        engine.set_key(rk)
+        assert engine.launch_count == n0 and engine.hash_subkey() == h
+        iv, pt = _rb(rng, 12), _rb(rng, 100)
+        ct1, tag1 = engine.encrypt(iv, b"", pt)
+        engine.set_key(key)
+        assert engine.launch_count > n0
+        ct2, tag2 = engine.encrypt(iv, b"", pt)
+        assert (ct1, tag1) == (ct2, tag2) == oracle.gcm_crypt(key, iv, b"", pt)
+        other = bytes(b ^ 1 for b in key)
+        engine.set_key(other)
+        assert engine.encrypt(iv, b"", pt) == oracle.gcm_crypt(other, iv, b"", pt)
     import aesgcm_b200
     with pytest.raises(aesgcm_b200.AgcmError):
         engine.set_key(b"x" * 17)
