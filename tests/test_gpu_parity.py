@@ -722,8 +722,9 @@ def test_fuzz_all_paths(engine, engine_small, oracle, torch_mod):
     """Seeded fuzz over every device entry point: random key size, direction, lengths, AAD lengths,
     byte alignment, lane counts, shard position (incl. counters that wrap 2^32)."""
     torch = torch_mod
-    rng = np.random.default_rng(2026)
-    for it in range(60):
+    # soak runs: AGCM_FUZZ_SEED / AGCM_FUZZ_ITERS override the committed seed and length
+    rng = np.random.default_rng(int(os.environ.get("AGCM_FUZZ_SEED", "2026")))
+    for it in range(int(os.environ.get("AGCM_FUZZ_ITERS", "60"))):
         eng = engine if it % 2 else engine_small
         kb = int(rng.choice([16, 24, 32]))
         key, iv = _rb(rng, kb), _rb(rng, 12)
@@ -760,7 +761,7 @@ def test_fuzz_all_paths(engine, engine_small, oracle, torch_mod):
         ivs = rng.integers(0, 256, 12 * nm, dtype=np.uint8)
         w_out, w_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), kb, True, ivs, aad, aad_off, msg, in_off,
                                          decrypt=False, threads=8)
-        lanes = int(rng.choice([0, 1, 2, 4, 8, 16, 32, 1024]))
+        lanes = int(rng.choice([0, 1, 2, 4, 8, 16, 32, 1024, 1026, 1032]))
         d_out = torch.zeros(max(1, msg.size), dtype=torch.uint8, device="cuda")
         d_tags = torch.zeros(16 * nm, dtype=torch.uint8, device="cuda")
         d_io, d_ao = torch.from_numpy(in_off.view(np.int64)).cuda(), torch.from_numpy(aad_off.view(np.int64)).cuda()
