@@ -39,6 +39,7 @@ SIGNATURES = {
     "agcm_get_round_keys": (c_int, [c_vp, c_u8p, c_sz]),
     "agcm_get_h": (c_int, [c_vp, c_u8p]),
     "agcm_stream_crypt": (c_int, [c_vp, c_int, c_u8p, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u8p, c_u8p, c_vp]),
+    "agcm_stream_crypt_iv": (c_int, [c_vp, c_int, c_u8p, c_sz, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u8p, c_u8p, c_vp]),
     "agcm_stream_part": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_vp]),
     "agcm_stream_finish": (c_int, [c_vp, c_int, c_u8p, c_u8p, c_int, c_u8p, c_u64, c_u64, c_u8p, c_u8p, c_vp]),
     "agcm_peer_setup": (c_int, [c_vp, c_int, c_int, ctypes.POINTER(c_u64)]),
@@ -55,6 +56,8 @@ SIGNATURES = {
                                                 c_u64, c_u64, c_u8p, c_u8p, c_sz, c_vp]),
     "agcm_stream_crypt_host": (c_int, [c_vp, c_int, c_u8p, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u8p,
                                        ctypes.POINTER(c_int)]),
+    "agcm_stream_crypt_iv_host": (c_int, [c_vp, c_int, c_u8p, c_sz, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u8p,
+                                          ctypes.POINTER(c_int)]),
     "agcm_stream_part_host": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p]),
     "agcm_stream_finish_host": (c_int, [c_vp, c_int, c_u8p, c_u8p, c_int, c_u8p, c_u64, c_u64, c_u8p,
                                         ctypes.POINTER(c_int)]),

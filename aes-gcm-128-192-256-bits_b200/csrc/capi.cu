@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <vector>
 
 #include "../../include/aesgcm_b200.h"
 #include "kernels.h"
@@ -25,6 +26,7 @@ constexpr size_t SC_PART_CT = 0;     // 16
 constexpr size_t SC_TAGCALC = 32;    // 16
 constexpr size_t SC_OK = 48;         // 1
 constexpr size_t SC_TAG = 64;        // 16 (host API)
+constexpr size_t SC_J0 = 80;         // 16: J0 of a non-96-bit IV
 constexpr size_t SC_KEY = 96;        // 32 raw key upload
 constexpr size_t SC_PARTS = 256;     // list of 16 B partials for finish (user parts + AAD part)
 constexpr size_t SC_PARTS_MAX = 1024;
@@ -43,6 +45,9 @@ struct agcm_ctx {
     uint32_t* d_counters = nullptr;  // last-CTA tickets: [0] context scratch, [1+s] pipeline slot s
     uint32_t* d_pow_n = nullptr;     // cached H^n (4 BE words) for the tag finish
     uint64_t pow_n = ~0ull;          // exponent it was computed for (~0 = none)
+    uint32_t j0ctr = 1;              // counter field of J0 for the call in progress (1 for a 96-bit IV)
+    uint8_t* d_iv_stage = nullptr;   // padded long IV for the J0 derivation
+    size_t iv_stage_cap = 0;
     // peer-memory exchange (multi-GPU)
     uint8_t** d_peer_bufs = nullptr; // device array of world pointers
     uint32_t* d_peer_status = nullptr;
@@ -156,7 +161,8 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
     memset(&p, 0, sizeof(p));
     memcpy(p.rk, c->h_rk, sizeof(p.rk));
     iv_words(iv, p.iv);
-    p.ctr0 = (uint32_t)(2 + first_block);
+    p.ctr0 = (uint32_t)(c->j0ctr + 1 + first_block);   // inc32 from J0 (2 + first_block for a 96-bit IV)
+    p.j0w = __builtin_bswap32(c->j0ctr);
     p.n_bytes = n_bytes;
     p.in = d_in;
     p.out = d_out;
@@ -238,6 +244,7 @@ int run_finish(agcm_ctx* c, int decrypt, const uint8_t iv[12], const uint8_t* d_
     memcpy(f.rk, c->h_rk, sizeof(f.rk));
     f.nr = (uint32_t)c->nr;
     iv_words(iv, f.iv);
+    f.j0w = __builtin_bswap32(c->j0ctr);
     f.key = c->d_key;
     f.te0 = c->d_te0;
     f.parts = parts;
@@ -270,6 +277,11 @@ int reserve_aad_stage(agcm_ctx* c, uint64_t aad_len)
     c->aad_stage_cap = aad_len;
     return AGCM_OK;
 }
+
+// J0 of an IV that is not 96 bits long (SP 800-38D 7.1 step 2): GHASH_H(IV || 0^(s+64) || [len(IV)]_64),
+// computed by the device (k_stream<GHASH_ONLY>) and read back; the message then runs with the
+// first 96 bits of J0 as its "IV" and J0's last 32 bits as the counter field.  Synchronises `st`.
+int derive_j0(agcm_ctx* c, const uint8_t* h_iv, size_t iv_len, uint8_t j0[16], cudaStream_t st);
 
 int ensure_pipeline(agcm_ctx* c)
 {
@@ -338,6 +350,35 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, 
     return (int)g;
 }
 
+}  // namespace
+
+namespace {
+int derive_j0(agcm_ctx* c, const uint8_t* h_iv, size_t iv_len, uint8_t j0[16], cudaStream_t st)
+{
+    if (!h_iv || iv_len == 0 || iv_len > (1ull << 32)) return AGCM_E_BAD_LEN;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    const size_t padded = ((iv_len + 15) & ~(size_t)15) + 16;
+    std::vector<uint8_t> buf(padded, 0);
+    memcpy(buf.data(), h_iv, iv_len);
+    const uint64_t bits = (uint64_t)iv_len * 8;
+    for (int i = 0; i < 8; ++i) buf[padded - 1 - i] = (uint8_t)(bits >> (8 * i));
+    if (padded > c->iv_stage_cap) {
+        AG_CUDA(c, cudaFree(c->d_iv_stage));
+        c->d_iv_stage = nullptr;
+        c->iv_stage_cap = 0;
+        const size_t cap = padded < 4096 ? 4096 : padded;
+        AG_CUDA(c, cudaMalloc(&c->d_iv_stage, cap));
+        c->iv_stage_cap = cap;
+    }
+    AG_CUDA(c, cudaMemcpyAsync(c->d_iv_stage, buf.data(), padded, cudaMemcpyHostToDevice, st));
+    const uint8_t iv0[12] = {0};
+    int rc = run_stream(c, AG_MODE_GHASH_ONLY, iv0, 0, c->d_iv_stage, nullptr, padded, 0, c->d_parts, c->d_scratch + SC_J0, st,
+                        c->d_counters);
+    if (rc) return rc;
+    AG_CUDA(c, cudaMemcpyAsync(j0, c->d_scratch + SC_J0, 16, cudaMemcpyDeviceToHost, st));
+    AG_CUDA(c, cudaStreamSynchronize(st));
+    return AGCM_OK;
+}
 }  // namespace
 
 #pragma GCC visibility push(default)
@@ -426,6 +467,7 @@ void agcm_ctx_destroy(agcm_ctx* c)
     cudaFree(c->d_key);
     cudaFree(c->d_parts);
     cudaFree(c->d_seg_parts);
+    cudaFree(c->d_iv_stage);
     cudaFree(c->d_scratch);
     cudaFree(c->d_counters);
     cudaFree(c->d_pow_n);
@@ -612,6 +654,21 @@ int agcm_stream_crypt(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const 
     int rc = agcm_stream_part(c, decrypt, h_iv12, 0, d_in, d_out, n_bytes, 0, part, stream);
     if (rc) return rc;
     return agcm_stream_finish(c, decrypt, h_iv12, part, 1, d_aad, aad_len, n_bytes, d_tag, d_ok, stream);
+}
+
+int agcm_stream_crypt_iv(agcm_ctx* c, int decrypt, const uint8_t* h_iv, size_t iv_len, const uint8_t* d_aad, uint64_t aad_len,
+                         const uint8_t* d_in, uint8_t* d_out, uint64_t n_bytes, uint8_t* d_tag, uint8_t* d_ok, void* stream)
+{
+    if (!c || !h_iv) return AGCM_E_BAD_ARG;
+    if (iv_len == 12) return agcm_stream_crypt(c, decrypt, h_iv, d_aad, aad_len, d_in, d_out, n_bytes, d_tag, d_ok, stream);
+    AG_CUDA(c, cudaSetDevice(c->device));
+    uint8_t j0[16];
+    int rc = derive_j0(c, h_iv, iv_len, j0, (cudaStream_t)stream);
+    if (rc) return rc;
+    c->j0ctr = ((uint32_t)j0[12] << 24) | ((uint32_t)j0[13] << 16) | ((uint32_t)j0[14] << 8) | (uint32_t)j0[15];
+    rc = agcm_stream_crypt(c, decrypt, j0, d_aad, aad_len, d_in, d_out, n_bytes, d_tag, d_ok, stream);
+    c->j0ctr = 1;
+    return rc;
 }
 
 int agcm_peer_setup(agcm_ctx* c, int rank, int world, const uint64_t* h_peer_ptrs)
@@ -988,6 +1045,24 @@ int agcm_stream_crypt_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], c
     AG_CUDA(c, cudaStreamSynchronize(c->hs[0]));
     if (h_ok) *h_ok = okb ? 1 : 0;
     return AGCM_OK;
+}
+
+int agcm_stream_crypt_iv_host(agcm_ctx* c, int decrypt, const uint8_t* h_iv, size_t iv_len, const uint8_t* h_aad,
+                              uint64_t aad_len, const uint8_t* h_in, uint8_t* h_out, uint64_t n_bytes, uint8_t h_tag[16],
+                              int* h_ok)
+{
+    if (!c || !h_iv) return AGCM_E_BAD_ARG;
+    if (iv_len == 12) return agcm_stream_crypt_host(c, decrypt, h_iv, h_aad, aad_len, h_in, h_out, n_bytes, h_tag, h_ok);
+    AG_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc) return rc;
+    uint8_t j0[16];
+    rc = derive_j0(c, h_iv, iv_len, j0, c->hs[0]);
+    if (rc) return rc;
+    c->j0ctr = ((uint32_t)j0[12] << 24) | ((uint32_t)j0[13] << 16) | ((uint32_t)j0[14] << 8) | (uint32_t)j0[15];
+    rc = agcm_stream_crypt_host(c, decrypt, j0, h_aad, aad_len, h_in, h_out, n_bytes, h_tag, h_ok);
+    c->j0ctr = 1;
+    return rc;
 }
 
 int agcm_batch_crypt_uniform_host(agcm_ctx* c, int decrypt, int lanes, const uint8_t* h_iv12, const uint8_t* h_aad,

@@ -113,7 +113,9 @@ AG_HD void ag_mask_block(uint32_t x[4], uint32_t nvalid)
 struct StreamParams {
     uint32_t rk[60];
     uint32_t iv[3];       // the 12 IV bytes as LE words
-    uint32_t ctr0;        // counter of this shard's block 0 = 2 + first_block (mod 2^32; aes_icb.vhd:100)
+    uint32_t ctr0;        // counter of this shard's block 0 = J0 counter + 1 + first_block (mod 2^32; = 2 + first_block
+                          // for a 96-bit IV, aes_icb.vhd:100)
+    uint32_t j0w;         // counter word of J0 as the AES state holds it (byte-swapped; 0x01000000 for a 96-bit IV)
     uint64_t n_bytes;     // bytes in this shard
     const uint8_t* in;
     uint8_t* out;

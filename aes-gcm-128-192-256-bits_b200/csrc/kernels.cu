@@ -243,6 +243,7 @@ struct FinishArgs {
     const uint32_t* rk;
     uint32_t nr;
     const uint32_t* iv;
+    uint32_t j0w;         // counter word of J0 (byte-swapped)
     const KeyDev* key;
     const uint32_t* te0;
     const uint8_t* aad;
@@ -294,10 +295,10 @@ __device__ void finish_warp(const FinishArgs& p, gf128 s)
         uint32_t e[4];
         if (p.smem_tables) {
             TeSmem te{ag_smem, 0};
-            aes_encrypt_words(p.rk, (int)p.nr, p.iv[0], p.iv[1], p.iv[2], 0x01000000u, te, e);  // J0 = IV || 00000001
+            aes_encrypt_words(p.rk, (int)p.nr, p.iv[0], p.iv[1], p.iv[2], p.j0w, te, e);  // J0 (= IV || 00000001 for a 96-bit IV)
         } else {
             TeGlobal te{p.te0};
-            aes_encrypt_words(p.rk, (int)p.nr, p.iv[0], p.iv[1], p.iv[2], 0x01000000u, te, e);
+            aes_encrypt_words(p.rk, (int)p.nr, p.iv[0], p.iv[1], p.iv[2], p.j0w, te, e);
         }
         uint32_t t[4] = {ag_bswap32(s.w[0]) ^ e[0], ag_bswap32(s.w[1]) ^ e[1], ag_bswap32(s.w[2]) ^ e[2],
                          ag_bswap32(s.w[3]) ^ e[3]};
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(32) k_stream_finish(const __grid_constant__ Fi
         s = gf_xor(s, gf_from_le_words(x[0], x[1], x[2], x[3]));
     }
     s = warp_xor(s);
-    FinishArgs a{p.rk, p.nr, p.iv, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc, p.tag_expected, p.ok, p.hn, false};
+    FinishArgs a{p.rk, p.nr, p.iv, p.j0w, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc, p.tag_expected, p.ok, p.hn, false};
     finish_warp(a, s);
 }
 
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_con
                     if (!__all_sync(0xffffffffu, arrived) && tid == 0 && p.peer_status) *p.peer_status = 1;
                 }
                 if (p.fuse_finish) {
-                    FinishArgs a{p.rk, (uint32_t)NR, p.iv, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc,
+                    FinishArgs a{p.rk, (uint32_t)NR, p.iv, p.j0w, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc,
                                  p.tag_expected, p.ok, p.hn, MODE != AG_MODE_GHASH_ONLY};
                     finish_warp(a, s);
                 }

@@ -9,6 +9,7 @@ struct FinishParams {
     uint32_t rk[60];
     uint32_t nr;
     uint32_t iv[3];
+    uint32_t j0w;                 // counter word of J0, byte-swapped (0x01000000 for a 96-bit IV)
     const KeyDev* key;
     const uint32_t* te0;
     const uint8_t* parts;         // n_parts x 16 B in natural GHASH byte order

@@ -153,9 +153,9 @@ class GcmEngine:
         return pt, ok
 
     def _crypt_host(self, decrypt, iv, aad, data, tag, out):
-        ivb = _np_u8(iv)
-        if ivb.size != 12:
-            raise _lib.AgcmError(_lib.E_BAD_LEN, "IV must be 96 bits (src/gcm_pkg.vhd:17)")
+        ivb = _np_u8(iv)   # 96 bits as in the reference IP (src/gcm_pkg.vhd:17), or any other length (SP 800-38D J0)
+        if ivb.size == 0:
+            raise _lib.AgcmError(_lib.E_BAD_LEN, "empty IV")
         a = _np_u8(aad)
         d = _np_u8(data)
         ret_bytes = out is None
@@ -169,8 +169,8 @@ class GcmEngine:
                 raise _lib.AgcmError(_lib.E_BAD_LEN, "tag must be 16 bytes")
             t[:] = tb
         ok = ctypes.c_int(1)
-        self._ck(self._L.agcm_stream_crypt_host(self._ctx, decrypt, _addr(ivb), _addr(a), a.size, _addr(d), _addr(o),
-                                                d.size, _addr(t), ctypes.byref(ok)))
+        self._ck(self._L.agcm_stream_crypt_iv_host(self._ctx, decrypt, _addr(ivb), ivb.size, _addr(a), a.size, _addr(d),
+                                                   _addr(o), d.size, _addr(t), ctypes.byref(ok)))
         res = o[: d.size].tobytes() if ret_bytes else o[: d.size]
         if decrypt:
             return res, bool(ok.value)
@@ -218,9 +218,9 @@ class GcmEngine:
     def stream_crypt_device(self, decrypt, iv, aad, data_in, data_out, tag, ok=None, n_bytes=None, stream=None):
         ivb = _np_u8(iv)
         n = data_in.numel() if n_bytes is None else int(n_bytes)
-        self._ck(self._L.agcm_stream_crypt(self._ctx, int(decrypt), _addr(ivb), _dptr(aad),
-                                           0 if aad is None else aad.numel(), _dptr(data_in), _dptr(data_out), n,
-                                           _dptr(tag), _dptr(ok), _stream(stream)))
+        self._ck(self._L.agcm_stream_crypt_iv(self._ctx, int(decrypt), _addr(ivb), ivb.size, _dptr(aad),
+                                              0 if aad is None else aad.numel(), _dptr(data_in), _dptr(data_out), n,
+                                              _dptr(tag), _dptr(ok), _stream(stream)))
 
     def stream_part_device(self, decrypt, iv, first_block, data_in, data_out, blocks_after, partial16, n_bytes=None,
                            stream=None):

@@ -21,8 +21,8 @@
  *     used from different threads at the same time.
  *   - Return 0 on success, a negative AGCM_E_* otherwise.  Nothing throws.
  *   - mode = key size in bits: 128 / 192 / 256 (src/aes_pkg.vhd:31-33 Nr=10/12/14).
- *   - IV is always 96 bits; the counter block is IV || cnt32, cnt = 1 for J0 and
- *     2.. for data (src/aes_icb.vhd:34,99-100,118).  More than 2^32-2 data
+ *   - IV is 96 bits as in the IP (the two *_iv entry points take any length); the counter
+ *     block is IV || cnt32, cnt = 1 for J0 and 2.. for data (src/aes_icb.vhd:34,99-100,118).  More than 2^32-2 data
  *     blocks per IV is AGCM_E_COUNTER_OVERFLOW (the IP raises its overflow flag,
  *     src/aes_icb.vhd:65,114,119).
  *   - There is no CPU fallback.  Every call needs a CUDA device of compute
@@ -108,6 +108,15 @@ int agcm_get_h(const agcm_ctx* ctx, uint8_t h_h16[16]);
 int agcm_stream_crypt(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], const uint8_t* d_aad, uint64_t aad_len,
                       const uint8_t* d_in, uint8_t* d_out, uint64_t n_bytes, uint8_t* d_tag, uint8_t* d_ok, void* stream);
 
+/* The same for an IV of ANY length (SP 800-38D 7.1: J0 = GHASH_H(IV || 0^(s+64) || [len(IV)]_64),
+ * derived on the device; iv_len == 12 is the plain call above).  The reference IP fixes the IV at
+ * 96 bits (src/gcm_pkg.vhd:17), so this goes beyond it; pycryptodome's AES.new(nonce=...), which
+ * the reference model calls (tb/gcm_model.py:18), accepts such nonces.  Synchronises `stream` once
+ * for the J0 readback.  h_iv is a HOST pointer. */
+int agcm_stream_crypt_iv(agcm_ctx* ctx, int decrypt, const uint8_t* h_iv, size_t iv_len, const uint8_t* d_aad,
+                         uint64_t aad_len, const uint8_t* d_in, uint8_t* d_out, uint64_t n_bytes, uint8_t* d_tag,
+                         uint8_t* d_ok, void* stream);
+
 /* Counter-range shard of one message (multi-GPU): blocks
  * [first_block, first_block + ceil(n_bytes/16)) of the message, counter start
  * 2 + first_block.  n_bytes must be a multiple of 16 unless this is the last
@@ -182,6 +191,10 @@ int agcm_batch_crypt_perkey_uniform(agcm_ctx* ctx, int mode, int decrypt, const 
  * encrypt). */
 int agcm_stream_crypt_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], const uint8_t* h_aad, uint64_t aad_len,
                            const uint8_t* h_in, uint8_t* h_out, uint64_t n_bytes, uint8_t h_tag[16], int* h_ok);
+/* host buffers, IV of any length (see agcm_stream_crypt_iv) */
+int agcm_stream_crypt_iv_host(agcm_ctx* ctx, int decrypt, const uint8_t* h_iv, size_t iv_len, const uint8_t* h_aad,
+                              uint64_t aad_len, const uint8_t* h_in, uint8_t* h_out, uint64_t n_bytes,
+                              uint8_t h_tag[16], int* h_ok);
 /* Host-buffer forms of agcm_stream_part / agcm_stream_finish (one rank's shard of a
  * sharded message; the 16-byte partials travel between ranks). */
 int agcm_stream_part_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* h_in,

@@ -135,6 +135,30 @@ def gcm_crypt(key: bytes, iv: bytes, aad: bytes, data, decrypt: bool = False, th
     return out[:n].tobytes(), tag.tobytes()
 
 
+def _pad16(b: bytes) -> bytes:
+    return bytes(b) + b"\0" * (-len(b) % 16)
+
+
+def gcm_crypt_any_iv(key: bytes, iv: bytes, aad: bytes, data: bytes, decrypt: bool = False):
+    """AES-GCM with an IV of any length, composed from the primitives above.  The reference fixes the
+    IV at 96 bits (src/gcm_pkg.vhd:17; J0 = IV || 0^31 || 1, src/aes_icb.vhd:34); for any other
+    length SP 800-38D 7.1 step 2 sets J0 = GHASH_H(IV || 0^(s+64) || [len(IV)]_64), the counter then
+    runs inc32 from J0 (src/aes_icb.vhd:99-100 semantics on J0's last word) and the tag is
+    GHASH_H(A, C) xor E_K(J0) (src/gcm_ghash.vhd:257,293).  Returns (out_bytes, computed_tag)."""
+    key, iv, aad, data = bytes(key), bytes(iv), bytes(aad), bytes(data)
+    if len(iv) == 12:
+        return gcm_crypt(key, iv, aad, data, decrypt=decrypt)
+    rk = key if len(key) in (176, 208, 240) else key_expand(key)
+    h = aes_encrypt_block(rk, b"\0" * 16)
+    j0 = ghash_absorb(h, _pad16(iv) + b"\0" * 8 + (8 * len(iv)).to_bytes(8, "big"))
+    c0 = int.from_bytes(j0[12:], "big")
+    out = gctr(rk, j0[:12], c0 + 1, data)
+    ct = data if decrypt else out
+    s = ghash_absorb(h, _pad16(aad) + _pad16(ct) + (8 * len(aad)).to_bytes(8, "big") + (8 * len(ct)).to_bytes(8, "big"))
+    ej0 = aes_encrypt_block(rk, j0)
+    return out, bytes(a ^ b for a, b in zip(s, ej0))
+
+
 def gcm_batch(keys, key_len, shared_key, ivs, aad, aad_off, data, in_off, decrypt=False, threads=1):
     """numpy arrays in, (out, tags) numpy arrays back.  keys: uint8 (n*key_len or key_len)."""
     n = len(in_off) - 1

@@ -157,6 +157,61 @@ def _stream_case(eng, oracle, kb, n, alen, rng):
     assert not ok
 
 
+def test_long_iv_vectors_engine(engine, oracle, torch_mod):
+    """IVs that are not 96 bits long (agcm_stream_crypt_iv / _iv_host: J0 = GHASH_H(IV || pad || len)
+    derived on the device): committed OpenSSL vectors incl. the published McGrew-Viega cases 5, 6,
+    11, 12, 17, 18, through the host and the device entry points, decrypt and forged tag."""
+    torch = torch_mod
+    for v in _load("long_iv_vectors.json")["vectors"]:
+        key, iv = bytes.fromhex(v["key"]), bytes.fromhex(v["iv"])
+        pt, aad = bytes.fromhex(v["pt"]), bytes.fromhex(v["aad"])
+        engine.set_key(key)
+        ct, tag = engine.encrypt(iv, aad, pt)
+        assert ct.hex() == v["ct"] and tag.hex() == v["tag"], v["name"]
+        assert engine.decrypt(iv, aad, ct, tag) == pt
+        bad = bytearray(tag)
+        bad[0] ^= 1
+        assert engine.decrypt(iv, aad, ct, bytes(bad), raise_on_fail=False)[1] is False
+        d_in, d_aad = _dev(torch, pt), (_dev(torch, aad) if aad else None)
+        d_out = torch.empty_like(d_in)
+        d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+        engine.stream_crypt_device(0, iv, d_aad, d_in, d_out, d_tag)
+        torch.cuda.synchronize()
+        assert d_out.cpu().numpy().tobytes().hex() == v["ct"] and d_tag.cpu().numpy().tobytes().hex() == v["tag"], v["name"]
+
+
+def test_long_iv_paths_vs_oracle(engine, engine_small, oracle, torch_mod):
+    """IV lengths from 1 byte to several KB (the IV itself spans more than one GHASH row), J0
+    counters that wrap 2^32 mid-message are whatever GHASH makes them; messages of several grid
+    rows, AAD beyond the inline limit (part + finish path), in place, both directions, both grids.
+    A 96-bit IV afterwards still gives the 96-bit result (the J0 counter does not leak)."""
+    torch = torch_mod
+    rng = np.random.default_rng(96)
+    for it, (eng, ivl, n, alen) in enumerate(((engine, 1, 100, 0), (engine, 16, 16 * 151552 + 33, 20),
+                                              (engine, 13, 70000, 5000), (engine_small, 60, 640 * 16 * 5 + 7, 16),
+                                              (engine_small, 4096 + 5, 3000, 4097), (engine, 20000, 1 << 20, 64),
+                                              (engine, 11, 0, 33))):
+        kb = (16, 24, 32)[it % 3]
+        key, iv, aad, pt = _rb(rng, kb), _rb(rng, ivl), _rb(rng, alen), _rb(rng, n)
+        eng.set_key(key)
+        want_ct, want_tag = oracle.gcm_crypt_any_iv(key, iv, aad, pt)
+        ct, tag = eng.encrypt(iv, aad, pt)
+        assert ct == want_ct and tag == want_tag, (it, "host")
+        assert eng.decrypt(iv, aad, ct, tag) == pt
+        d = _dev(torch, pt) if n else torch.zeros(1, dtype=torch.uint8, device="cuda")
+        d_aad = _dev(torch, aad) if alen else None
+        d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+        eng.stream_crypt_device(0, iv, d_aad, d, d, d_tag, n_bytes=n)       # in place
+        torch.cuda.synchronize()
+        assert d[:n].cpu().numpy().tobytes() == want_ct and d_tag.cpu().numpy().tobytes() == want_tag, (it, "device")
+        d_ok = torch.zeros(1, dtype=torch.uint8, device="cuda")
+        eng.stream_crypt_device(1, iv, d_aad, d, d, d_tag, d_ok, n_bytes=n)
+        torch.cuda.synchronize()
+        assert d[:n].cpu().numpy().tobytes() == pt and int(d_ok.item()) == 1, (it, "device dec")
+        iv12 = _rb(rng, 12)
+        assert eng.encrypt(iv12, aad, pt[:1000]) == oracle.gcm_crypt(key, iv12, aad, pt[:1000]), (it, "96-bit after")
+
+
 @pytest.mark.parametrize("kb", [16, 24, 32])
 def test_stream_random_sizes_vs_oracle(engine, oracle, kb):
     """Default persistent grid (#SMs x 1024): empty, sub-block, ragged, one partial row, >1 row."""
