@@ -40,6 +40,20 @@ int main(void)
     tag[3] ^= 1;
     rc = agcm_stream_crypt_host(ctx, 1, iv, aad, (uint64_t)aad_len, ct, back, (uint64_t)n, tag, &ok);
     if (rc || ok) { printf("forged tag accepted\n"); return 1; }
+    /* an 8-byte IV (McGrew-Viega test case 5): J0 is derived on the device */
+    {
+        uint8_t k5[16], iv5[8], a5[20], p5[60], c5[60], t5[16], want_t5[16];
+        unhex("feffe9928665731c6d6a8f9467308308", k5);
+        unhex("cafebabefacedbad", iv5);
+        unhex("feedfacedeadbeeffeedfacedeadbeefabaddad2", a5);
+        unhex("d9313225f88406e5a55909c5aff5269a86a7a9531534f7da2e4c303d8a318a721c3c0c95956809532fcf0e2449a6b525b16aedf5aa0de657ba637b39", p5);
+        unhex("3612d2e79e3b0785561be14aaca2fccb", want_t5);
+        rc = agcm_set_key(ctx, 128, 0, k5, sizeof k5);
+        if (!rc) rc = agcm_stream_crypt_iv_host(ctx, 0, iv5, sizeof iv5, a5, sizeof a5, p5, c5, sizeof p5, t5, &ok);
+        if (rc || memcmp(t5, want_t5, 16) || c5[0] != 0x61 || c5[1] != 0x35) { printf("8-byte IV mismatch (rc=%d)\n", rc); return 1; }
+        rc = agcm_set_key(ctx, 128, 0, key, sizeof key);
+        if (rc) return 2;
+    }
     uint8_t rk[176];
     rc = agcm_key_expand_host(ctx, 128, key, rk);
     if (rc || memcmp(rk, key, 16)) { printf("key_expand\n"); return 1; }
