@@ -45,6 +45,8 @@ struct agcm_ctx {
     uint32_t* d_counters = nullptr;  // last-CTA tickets: [0] context scratch, [1+s] pipeline slot s
     uint32_t* d_pow_n = nullptr;     // cached H^n (4 BE words) for the tag finish
     uint64_t pow_n = ~0ull;          // exponent it was computed for (~0 = none)
+    uint32_t* d_pow_scale = nullptr; // cached H^blocks_after of the last shard call (4 BE words)
+    uint64_t pow_scale_e = ~0ull;
     uint32_t j0ctr = 1;              // counter field of J0 for the call in progress (1 for a 96-bit IV)
     uint8_t* d_iv_stage = nullptr;   // padded long IV for the J0 derivation
     size_t iv_stage_cap = 0;
@@ -172,6 +174,19 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
     if (mode != AG_MODE_CTR_ONLY) {
         p.done_counter = counter;
         p.scale_e = blocks_after;
+        // a shard of a long stream is called again and again with the same exponent (every
+        // step of a sharded job): H^blocks_after is computed once per (key, exponent) by k_pow on
+        // this stream instead of seven dependent products in the tail of every launch.  The
+        // host-pipeline chunks (their own streams, a different exponent each) compute it in the tail.
+        if (blocks_after && counter == c->d_counters && mode != AG_MODE_GHASH_ONLY) {
+            if (c->pow_scale_e != blocks_after) {
+                if (!c->d_pow_scale) AG_CUDA(c, cudaMalloc(&c->d_pow_scale, 16));
+                AG_CUDA(c, ag_launch_pow(c->d_key, blocks_after, c->d_pow_scale, st));
+                c->launches++;
+                c->pow_scale_e = blocks_after;
+            }
+            p.scale_pow = c->d_pow_scale;
+        }
         p.out16 = d_partial16;
         if (ff) {
             p.fuse_finish = 1;
@@ -471,6 +486,7 @@ void agcm_ctx_destroy(agcm_ctx* c)
     cudaFree(c->d_scratch);
     cudaFree(c->d_counters);
     cudaFree(c->d_pow_n);
+    cudaFree(c->d_pow_scale);
     cudaFree(c->d_peer_bufs);
     cudaFree(c->d_peer_status);
     delete c;
@@ -553,6 +569,7 @@ int agcm_set_key(agcm_ctx* c, int mode, int pre_expanded, const uint8_t* h_key, 
     AG_CUDA(c, cudaSetDevice(c->device));
     c->key_set = false;
     c->pow_n = ~0ull;
+    c->pow_scale_e = ~0ull;
     KeyIn in;
     memset(&in, 0, sizeof(in));
     memcpy(in.w, h_key, key_len);   // LE words == the byte string

@@ -125,6 +125,7 @@ struct StreamParams {
     // fused tail, run by the last CTA to finish (null done_counter = off)
     uint32_t* done_counter;       // zero before the launch; reset by the kernel
     uint64_t scale_e;             // partial *= H^scale_e (blocks after this shard)
+    const uint32_t* scale_pow;    // H^scale_e precomputed by k_pow (4 BE words), or null: compute in the tail
     uint8_t* out16;               // scaled partial in natural byte order (may be null)
     uint32_t fuse_finish;         // also finish the tag (single-shard message, short AAD)
     const uint8_t* aad;

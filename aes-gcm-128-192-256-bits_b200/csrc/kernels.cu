@@ -380,7 +380,13 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_con
                 }
                 s = warp_xor(s);
                 if (p.scale_e) {
-                    const gf128 he = warp_gf_pow(p.key, p.scale_e);
+                    gf128 he;
+                    if (p.scale_pow) {
+                        he.w[0] = __ldcg(p.scale_pow + 0); he.w[1] = __ldcg(p.scale_pow + 1);
+                        he.w[2] = __ldcg(p.scale_pow + 2); he.w[3] = __ldcg(p.scale_pow + 3);
+                    } else {
+                        he = warp_gf_pow(p.key, p.scale_e);
+                    }
                     s = gf_mul(s, he);
                 }
                 if (p.out16 && tid == 0) {
