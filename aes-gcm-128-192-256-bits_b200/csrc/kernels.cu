@@ -587,12 +587,13 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
     GhSmem gh_g{ag_smem + SM_GH, (lane & 7) * 16};
     gf128* red = reinterpret_cast<gf128*>(ag_smem + SM_MISC);
     const gf128 wgt = p.key->hpow_thread[nt - tid];
-    // H^after cache of the split layout, 4 direct-mapped entries (key 0 = empty): with equal-length
-    // messages a CTA meets at most a few distinct exponents, and one exponentiation by a single
-    // warp (seven dependent generic products, the rest of the CTA waiting) costs ~20 us
-    uint64_t* pow_keys = reinterpret_cast<uint64_t*>(ag_smem + SM_MISC + 1056);
-    gf128* pow_vals = reinterpret_cast<gf128*>(ag_smem + SM_MISC + 1088);
-    if (tid < 4) pow_keys[tid] = 0;
+    // H^after cache of the split layout, 32 direct-mapped entries (key 0 = empty): with equal-length
+    // messages a CTA meets S / gcd(gridDim, S) distinct segment indices (S/4 on 148 CTAs, 4 apart),
+    // and one exponentiation by a single warp (seven dependent generic products, the rest of the
+    // CTA waiting) costs ~20 us
+    uint64_t* pow_keys = reinterpret_cast<uint64_t*>(ag_smem + SM_MISC + 1056);   // 32 x 8 B
+    gf128* pow_vals = reinterpret_cast<gf128*>(ag_smem + SM_MISC + 1312);         // 32 x 16 B
+    if (tid < 32) pow_keys[tid] = 0;
     __syncthreads();
     // One unit per CTA pass: a whole message, or (split > 1) one counter-range segment of it --
     // a few long messages would otherwise leave the grid idle in the last round (256 messages on
@@ -633,7 +634,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
             const uint32_t* ej = reinterpret_cast<const uint32_t*>(ag_smem + SM_MISC + 1024);
             if (S > 1) {
                 if (after) {  // uniform
-                    const uint32_t slot = seg & 3u;
+                    const uint32_t slot = (seg >> 2) & 31u;
                     gf128 ha;
                     if (pow_keys[slot] == after) {
                         ha = pow_vals[slot];
