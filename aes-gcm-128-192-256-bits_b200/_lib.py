@@ -13,7 +13,7 @@ SO_PATH = os.environ.get("AGCM_LIB_PATH") or os.path.join(_HERE, "libaesgcm_b200
 CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0
-E_BAD_MODE, E_BAD_LEN, E_COUNTER_OVERFLOW, E_CUDA, E_NO_KEY, E_BAD_ARG, E_NO_DEVICE = -1, -2, -3, -4, -5, -6, -7
+E_BAD_MODE, E_BAD_LEN, E_COUNTER_OVERFLOW, E_CUDA, E_NO_KEY, E_BAD_ARG, E_NO_DEVICE, E_PEER_TIMEOUT = -1, -2, -3, -4, -5, -6, -7, -8
 
 c_u8p = ctypes.c_void_p  # raw addresses (host or device) are passed as integers
 c_u64 = ctypes.c_uint64
@@ -46,6 +46,9 @@ SIGNATURES = {
     "agcm_peer_status": (c_int, [c_vp, ctypes.POINTER(c_int)]),
     "agcm_stream_crypt_peer": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u64, c_u64, c_u8p,
                                        c_u8p, c_vp]),
+    "agcm_peer_join": (c_int, [c_vp, c_vp]),
+    "agcm_stream_crypt_peer_async": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u64, c_u64,
+                                             c_u8p, c_u8p, c_vp]),
     "agcm_batch_crypt": (c_int, [c_vp, c_int, c_int, c_u64, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
                                  c_sz, c_vp]),
     "agcm_batch_crypt_uniform": (c_int, [c_vp, c_int, c_int, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u8p, c_u64, c_u64,
@@ -61,6 +64,8 @@ SIGNATURES = {
     "agcm_stream_part_host": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p]),
     "agcm_stream_finish_host": (c_int, [c_vp, c_int, c_u8p, c_u8p, c_int, c_u8p, c_u64, c_u64, c_u8p,
                                         ctypes.POINTER(c_int)]),
+    "agcm_stream_crypt_peer_host": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u64, c_u64, c_u8p,
+                                            ctypes.POINTER(c_int)]),
     "agcm_batch_crypt_uniform_host": (c_int, [c_vp, c_int, c_int, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u8p, c_u64,
                                               c_u64, c_u8p, c_u8p, c_sz]),
     "agcm_host_alloc": (c_int, [ctypes.POINTER(c_vp), c_sz]),

@@ -53,8 +53,16 @@ struct agcm_ctx {
     // peer-memory exchange (multi-GPU)
     uint8_t** d_peer_bufs = nullptr; // device array of world pointers
     uint32_t* d_peer_status = nullptr;
+    uint32_t* h_peer_status = nullptr;   // mapped pinned word raised by k_peer_finish on a timeout
     int peer_rank = 0, peer_world = 0;
-    uint32_t peer_epoch = 0;
+    uint32_t peer_epoch = 0;             // exchanges issued so far
+    uint64_t peer_timeout_ns = 3000000000ull;
+    cudaStream_t peer_side = nullptr;    // the finishes wait for the world's flags here, off the caller's stream
+    cudaEvent_t peer_bulk_ev[AG_PEER_RING] = {};
+    cudaEvent_t peer_fin_ev[AG_PEER_RING] = {};
+    // producer of the cached powers (a consumer on another stream waits for the event)
+    cudaEvent_t pow_n_ev = nullptr, pow_scale_ev = nullptr;
+    cudaStream_t pow_n_st = nullptr, pow_scale_st = nullptr;
     uint32_t h_rk[60];
     uint8_t h_H[16];
     uint8_t h_key_in[240];           // the key as it was loaded, to recognise a reload of the same key
@@ -128,14 +136,42 @@ int timing_drain(agcm_ctx* c)
     return AGCM_OK;
 }
 
+// A cached power is produced asynchronously by k_pow on whichever stream asked first; a later
+// consumer on a DIFFERENT stream (a user stream, the library's pipeline or side streams) must not
+// read it before that launch ran.
+int pow_publish(agcm_ctx* c, cudaEvent_t* ev, cudaStream_t* owner, cudaStream_t st)
+{
+    if (!*ev) AG_CUDA(c, cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    AG_CUDA(c, cudaEventRecord(*ev, st));
+    *owner = st;
+    return AGCM_OK;
+}
+
+int pow_consume(agcm_ctx* c, cudaEvent_t ev, cudaStream_t owner, cudaStream_t st)
+{
+    if (ev && owner != st) AG_CUDA(c, cudaStreamWaitEvent(st, ev, 0));
+    return AGCM_OK;
+}
+
+// the caller's stream waits for every peer finish issued so far (they may still read d_pow_n)
+int peer_join_stream(agcm_ctx* c, cudaStream_t st)
+{
+    if (c->peer_epoch && c->peer_fin_ev[0]) AG_CUDA(c, cudaStreamWaitEvent(st, c->peer_fin_ev[c->peer_epoch % AG_PEER_RING], 0));
+    return AGCM_OK;
+}
+
 // H^n for the tag finish, computed once per (key, n) on the caller's stream
 int ensure_pow(agcm_ctx* c, uint64_t n_blocks, cudaStream_t st)
 {
-    if (c->pow_n == n_blocks) return AGCM_OK;
+    if (c->pow_n == n_blocks) return pow_consume(c, c->pow_n_ev, c->pow_n_st, st);
+    int rc = peer_join_stream(c, st);   // a deferred finish of an earlier message may still read the old power
+    if (rc) return rc;
+    rc = pow_consume(c, c->pow_n_ev, c->pow_n_st, st);   // ... and so may a consumer ordered after the old producer
+    if (rc) return rc;
     AG_CUDA(c, ag_launch_pow(c->d_key, n_blocks, c->d_pow_n, st));
     c->launches++;
     c->pow_n = n_blocks;
-    return AGCM_OK;
+    return pow_publish(c, &c->pow_n_ev, &c->pow_n_st, st);
 }
 
 // optional tag finish fused into the stream kernel (single-shard message, short AAD)
@@ -145,7 +181,6 @@ struct FuseFinish {
     uint8_t* tag_calc;
     const uint8_t* tag_expected;
     uint8_t* ok;
-    bool peer = false;  // exchange the partial with the other ranks over peer memory first
 };
 
 // GHASH partial of `n_bytes` at d_in (optionally also CTR) -> 16 B at d_partial16,
@@ -153,7 +188,7 @@ struct FuseFinish {
 // the same launch.  parts_raw: per-CTA scratch (AG_MAX_CTA x 4 words); counter: its ticket.
 int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
                uint64_t n_bytes, uint64_t blocks_after, uint32_t* parts_raw, uint8_t* d_partial16, cudaStream_t st,
-               uint32_t* counter, const FuseFinish* ff = nullptr)
+               uint32_t* counter, const FuseFinish* ff = nullptr, uint32_t peer_epoch = 0)
 {
     if (n_bytes == 0) {
         if (d_partial16) AG_CUDA(c, cudaMemsetAsync(d_partial16, 0, 16, st));
@@ -181,9 +216,16 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
         if (blocks_after && counter == c->d_counters && mode != AG_MODE_GHASH_ONLY) {
             if (c->pow_scale_e != blocks_after) {
                 if (!c->d_pow_scale) AG_CUDA(c, cudaMalloc(&c->d_pow_scale, 16));
+                int rc = pow_consume(c, c->pow_scale_ev, c->pow_scale_st, st);
+                if (rc) return rc;
                 AG_CUDA(c, ag_launch_pow(c->d_key, blocks_after, c->d_pow_scale, st));
                 c->launches++;
                 c->pow_scale_e = blocks_after;
+                rc = pow_publish(c, &c->pow_scale_ev, &c->pow_scale_st, st);
+                if (rc) return rc;
+            } else {
+                int rc = pow_consume(c, c->pow_scale_ev, c->pow_scale_st, st);
+                if (rc) return rc;
             }
             p.scale_pow = c->d_pow_scale;
         }
@@ -197,13 +239,12 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
             p.tag_expected = ff->tag_expected;
             p.ok = ff->ok;
             p.hn = c->d_pow_n;
-            if (ff->peer) {
-                p.peer_bufs = c->d_peer_bufs;
-                p.peer_rank = (uint32_t)c->peer_rank;
-                p.peer_world = (uint32_t)c->peer_world;
-                p.peer_epoch = ++c->peer_epoch;
-                p.peer_status = c->d_peer_status;
-            }
+        }
+        if (peer_epoch) {   // post the scaled partial to every rank (k_peer_finish does the rest)
+            p.peer_bufs = c->d_peer_bufs;
+            p.peer_rank = (uint32_t)c->peer_rank;
+            p.peer_world = (uint32_t)c->peer_world;
+            p.peer_epoch = peer_epoch;
         }
     }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -410,6 +451,7 @@ const char* agcm_strerror(int rc)
         case AGCM_E_NO_KEY: return "no key set";
         case AGCM_E_BAD_ARG: return "bad argument";
         case AGCM_E_NO_DEVICE: return "no sm_100 CUDA device (the engine has no CPU path)";
+        case AGCM_E_PEER_TIMEOUT: return "a peer never posted its shard partial (the tag of that message was zeroed, ok = 0)";
     }
     return "unknown error";
 }
@@ -489,6 +531,14 @@ void agcm_ctx_destroy(agcm_ctx* c)
     cudaFree(c->d_pow_scale);
     cudaFree(c->d_peer_bufs);
     cudaFree(c->d_peer_status);
+    if (c->h_peer_status) cudaFreeHost(c->h_peer_status);
+    if (c->peer_side) cudaStreamDestroy(c->peer_side);
+    for (uint32_t i = 0; i < AG_PEER_RING; ++i) {
+        if (c->peer_bulk_ev[i]) cudaEventDestroy(c->peer_bulk_ev[i]);
+        if (c->peer_fin_ev[i]) cudaEventDestroy(c->peer_fin_ev[i]);
+    }
+    if (c->pow_n_ev) cudaEventDestroy(c->pow_n_ev);
+    if (c->pow_scale_ev) cudaEventDestroy(c->pow_scale_ev);
     delete c;
 }
 
@@ -692,8 +742,22 @@ int agcm_peer_setup(agcm_ctx* c, int rank, int world, const uint64_t* h_peer_ptr
 {
     if (!c || !h_peer_ptrs || world < 1 || world > (int)AG_PEER_MAX || rank < 0 || rank >= world) return AGCM_E_BAD_ARG;
     AG_CUDA(c, cudaSetDevice(c->device));
+    AG_CUDA(c, cudaDeviceSynchronize());   // no finish of an earlier session may still be waiting
     if (!c->d_peer_bufs) AG_CUDA(c, cudaMalloc(&c->d_peer_bufs, sizeof(uint8_t*) * AG_PEER_MAX));
     if (!c->d_peer_status) AG_CUDA(c, cudaMalloc(&c->d_peer_status, sizeof(uint32_t)));
+    if (!c->h_peer_status) AG_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_peer_status), sizeof(uint32_t), cudaHostAllocMapped));
+    if (!c->peer_side) {
+        AG_CUDA(c, cudaStreamCreateWithFlags(&c->peer_side, cudaStreamNonBlocking));
+        for (uint32_t i = 0; i < AG_PEER_RING; ++i) {
+            AG_CUDA(c, cudaEventCreateWithFlags(&c->peer_bulk_ev[i], cudaEventDisableTiming));
+            AG_CUDA(c, cudaEventCreateWithFlags(&c->peer_fin_ev[i], cudaEventDisableTiming));
+        }
+    }
+    if (const char* e = getenv("AGCM_PEER_TIMEOUT_MS")) {
+        const long ms = atol(e);
+        if (ms >= 1) c->peer_timeout_ns = (uint64_t)ms * 1000000ull;
+    }
+    *c->h_peer_status = 0;
     AG_CUDA(c, cudaMemset(c->d_peer_status, 0, sizeof(uint32_t)));
     AG_CUDA(c, cudaMemcpy(c->d_peer_bufs, h_peer_ptrs, sizeof(uint64_t) * (size_t)world, cudaMemcpyHostToDevice));
     // my own buffer starts with all flags clear; the caller barriers before the first exchange
@@ -709,38 +773,123 @@ int agcm_peer_status(agcm_ctx* c, int* h_timed_out)
 {
     if (!c || !h_timed_out) return AGCM_E_BAD_ARG;
     uint32_t v = 0;
-    if (c->d_peer_status) AG_CUDA(c, cudaMemcpy(&v, c->d_peer_status, sizeof(v), cudaMemcpyDeviceToHost));
+    if (c->d_peer_status) {
+        AG_CUDA(c, cudaSetDevice(c->device));
+        if (c->peer_side) AG_CUDA(c, cudaStreamSynchronize(c->peer_side));   // every finish issued so far has run
+        AG_CUDA(c, cudaMemcpy(&v, c->d_peer_status, sizeof(v), cudaMemcpyDeviceToHost));
+    }
     *h_timed_out = (int)v;
     return AGCM_OK;
+}
+
+int agcm_peer_join(agcm_ctx* c, void* stream)
+{
+    if (!c) return AGCM_E_BAD_ARG;
+    if (c->peer_world < 1) return AGCM_E_BAD_ARG;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    return peer_join_stream(c, (cudaStream_t)stream);
+}
+
+// Common checks of the peer calls + the ring's flow control on `st`; returns the new epoch.
+static int peer_begin(agcm_ctx* c, uint64_t first_block, uint64_t n_bytes, uint64_t blocks_after, uint64_t aad_len,
+                      uint64_t total_len, cudaStream_t st, uint32_t* epoch_out)
+{
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (c->peer_world < 1) return AGCM_E_BAD_ARG;                          // agcm_peer_setup first
+    if (*(volatile uint32_t*)c->h_peer_status) return AGCM_E_PEER_TIMEOUT; // an earlier exchange failed closed
+    if (aad_len > kAadInlineMax) return AGCM_E_BAD_LEN;                    // bulk AAD: use the gather path
+    const uint64_t nb = (n_bytes + 15) >> 4, tb = (total_len + 15) >> 4;
+    if (tb > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
+    if (first_block > tb || nb > tb - first_block || blocks_after != tb - first_block - nb) return AGCM_E_BAD_LEN;
+    if (blocks_after && (n_bytes & 15)) return AGCM_E_BAD_LEN;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t epoch = c->peer_epoch + 1;
+    // flow control of the ring (gcm_core.cuh): post epoch e only after my finish of e - AHEAD ran
+    if (epoch > AG_PEER_AHEAD) AG_CUDA(c, cudaStreamWaitEvent(st, c->peer_fin_ev[(epoch - AG_PEER_AHEAD) % AG_PEER_RING], 0));
+    if (aad_len) {
+        int rc = ensure_pow(c, tb, st);
+        if (rc) return rc;
+    }
+    *epoch_out = epoch;
+    return AGCM_OK;
+}
+
+// The one-warp finish of `epoch` on the side stream, ordered after everything queued on `st`.
+static int peer_finish(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], const uint8_t* d_aad, uint64_t aad_len,
+                       uint64_t total_len, uint8_t* d_tag, uint8_t* d_ok, cudaStream_t st, uint32_t epoch, bool deferred)
+{
+    const uint32_t slot = epoch % AG_PEER_RING;
+    c->peer_epoch = epoch;
+    PeerFinishParams pf;
+    memset(&pf, 0, sizeof(pf));
+    memcpy(pf.f.rk, c->h_rk, sizeof(pf.f.rk));
+    pf.f.nr = (uint32_t)c->nr;
+    iv_words(h_iv12, pf.f.iv);
+    pf.f.j0w = __builtin_bswap32(c->j0ctr);
+    pf.f.key = c->d_key;
+    pf.f.te0 = c->d_te0;
+    pf.f.aad = aad_len ? d_aad : nullptr;
+    pf.f.aad_len = aad_len;
+    pf.f.ct_len = total_len;
+    pf.f.tag_calc = decrypt ? c->d_scratch + SC_TAGCALC : d_tag;
+    pf.f.tag_expected = decrypt ? d_tag : nullptr;
+    pf.f.ok = decrypt ? d_ok : nullptr;
+    pf.f.hn = aad_len ? c->d_pow_n : nullptr;
+    pf.peer_bufs = c->d_peer_bufs;
+    pf.rank = (uint32_t)c->peer_rank;
+    pf.world = (uint32_t)c->peer_world;
+    pf.epoch = epoch;
+    pf.timeout_ns = c->peer_timeout_ns;
+    pf.status_dev = c->d_peer_status;
+    uint32_t* mapped = nullptr;
+    AG_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&mapped), c->h_peer_status, 0));
+    pf.status_host = mapped;
+    // the finish waits for the world on the side stream: the caller's stream is free for the next bulk kernel
+    AG_CUDA(c, cudaEventRecord(c->peer_bulk_ev[slot], st));
+    AG_CUDA(c, cudaStreamWaitEvent(c->peer_side, c->peer_bulk_ev[slot], 0));
+    AG_CUDA(c, ag_launch_peer_finish(pf, c->peer_side));
+    c->launches++;
+    AG_CUDA(c, cudaEventRecord(c->peer_fin_ev[slot], c->peer_side));
+    if (!deferred) AG_CUDA(c, cudaStreamWaitEvent(st, c->peer_fin_ev[slot], 0));
+    return AGCM_OK;
+}
+
+static int stream_crypt_peer(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in,
+                             uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, const uint8_t* d_aad, uint64_t aad_len,
+                             uint64_t total_len, uint8_t* d_tag, uint8_t* d_ok, void* stream, bool deferred)
+{
+    if (!c || !h_iv12 || (n_bytes && (!d_in || !d_out)) || !d_tag || (decrypt && !d_ok) || (aad_len && !d_aad))
+        return AGCM_E_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t epoch = 0;
+    int rc = peer_begin(c, first_block, n_bytes, blocks_after, aad_len, total_len, st, &epoch);
+    if (rc) return rc;
+    if (n_bytes) {
+        rc = run_stream(c, decrypt ? AG_MODE_DEC : AG_MODE_ENC, h_iv12, first_block, d_in, d_out, n_bytes, blocks_after,
+                        c->d_parts, nullptr, st, c->d_counters, nullptr, epoch);
+        if (rc) return rc;
+    } else {   // an empty counter range (fewer blocks than ranks) still posts its zero partial
+        AG_CUDA(c, ag_launch_peer_post(c->d_peer_bufs, (uint32_t)c->peer_rank, (uint32_t)c->peer_world, epoch, nullptr, st));
+        c->launches++;
+    }
+    return peer_finish(c, decrypt, h_iv12, d_aad, aad_len, total_len, d_tag, d_ok, st, epoch, deferred);
 }
 
 int agcm_stream_crypt_peer(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in,
                            uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, const uint8_t* d_aad, uint64_t aad_len,
                            uint64_t total_len, uint8_t* d_tag, uint8_t* d_ok, void* stream)
 {
-    if (!c || !h_iv12 || !d_in || !d_out || !d_tag || (decrypt && !d_ok) || (aad_len && !d_aad)) return AGCM_E_BAD_ARG;
-    if (!c->key_set) return AGCM_E_NO_KEY;
-    if (c->peer_world < 1) return AGCM_E_BAD_ARG;                          // agcm_peer_setup first
-    if (n_bytes == 0 || aad_len > kAadInlineMax) return AGCM_E_BAD_LEN;   // every rank must launch; bulk AAD: use the gather path
-    const uint64_t nb = (n_bytes + 15) >> 4, tb = (total_len + 15) >> 4;
-    if (tb > kMaxBlocks || first_block > tb || nb > tb - first_block || blocks_after != tb - first_block - nb)
-        return AGCM_E_BAD_LEN;
-    if (blocks_after && (n_bytes & 15)) return AGCM_E_BAD_LEN;
-    AG_CUDA(c, cudaSetDevice(c->device));
-    FuseFinish ff;
-    ff.aad = aad_len ? d_aad : nullptr;
-    ff.aad_len = aad_len;
-    ff.ct_len = total_len;
-    ff.tag_calc = decrypt ? c->d_scratch + SC_TAGCALC : d_tag;
-    ff.tag_expected = decrypt ? d_tag : nullptr;
-    ff.ok = decrypt ? d_ok : nullptr;
-    ff.peer = true;
-    if (aad_len) {
-        int rc = ensure_pow(c, tb, (cudaStream_t)stream);
-        if (rc) return rc;
-    }
-    return run_stream(c, decrypt ? AG_MODE_DEC : AG_MODE_ENC, h_iv12, first_block, d_in, d_out, n_bytes, blocks_after,
-                      c->d_parts, nullptr, (cudaStream_t)stream, c->d_counters, &ff);
+    return stream_crypt_peer(c, decrypt, h_iv12, first_block, d_in, d_out, n_bytes, blocks_after, d_aad, aad_len, total_len,
+                             d_tag, d_ok, stream, false);
+}
+
+int agcm_stream_crypt_peer_async(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uint64_t first_block,
+                                 const uint8_t* d_in, uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after,
+                                 const uint8_t* d_aad, uint64_t aad_len, uint64_t total_len, uint8_t* d_tag, uint8_t* d_ok,
+                                 void* stream)
+{
+    return stream_crypt_peer(c, decrypt, h_iv12, first_block, d_in, d_out, n_bytes, blocks_after, d_aad, aad_len, total_len,
+                             d_tag, d_ok, stream, true);
 }
 
 int agcm_gctr(agcm_ctx* c, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
@@ -935,7 +1084,10 @@ static int host_pipeline(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uin
     const uint64_t nblocks = (n_bytes + 15) >> 4;
     // granule: the tuned size, grown for very long ranges so the partial list stays bounded
     uint64_t kChunkBytes = c->chunk_bytes;
-    while ((n_bytes + kChunkBytes - 1) / kChunkBytes > SC_PARTS_MAX && kChunkBytes < kChunkBytesMax) kChunkBytes <<= 1;
+    while ((n_bytes + kChunkBytes - 1) / kChunkBytes > SC_PARTS_MAX && kChunkBytes < kChunkBytesMax) {
+        kChunkBytes <<= 1;
+        if (kChunkBytes > kChunkBytesMax) kChunkBytes = kChunkBytesMax;   // a non-power-of-two AGCM_CHUNK_MB must not outgrow d_stage
+    }
     const uint64_t n_chunks = (n_bytes + kChunkBytes - 1) / kChunkBytes;
     if (n_chunks > kMaxChunks || n_chunks > SC_PARTS_MAX) return AGCM_E_BAD_LEN;
     const int mode = decrypt ? AG_MODE_DEC : AG_MODE_ENC;
@@ -1012,6 +1164,49 @@ int agcm_stream_finish_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], 
     else AG_CUDA(c, cudaMemcpyAsync(h_tag, d_tag, 16, cudaMemcpyDeviceToHost, st));
     AG_CUDA(c, cudaStreamSynchronize(st));
     if (h_ok) *h_ok = okb ? 1 : 0;
+    return AGCM_OK;
+}
+
+int agcm_stream_crypt_peer_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* h_in,
+                                uint8_t* h_out, uint64_t n_bytes, uint64_t blocks_after, const uint8_t* h_aad, uint64_t aad_len,
+                                uint64_t total_len, uint8_t h_tag[16], int* h_ok)
+{
+    if (!c || !h_iv12 || !h_tag || (n_bytes && (!h_in || !h_out)) || (aad_len && !h_aad) || (decrypt && !h_ok))
+        return AGCM_E_BAD_ARG;
+    if (c->peer_world < 1) return AGCM_E_BAD_ARG;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc) return rc;
+    rc = reserve_aad_stage(c, aad_len);
+    if (rc) return rc;
+    cudaStream_t st = c->hs[0];
+    uint32_t epoch = 0;
+    rc = peer_begin(c, first_block, n_bytes, blocks_after, aad_len, total_len, st, &epoch);
+    if (rc) return rc;
+    if (aad_len) AG_CUDA(c, cudaMemcpyAsync(c->d_aad_stage, h_aad, aad_len, cudaMemcpyHostToDevice, st));
+    uint8_t* d_tag = c->d_scratch + SC_TAG;
+    uint8_t* d_ok = c->d_scratch + SC_OK;
+    if (decrypt) AG_CUDA(c, cudaMemcpyAsync(d_tag, h_tag, 16, cudaMemcpyHostToDevice, st));
+    uint64_t n_chunks = 0;
+    rc = host_pipeline(c, decrypt, h_iv12, first_block, h_in, h_out, n_bytes, blocks_after, &n_chunks);
+    if (rc) return rc;
+    for (int s = 1; s < kSlots; ++s) AG_CUDA(c, cudaStreamSynchronize(c->hs[s]));
+    const uint8_t* d_p = nullptr;   // null = the zero partial of an empty range
+    if (n_chunks) {
+        AG_CUDA(c, ag_launch_xor_parts(c->d_chunk_partials, (uint32_t)n_chunks, c->d_scratch + SC_PART_CT, st));
+        c->launches++;
+        d_p = c->d_scratch + SC_PART_CT;
+    }
+    AG_CUDA(c, ag_launch_peer_post(c->d_peer_bufs, (uint32_t)c->peer_rank, (uint32_t)c->peer_world, epoch, d_p, st));
+    c->launches++;
+    rc = peer_finish(c, decrypt, h_iv12, c->d_aad_stage, aad_len, total_len, d_tag, d_ok, st, epoch, false);
+    if (rc) return rc;
+    uint8_t okb = 1;
+    if (decrypt) AG_CUDA(c, cudaMemcpyAsync(&okb, d_ok, 1, cudaMemcpyDeviceToHost, st));
+    else AG_CUDA(c, cudaMemcpyAsync(h_tag, d_tag, 16, cudaMemcpyDeviceToHost, st));
+    AG_CUDA(c, cudaStreamSynchronize(st));
+    if (h_ok) *h_ok = okb ? 1 : 0;
+    if (*(volatile uint32_t*)c->h_peer_status) return AGCM_E_PEER_TIMEOUT;
     return AGCM_OK;
 }
 

@@ -134,18 +134,24 @@ struct StreamParams {
     const uint8_t* tag_expected;
     uint8_t* ok;
     const uint32_t* hn;           // H^(ct blocks), precomputed (k_pow) or null
-    // exchange of the shard partials over peer memory (NVLink), fused into the same tail:
+    // exchange of the shard partials over peer memory (NVLink): the tail POSTS this rank's scaled
+    // partial into slot (peer_epoch % AG_PEER_RING, peer_rank) of every peer's exchange buffer and
+    // raises the slot's epoch flag; k_peer_finish (side stream) waits for the world's flags.
     // peer_bufs[w] = rank w's exchange buffer mapped in this process (AG_PEER_* layout)
     uint8_t* const* peer_bufs;
     uint32_t peer_rank, peer_world, peer_epoch;
-    uint32_t* peer_status;        // set to 1 if a peer never showed up (bounded spin)
 };
 
-// Exchange buffer of one rank: two parities (epoch & 1) x AG_PEER_MAX slots of 16 B written by
-// the peers, then the matching 4-byte epoch flags.
+// Exchange buffer of one rank: a ring of AG_PEER_RING epochs x AG_PEER_MAX slots of 16 B written
+// by the peers, then the matching 4-byte epoch flags.  A rank posts epoch e only after its own
+// finish of epoch e - AG_PEER_AHEAD completed (which proves every peer posted e - AG_PEER_AHEAD,
+// hence finished e - 2*AG_PEER_AHEAD): with RING >= 2*AHEAD a slot is never overwritten before
+// its reader is done, and a rank runs at most AHEAD messages ahead of the slowest one.
 constexpr uint32_t AG_PEER_MAX = 16;
-constexpr uint32_t AG_PEER_FLAGS = 2 * AG_PEER_MAX * 16;
-constexpr uint32_t AG_PEER_BYTES = AG_PEER_FLAGS + 2 * AG_PEER_MAX * 4;
+constexpr uint32_t AG_PEER_RING = 8;
+constexpr uint32_t AG_PEER_AHEAD = 4;
+constexpr uint32_t AG_PEER_FLAGS = AG_PEER_RING * AG_PEER_MAX * 16;
+constexpr uint32_t AG_PEER_BYTES = AG_PEER_FLAGS + AG_PEER_RING * AG_PEER_MAX * 4;
 
 // Returns Y_g for global lane g of Gt lanes; the caller multiplies by H^(Gt-g).
 // Block indices fit 32 bits (a counter range holds < 2^32 blocks).

@@ -312,6 +312,84 @@ __device__ void finish_warp(const FinishArgs& p, gf128 s)
     }
 }
 
+// One tiny all-to-all over NVLink peer memory instead of a collective library call (one warp):
+// lane w stores this rank's scaled partial into its slot of rank w's exchange buffer, fences at
+// system scope and raises the slot's epoch flag.  Nobody waits here: the bulk kernel of the next
+// message may start while the flags of this one are still in flight (k_peer_finish, on a side
+// stream, is the only waiter).
+__device__ __forceinline__ void ag_peer_post(uint8_t* const* peer_bufs, uint32_t rank, uint32_t world, uint32_t epoch,
+                                             const gf128& s)
+{
+    const uint32_t w = threadIdx.x & 31, slot = epoch % AG_PEER_RING;
+    if (w < world) {
+        uint8_t* dst = peer_bufs[w];
+        __stcg(reinterpret_cast<uint4*>(dst + (slot * AG_PEER_MAX + rank) * 16), make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]));
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(dst + AG_PEER_FLAGS + (slot * AG_PEER_MAX + rank) * 4) = epoch;
+    }
+}
+
+// Posts a partial computed by earlier launches (the host-buffer pipeline: 16 B in natural GHASH
+// byte order) or, with a null pointer, the zero partial of a rank whose counter range is empty
+// (fewer blocks than ranks): such a rank still takes part in the exchange.
+__global__ void __launch_bounds__(32) k_peer_post(uint8_t* const* peer_bufs, uint32_t rank, uint32_t world, uint32_t epoch,
+                                                  const uint8_t* __restrict__ partial16)
+{
+    gf128 s = gf_zero();
+    if (partial16) {
+        uint32_t x[4];
+        ag_load_block(partial16, 16, x);
+        s = gf_from_le_words(x[0], x[1], x[2], x[3]);
+    }
+    ag_peer_post(peer_bufs, rank, world, epoch, s);
+}
+
+// Waits (bounded by the global timer) for the world's flags of `epoch` in this rank's own buffer,
+// XORs the slots and finishes the tag.  FAILS CLOSED: if a peer never shows up the tag is
+// zeroed, ok = 0, and both status words are raised (the host-mapped one turns every later peer
+// call into AGCM_E_PEER_TIMEOUT).
+__global__ void __launch_bounds__(32) k_peer_finish(const __grid_constant__ PeerFinishParams p)
+{
+    const uint32_t w = threadIdx.x, slot = p.epoch % AG_PEER_RING;
+    const uint8_t* mine = p.peer_bufs[p.rank];
+    bool arrived = true;
+    if (w < p.world) {
+        const volatile uint32_t* f = reinterpret_cast<const volatile uint32_t*>(mine + AG_PEER_FLAGS + (slot * AG_PEER_MAX + w) * 4);
+        uint64_t t0 = 0;
+        uint32_t spins = 0;
+        while (*f != p.epoch) {
+            __nanosleep(64);
+            if ((++spins & 255u) == 0) {
+                uint64_t now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (!t0) t0 = now;
+                else if (now - t0 > p.timeout_ns) { arrived = false; break; }
+            }
+        }
+    }
+    __threadfence_system();
+    gf128 t = gf_zero();
+    if (w < p.world) {
+        const uint4 q = __ldcv(reinterpret_cast<const uint4*>(mine + (slot * AG_PEER_MAX + w) * 16));
+        t.w[0] = q.x; t.w[1] = q.y; t.w[2] = q.z; t.w[3] = q.w;
+    }
+    const gf128 s = warp_xor(t);
+    if (!__all_sync(0xffffffffu, arrived)) {
+        if (w == 0) {
+            const uint32_t z[4] = {0, 0, 0, 0};
+            ag_store_block(p.f.tag_calc, 16, z);
+            if (p.f.ok) *p.f.ok = 0;
+            if (p.status_dev) *p.status_dev = 1;
+            if (p.status_host) *p.status_host = 1;
+            __threadfence_system();
+        }
+        return;
+    }
+    FinishArgs a{p.f.rk, p.f.nr, p.f.iv, p.f.j0w, p.f.key, p.f.te0, p.f.aad, p.f.aad_len, p.f.ct_len, p.f.tag_calc,
+                 p.f.tag_expected, p.f.ok, p.f.hn, false};
+    finish_warp(a, s);
+}
+
 __global__ void __launch_bounds__(32) k_stream_finish(const __grid_constant__ FinishParams p)
 {
     const uint32_t lane = threadIdx.x;
@@ -393,44 +471,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_con
                     const uint32_t o[4] = {ag_bswap32(s.w[0]), ag_bswap32(s.w[1]), ag_bswap32(s.w[2]), ag_bswap32(s.w[3])};
                     ag_store_block(p.out16, 16, o);  // natural GHASH byte order
                 }
-                if (p.peer_world) {
-                    // One tiny all-to-all over NVLink peer memory instead of a collective library
-                    // call: every rank stores its scaled partial into its slot of every peer's
-                    // exchange buffer, raises the slot's epoch flag, waits for the world's flags
-                    // in its own buffer, and XORs the slots.  Two parities make back-to-back steps
-                    // safe (a rank can be at most one step ahead of a peer that still reads).
-                    const uint32_t par = p.peer_epoch & 1u, w = tid;
-                    if (w < p.peer_world) {
-                        uint8_t* dst = p.peer_bufs[w];
-                        *reinterpret_cast<uint4*>(dst + (par * AG_PEER_MAX + p.peer_rank) * 16) =
-                            make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
-                    }
-                    __threadfence_system();
-                    if (w < p.peer_world) {
-                        volatile uint32_t* f = reinterpret_cast<volatile uint32_t*>(
-                            p.peer_bufs[w] + AG_PEER_FLAGS + (par * AG_PEER_MAX + p.peer_rank) * 4);
-                        *f = p.peer_epoch;
-                    }
-                    uint8_t* mine = p.peer_bufs[p.peer_rank];
-                    bool arrived = true;
-                    if (w < p.peer_world) {
-                        volatile uint32_t* f =
-                            reinterpret_cast<volatile uint32_t*>(mine + AG_PEER_FLAGS + (par * AG_PEER_MAX + w) * 4);
-                        uint32_t spins = 0;
-                        while (*f != p.peer_epoch) {
-                            __nanosleep(100);
-                            if (++spins > (1u << 25)) { arrived = false; break; }  // ~ seconds: give up, never hang
-                        }
-                    }
-                    __threadfence_system();
-                    gf128 t = gf_zero();
-                    if (w < p.peer_world) {
-                        const uint4 q = __ldcv(reinterpret_cast<const uint4*>(mine + (par * AG_PEER_MAX + w) * 16));
-                        t.w[0] = q.x; t.w[1] = q.y; t.w[2] = q.z; t.w[3] = q.w;
-                    }
-                    s = warp_xor(t);
-                    if (!__all_sync(0xffffffffu, arrived) && tid == 0 && p.peer_status) *p.peer_status = 1;
-                }
+                if (p.peer_world) ag_peer_post(p.peer_bufs, p.peer_rank, p.peer_world, p.peer_epoch, s);
                 if (p.fuse_finish) {
                     FinishArgs a{p.rk, (uint32_t)NR, p.iv, p.j0w, p.key, p.te0, p.aad, p.aad_len, p.ct_len, p.tag_calc,
                                  p.tag_expected, p.ok, p.hn, MODE != AG_MODE_GHASH_ONLY};
@@ -985,6 +1026,19 @@ cudaError_t ag_launch_pow(const KeyDev* kd, uint64_t e, uint32_t* out, cudaStrea
 cudaError_t ag_launch_xor_parts(const uint8_t* parts, uint32_t n, uint8_t* out, cudaStream_t st)
 {
     k_xor_parts<<<1, 32, 0, st>>>(parts, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_peer_finish(const PeerFinishParams& p, cudaStream_t st)
+{
+    k_peer_finish<<<1, 32, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_peer_post(uint8_t* const* peer_bufs, uint32_t rank, uint32_t world, uint32_t epoch,
+                                const uint8_t* partial16, cudaStream_t st)
+{
+    k_peer_post<<<1, 32, 0, st>>>(peer_bufs, rank, world, epoch, partial16);
     return cudaGetLastError();
 }
 

@@ -23,6 +23,16 @@ struct FinishParams {
     const uint32_t* hn;           // H^(ct blocks) from k_pow, or null
 };
 
+// Tag finish of a sharded message whose partials arrive over peer memory (k_peer_finish).
+struct PeerFinishParams {
+    FinishParams f;               // parts / n_parts unused
+    uint8_t* const* peer_bufs;    // device array: rank w's exchange buffer mapped in this process
+    uint32_t rank, world, epoch;
+    uint64_t timeout_ns;          // give up (fail closed) when a peer's flag is this late
+    uint32_t* status_dev;         // set to 1 on timeout
+    volatile uint32_t* status_host;  // same, in mapped pinned host memory (read by the next call without a sync)
+};
+
 cudaError_t ag_launch_stream(const StreamParams& p, int nr, int mode, int ncta, int nt, cudaStream_t st);
 cudaError_t ag_launch_batch(const BatchParams& p, int nr, int decrypt, int g, int ncta, int nt, cudaStream_t st);
 cudaError_t ag_launch_batch_cta(const BatchParams& p, int nr, int decrypt, int ncta, int nt, cudaStream_t st);
@@ -40,5 +50,8 @@ cudaError_t ag_launch_key_setup(KeyDev* kd, const KeyIn& in, const uint32_t* te0
                                 cudaStream_t st);
 cudaError_t ag_launch_pow(const KeyDev* kd, uint64_t e, uint32_t* out4, cudaStream_t st);
 cudaError_t ag_launch_finish(const FinishParams& p, cudaStream_t st);
+cudaError_t ag_launch_peer_finish(const PeerFinishParams& p, cudaStream_t st);
+cudaError_t ag_launch_peer_post(uint8_t* const* peer_bufs, uint32_t rank, uint32_t world, uint32_t epoch,
+                                const uint8_t* partial16, cudaStream_t st);
 cudaError_t ag_launch_xor_parts(const uint8_t* parts16, uint32_t n, uint8_t* out16, cudaStream_t st);
 size_t ag_smem_bytes();

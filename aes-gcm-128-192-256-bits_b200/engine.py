@@ -195,6 +195,18 @@ class GcmEngine:
                                                  a.size, int(ct_len), _addr(t), ctypes.byref(ok)))
         return bool(ok.value) if decrypt else t.tobytes()
 
+    def stream_crypt_peer_host(self, decrypt, iv, first_block, data, out, blocks_after, aad, total_len, tag=None):
+        """One rank's shard in HOST memory + peer-memory exchange + finish.  -> tag (encrypt) / ok (decrypt)."""
+        ivb, d, o, a = _np_u8(iv), _np_u8(data), _np_u8(out), _np_u8(aad)
+        t = np.zeros(16, dtype=np.uint8)
+        if decrypt:
+            t[:] = _np_u8(tag)
+        ok = ctypes.c_int(1)
+        self._ck(self._L.agcm_stream_crypt_peer_host(self._ctx, int(decrypt), _addr(ivb), int(first_block), _addr(d), _addr(o),
+                                                     d.size, int(blocks_after), _addr(a), a.size, int(total_len), _addr(t),
+                                                     ctypes.byref(ok)))
+        return bool(ok.value) if decrypt else t.tobytes()
+
     def timing_enable(self, on=True):
         self._ck(self._L.agcm_timing_enable(self._ctx, int(bool(on))))
 
@@ -246,14 +258,19 @@ class GcmEngine:
         return bool(v.value)
 
     def stream_crypt_peer_device(self, decrypt, iv, first_block, data_in, data_out, blocks_after, aad, total_len, tag, ok=None,
-                                 n_bytes=None, stream=None):
-        """One rank's shard + peer-memory exchange + tag finish in ONE launch (every rank calls it)."""
+                                 n_bytes=None, stream=None, defer=False):
+        """One rank's shard + peer-memory exchange + tag finish (every rank calls it).  defer=True:
+        do not make `stream` wait for the finish -- call peer_join() before reading tag / ok."""
         ivb = _np_u8(iv)
-        n = data_in.numel() if n_bytes is None else int(n_bytes)
-        self._ck(self._L.agcm_stream_crypt_peer(self._ctx, int(decrypt), _addr(ivb), int(first_block), _dptr(data_in),
-                                                _dptr(data_out), n, int(blocks_after), _dptr(aad),
-                                                0 if aad is None else aad.numel(), int(total_len), _dptr(tag), _dptr(ok),
-                                                _stream(stream)))
+        n = (0 if data_in is None else data_in.numel()) if n_bytes is None else int(n_bytes)
+        fn = self._L.agcm_stream_crypt_peer_async if defer else self._L.agcm_stream_crypt_peer
+        self._ck(fn(self._ctx, int(decrypt), _addr(ivb), int(first_block), _dptr(data_in), _dptr(data_out), n,
+                    int(blocks_after), _dptr(aad), 0 if aad is None else aad.numel(), int(total_len), _dptr(tag), _dptr(ok),
+                    _stream(stream)))
+
+    def peer_join(self, stream=None):
+        """`stream` waits for every deferred peer finish issued so far (no host synchronisation)."""
+        self._ck(self._L.agcm_peer_join(self._ctx, _stream(stream)))
 
     def gctr_device(self, iv, first_block, data_in, data_out, n_bytes=None, stream=None):
         ivb = _np_u8(iv)

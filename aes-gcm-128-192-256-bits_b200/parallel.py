@@ -81,8 +81,9 @@ class PeerExchange:
 
     Allocates one small symmetric-memory buffer per rank (torch.distributed._symmetric_memory:
     CUDA VMM allocations mapped into every process of the node), hands the peer addresses to the
-    engine, and barriers once.  After that a sharded message costs ONE kernel launch per rank and
-    no collective call: the 16-byte partials cross NVLink as plain stores from the kernel's tail.
+    engine, and barriers once.  After that a sharded message costs one bulk kernel per rank plus a
+    one-warp finish on the engine's side stream, and no collective call: the 16-byte partials cross
+    NVLink as plain stores from the bulk kernel's tail (src/gcm_ghash.vhd:317-344 linearity).
     """
 
     def __init__(self, engine, group=None):
@@ -100,6 +101,26 @@ class PeerExchange:
         torch.cuda.synchronize(dev)
         self.engine = engine
 
-    def crypt(self, decrypt, iv, aad, shard, data_in, data_out, total_bytes, tag, ok=None, stream=None):
-        self.engine.stream_crypt_peer_device(decrypt, iv, shard.first_block, data_in, data_out, shard.blocks_after, aad,
-                                             total_bytes, tag, ok, n_bytes=shard.n_bytes, stream=stream)
+    def crypt(self, decrypt, iv, aad, shard, data_in, data_out, total_bytes, tag, ok=None, stream=None, defer=False):
+        """This rank's shard of one message.  defer=True keeps the ranks free-running (the finish of
+        message k overlaps the bulk kernel of message k+1); `join()` before `tag` / `ok` are read.
+        A rank that never posts makes the others fail closed (zero tag, ok = 0) after the timeout;
+        every later call then raises AgcmError(E_PEER_TIMEOUT), and `check()` raises at once."""
+        self.engine.stream_crypt_peer_device(decrypt, iv, shard.first_block, data_in if shard.n_bytes else None,
+                                             data_out if shard.n_bytes else None, shard.blocks_after, aad, total_bytes, tag,
+                                             ok, n_bytes=shard.n_bytes, stream=stream, defer=defer)
+
+    def crypt_host(self, decrypt, iv, aad, shard, h_in, h_out, total_bytes, tag=None):
+        """The same for a shard held in (pinned) HOST memory: chunked H2D / kernel / D2H, the rank's
+        partial posted to the peers, tag (encrypt) or ok flag (decrypt) returned on every rank."""
+        return self.engine.stream_crypt_peer_host(decrypt, iv, shard.first_block, h_in[:shard.n_bytes], h_out[:shard.n_bytes],
+                                                  shard.blocks_after, aad, total_bytes, tag)
+
+    def join(self, stream=None):
+        self.engine.peer_join(stream)
+
+    def check(self):
+        """Synchronise the finishes issued so far and raise if any of them timed out."""
+        if self.engine.peer_timed_out():
+            from . import _lib
+            raise _lib.AgcmError(_lib.E_PEER_TIMEOUT)

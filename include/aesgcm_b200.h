@@ -52,6 +52,7 @@ extern "C" {
 #define AGCM_E_NO_KEY (-5)           /* agcm_set_key() has not been called on this context */
 #define AGCM_E_BAD_ARG (-6)          /* null pointer / unsupported argument */
 #define AGCM_E_NO_DEVICE (-7)        /* no sm_100 device: the engine has no other path */
+#define AGCM_E_PEER_TIMEOUT (-8)     /* a rank never posted its shard partial: that message FAILED CLOSED (tag zeroed, ok = 0) */
 
 typedef struct agcm_ctx agcm_ctx;
 
@@ -132,21 +133,36 @@ int agcm_stream_finish(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], con
                        const uint8_t* d_aad, uint64_t aad_len, uint64_t ct_len, uint8_t* d_tag, uint8_t* d_ok,
                        void* stream);
 
-/* ---- sharded message, partials exchanged over peer memory (NVLink), one launch per rank ----
+/* ---- sharded message, partials exchanged over peer memory (NVLink) ---------------------------
  * agcm_peer_setup: h_peer_ptrs[w] = device address, valid in THIS process, of rank w's exchange
- * buffer (>= 640 bytes, e.g. torch symmetric memory); zeroes this rank's buffer -- barrier before
- * the first exchange.  world <= 16.
- * agcm_stream_crypt_peer: agcm_stream_part + the 16-byte all-to-all + agcm_stream_finish fused in
- * the tail of ONE kernel: the last CTA stores the scaled partial into every peer's buffer, raises
- * an epoch flag, waits (bounded) for the world's flags in its own buffer, XORs the slots and
- * finishes the tag on every rank.  All ranks must call it the same number of times; n_bytes > 0 on
- * every rank; aad_len <= 4096 (else use part + gather + finish).  agcm_peer_status reports a peer
- * that never arrived. */
+ * buffer (>= 2560 bytes, e.g. torch symmetric memory); zeroes this rank's buffer -- barrier before
+ * the first exchange.  world <= 16.  AGCM_PEER_TIMEOUT_MS (environment, default 3000) bounds the wait.
+ * agcm_stream_crypt_peer: agcm_stream_part + the 16-byte all-to-all + agcm_stream_finish without a
+ * collective library call.  The last CTA of the bulk kernel stores the scaled partial into every
+ * peer's buffer (plain stores over NVLink) and raises an epoch flag; it does NOT wait.  A one-warp
+ * finish kernel on a side stream of the context waits (bounded) for the world's flags in this
+ * rank's buffer, XORs the slots and finishes the tag on every rank (the two-way split of
+ * src/gcm_ghash.vhd:317-344 at width `world`); `stream` then waits for that finish, so d_tag / d_ok
+ * are valid in stream order as for every other call.
+ * agcm_stream_crypt_peer_async: the same without the last wait -- the next message's bulk kernel
+ * starts while this message's flags are still arriving, so the ranks are not barriered per message
+ * (a rank may run up to 4 messages ahead of the slowest one; the exchange ring holds 8).  d_tag /
+ * d_ok are valid on `stream` after agcm_peer_join(ctx, stream) (a stream-side wait, no host sync).
+ * All ranks must make the same sequence of peer calls; n_bytes == 0 is allowed (a rank whose
+ * counter range is empty still posts); aad_len <= 4096 (else use part + gather + finish).
+ * FAILS CLOSED: if a rank never posts, the finish zeroes the tag, clears ok, and every later peer
+ * call on the context returns AGCM_E_PEER_TIMEOUT until agcm_peer_setup is called again;
+ * agcm_peer_status (synchronises the side stream) reports it too. */
 int agcm_peer_setup(agcm_ctx* ctx, int rank, int world, const uint64_t* h_peer_ptrs);
 int agcm_peer_status(agcm_ctx* ctx, int* h_timed_out);
+int agcm_peer_join(agcm_ctx* ctx, void* stream);
 int agcm_stream_crypt_peer(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in,
                            uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, const uint8_t* d_aad, uint64_t aad_len,
                            uint64_t total_len, uint8_t* d_tag, uint8_t* d_ok, void* stream);
+int agcm_stream_crypt_peer_async(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], uint64_t first_block,
+                                 const uint8_t* d_in, uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after,
+                                 const uint8_t* d_aad, uint64_t aad_len, uint64_t total_len, uint8_t* d_tag, uint8_t* d_ok,
+                                 void* stream);
 
 /* ---- many independent messages under the shared key ---------------------------
  * Message i: IV d_iv12[12i..], AAD d_aad[aad_off[i]..aad_off[i+1]), payload
@@ -201,6 +217,12 @@ int agcm_stream_part_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], 
                           uint8_t* h_out, uint64_t n_bytes, uint64_t blocks_after, uint8_t h_partial16[16]);
 int agcm_stream_finish_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], const uint8_t* h_partials16, int n_parts,
                             const uint8_t* h_aad, uint64_t aad_len, uint64_t ct_len, uint8_t h_tag[16], int* h_ok);
+/* Host-buffer form of agcm_stream_crypt_peer: this rank's shard is staged through HBM in chunks
+ * (the same H2D / kernel / D2H pipeline), the rank's partial is posted to the peers, and the tag /
+ * ok flag come back to the host on every rank.  Synchronous; no collective library call. */
+int agcm_stream_crypt_peer_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], uint64_t first_block,
+                                const uint8_t* h_in, uint8_t* h_out, uint64_t n_bytes, uint64_t blocks_after,
+                                const uint8_t* h_aad, uint64_t aad_len, uint64_t total_len, uint8_t h_tag[16], int* h_ok);
 int agcm_batch_crypt_uniform_host(agcm_ctx* ctx, int decrypt, int lanes, const uint8_t* h_iv12, const uint8_t* h_aad,
                                   uint64_t aad_len, uint64_t aad_stride, const uint8_t* h_in, uint8_t* h_out,
                                   uint64_t len, uint64_t stride, uint8_t* h_tag, uint8_t* h_ok, size_t n_msgs);

@@ -290,7 +290,7 @@ def test_config1_aes128_4k_messages_vs_oracle_and_openssl(engine, oracle, torch_
     rng = np.random.default_rng(0)
     key = _rb(rng, 16)
     engine.set_key(key)
-    n_msgs, length = 2000, 4096
+    n_msgs, length = 10000, 4096   # 10 k messages
     for alen in (0, 16, 20, 64):
         ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
         data = rng.integers(0, 256, n_msgs * length, dtype=np.uint8)
@@ -299,7 +299,7 @@ def test_config1_aes128_4k_messages_vs_oracle_and_openssl(engine, oracle, torch_
         aad_off = (np.arange(n_msgs + 1) * alen).astype(np.uint64)
         want_out, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), 16, True, ivs, aad, aad_off, data, in_off,
                                                threads=8)
-        for lanes in (0, 1, 8, 32):
+        for lanes in ((0, 1, 8, 32) if alen in (0, 20) else (0,)):
             d_out = torch.empty(n_msgs * length, dtype=torch.uint8, device="cuda")
             d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
             engine.batch_crypt_uniform_device(0, _dev(torch, ivs), _dev(torch, aad) if alen else None, alen, alen,
@@ -468,6 +468,54 @@ def test_config3_shape_strided_packets(engine, oracle, torch_mod):
             assert (d_tags.cpu().numpy() == want_tags).all(), (stride, lanes)
 
 
+def test_batch_split_over_ranks_single_gpu(engine, oracle, torch_mod):
+    """SURVEY 8(e) regime 1 (independent messages, no collective): parallel.batch_split hands each
+    rank a contiguous message range; the ranks are played one after the other on this GPU, each on
+    ITS slice of the buffers (shared-key batch and per-message-key batch, ragged lengths)."""
+    torch = torch_mod
+    from aesgcm_b200.parallel import batch_split
+    rng = np.random.default_rng(77)
+    key = _rb(rng, 24)
+    n_msgs = 1003
+    lens = rng.integers(0, 700, n_msgs)
+    alens = rng.integers(0, 40, n_msgs)
+    in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.uint64)
+    data = rng.integers(0, 256, int(in_off[-1]), dtype=np.uint8)
+    aad = rng.integers(0, 256, int(aad_off[-1]), dtype=np.uint8)
+    ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+    keys = rng.integers(0, 256, 32 * n_msgs, dtype=np.uint8)
+    want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), 24, True, ivs, aad, aad_off, data, in_off, threads=8)
+    wk_ct, wk_tags = oracle.gcm_batch(keys, 32, False, ivs, aad, aad_off, data, in_off, threads=8)
+    engine.set_key(key)
+    for world in (1, 2, 3, 8):
+        got_ct, got_tags = np.zeros_like(data), np.zeros(16 * n_msgs, dtype=np.uint8)
+        gk_ct, gk_tags = np.zeros_like(data), np.zeros(16 * n_msgs, dtype=np.uint8)
+        for rank in range(world):
+            lo, hi = batch_split(n_msgs, world, rank)
+            b0, b1 = int(in_off[lo]), int(in_off[hi])
+            a0, a1 = int(aad_off[lo]), int(aad_off[hi])
+            r_in = _dev(torch, data[b0:b1])
+            r_aad = _dev(torch, aad[a0:a1]) if a1 > a0 else torch.zeros(1, dtype=torch.uint8, device="cuda")
+            r_inoff = torch.from_numpy((in_off[lo:hi + 1] - in_off[lo]).astype(np.int64)).cuda()
+            r_aadoff = torch.from_numpy((aad_off[lo:hi + 1] - aad_off[lo]).astype(np.int64)).cuda()
+            r_iv = _dev(torch, ivs[12 * lo:12 * hi])
+            r_out = torch.zeros(max(1, b1 - b0), dtype=torch.uint8, device="cuda")
+            r_tags = torch.zeros(16 * (hi - lo), dtype=torch.uint8, device="cuda")
+            engine.batch_crypt_device(0, r_iv, r_aad, r_aadoff, r_in if b1 > b0 else r_out, r_inoff, r_out, r_tags)
+            torch.cuda.synchronize()
+            got_ct[b0:b1] = r_out.cpu().numpy()[:b1 - b0]
+            got_tags[16 * lo:16 * hi] = r_tags.cpu().numpy()
+            r_out.zero_()
+            engine.batch_crypt_perkey_device(256, 0, _dev(torch, keys[32 * lo:32 * hi]), r_iv, r_aad, r_aadoff,
+                                             r_in if b1 > b0 else r_out, r_inoff, r_out, r_tags)
+            torch.cuda.synchronize()
+            gk_ct[b0:b1] = r_out.cpu().numpy()[:b1 - b0]
+            gk_tags[16 * lo:16 * hi] = r_tags.cpu().numpy()
+        assert (got_ct == want_ct).all() and (got_tags == want_tags).all(), world
+        assert (gk_ct == wk_ct).all() and (gk_tags == wk_tags).all(), world
+
+
 def test_batch_host_api_roundtrip(engine, oracle):
     rng = np.random.default_rng(9)
     key = _rb(rng, 32)
@@ -616,8 +664,9 @@ def test_counter_range_shards_combine(engine, oracle, torch_mod):
 
 def test_peer_exchange_single_gpu_emulation(engine_lib, oracle, torch_mod):
     """agcm_stream_crypt_peer on ONE GPU: world = 1 (own buffer), and world = 2 emulated with two
-    contexts, two exchange buffers and two streams on the same device (the kernels overlap: the
-    second grid runs on the SMs the first one frees while its last CTA waits for the peer flag)."""
+    contexts, two exchange buffers and two streams on the same device.  The bulk kernels only POST;
+    the one-warp finishes wait on the contexts' side streams.  Covers the synchronous and the
+    deferred form, more messages than the ring holds, and an empty counter range."""
     torch = torch_mod
     import aesgcm_b200
     from aesgcm_b200.parallel import shard_plan
@@ -635,8 +684,9 @@ def test_peer_exchange_single_gpu_emulation(engine_lib, oracle, torch_mod):
         d_in = _dev(torch, pt)
         d_out = torch.zeros_like(d_in)
         d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
-        for rep in range(3):   # epochs 1..3: both parities
-            e0.stream_crypt_peer_device(0, iv, 0, d_in, d_out, 0, d_aad, n, d_tag)
+        for rep in range(11):   # epochs wrap the 8-deep ring
+            e0.stream_crypt_peer_device(0, iv, 0, d_in, d_out, 0, d_aad, n, d_tag, defer=bool(rep & 1))
+        e0.peer_join()
         torch.cuda.synchronize()
         assert d_out.cpu().numpy().tobytes() == want_ct and d_tag.cpu().numpy().tobytes() == want_tag
         assert not e0.peer_timed_out()
@@ -648,34 +698,73 @@ def test_peer_exchange_single_gpu_emulation(engine_lib, oracle, torch_mod):
     e0.peer_setup(0, 2, ptrs)
     e1.peer_setup(1, 2, ptrs)
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-    for n in (16 * 100 + 7, 4 * 16 * 151552 + 11):
+    for n in (9, 16 * 100 + 7, 4 * 16 * 151552 + 11):   # 9 B: one block, rank 1's range is empty
         pt = rng.integers(0, 256, n, dtype=np.uint8)
         want_ct, want_tag = oracle.gcm_crypt(key, iv, aad, pt, threads=8)
         d_in = _dev(torch, pt)
         for dec in (0, 1):
-            src = d_in if not dec else _dev(torch, np.frombuffer(want_ct, dtype=np.uint8))
-            d_out = torch.zeros_like(d_in)
-            tags = [torch.zeros(16, dtype=torch.uint8, device="cuda") for _ in range(2)]
-            oks = [torch.zeros(1, dtype=torch.uint8, device="cuda") for _ in range(2)]
-            if dec:
-                for t in tags:
-                    t.copy_(torch.from_numpy(np.frombuffer(want_tag, dtype=np.uint8).copy()))
-            torch.cuda.synchronize()
-            plan = shard_plan(n, 2)
-            for r, (eng, st) in enumerate(zip((e0, e1), streams)):
-                sh = plan[r]
-                sl = slice(sh.byte_offset, sh.byte_offset + sh.n_bytes)
-                eng.stream_crypt_peer_device(dec, iv, sh.first_block, src[sl], d_out[sl], sh.blocks_after, d_aad, n, tags[r],
-                                             oks[r], n_bytes=sh.n_bytes, stream=st)
-            torch.cuda.synchronize()
-            assert not e0.peer_timed_out() and not e1.peer_timed_out()
-            assert d_out.cpu().numpy().tobytes() == (pt.tobytes() if dec else want_ct), (n, dec)
-            if dec:
-                assert int(oks[0].item()) == 1 and int(oks[1].item()) == 1
-            else:
-                assert tags[0].cpu().numpy().tobytes() == want_tag and tags[1].cpu().numpy().tobytes() == want_tag
+            for defer in (False, True):
+                src = d_in if not dec else _dev(torch, np.frombuffer(want_ct, dtype=np.uint8))
+                d_out = torch.zeros_like(d_in)
+                tags = [torch.zeros(16, dtype=torch.uint8, device="cuda") for _ in range(2)]
+                oks = [torch.zeros(1, dtype=torch.uint8, device="cuda") for _ in range(2)]
+                if dec:
+                    for t in tags:
+                        t.copy_(torch.from_numpy(np.frombuffer(want_tag, dtype=np.uint8).copy()))
+                torch.cuda.synchronize()
+                plan = shard_plan(n, 2)
+                for rep in range(3 if defer else 1):
+                    for r, (eng, st) in enumerate(zip((e0, e1), streams)):
+                        sh = plan[r]
+                        sl = slice(sh.byte_offset, sh.byte_offset + sh.n_bytes)
+                        eng.stream_crypt_peer_device(dec, iv, sh.first_block, src[sl] if sh.n_bytes else None,
+                                                     d_out[sl] if sh.n_bytes else None, sh.blocks_after, d_aad, n, tags[r],
+                                                     oks[r], n_bytes=sh.n_bytes, stream=st, defer=defer)
+                for eng, st in zip((e0, e1), streams):
+                    eng.peer_join(st)
+                torch.cuda.synchronize()
+                assert not e0.peer_timed_out() and not e1.peer_timed_out()
+                assert d_out.cpu().numpy().tobytes() == (pt.tobytes() if dec else want_ct), (n, dec, defer)
+                if dec:
+                    assert int(oks[0].item()) == 1 and int(oks[1].item()) == 1
+                else:
+                    assert tags[0].cpu().numpy().tobytes() == want_tag and tags[1].cpu().numpy().tobytes() == want_tag
     e0.close()
     e1.close()
+
+
+def test_peer_exchange_fails_closed_on_missing_rank(engine_lib, oracle, torch_mod, monkeypatch):
+    """world = 2 but rank 1 never calls: rank 0's finish gives up after the timeout, ZEROES the tag
+    (a tag built from an incomplete XOR must never leave the engine), clears ok, and every later
+    peer call returns AGCM_E_PEER_TIMEOUT until the exchange is set up again."""
+    torch = torch_mod
+    import aesgcm_b200
+    monkeypatch.setenv("AGCM_PEER_TIMEOUT_MS", "200")
+    rng = np.random.default_rng(89)
+    key, iv = _rb(rng, 16), _rb(rng, 12)
+    e0 = aesgcm_b200.GcmEngine(0)
+    e0.set_key(key)
+    bufs = [torch.zeros(4096, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    e0.peer_setup(0, 2, [b.data_ptr() for b in bufs])
+    n = 4096
+    d_in = _dev(torch, rng.integers(0, 256, n, dtype=np.uint8))
+    d_out = torch.zeros_like(d_in)
+    d_tag = torch.full((16,), 0xAA, dtype=torch.uint8, device="cuda")
+    d_ok = torch.ones(1, dtype=torch.uint8, device="cuda")
+    e0.stream_crypt_peer_device(1, iv, 0, d_in, d_out, n // 16, None, 2 * n, d_tag, d_ok)
+    torch.cuda.synchronize()
+    assert int(d_ok.item()) == 0
+    assert e0.peer_timed_out()
+    with pytest.raises(aesgcm_b200.AgcmError) as ei:
+        e0.stream_crypt_peer_device(0, iv, 0, d_in, d_out, n // 16, None, 2 * n, d_tag)
+    assert ei.value.rc == aesgcm_b200._lib.E_PEER_TIMEOUT
+    # encrypt side of the same failure: the tag that comes back is all zero, not a partial XOR
+    e0.peer_setup(0, 2, [b.data_ptr() for b in bufs])
+    e0.stream_crypt_peer_device(0, iv, 0, d_in, d_out, n // 16, None, 2 * n, d_tag)
+    torch.cuda.synchronize()
+    assert d_tag.cpu().numpy().tobytes() == bytes(16)
+    assert e0.peer_timed_out()
+    e0.close()
 
 
 def _peer_worker(rank, world, port, q):
@@ -706,13 +795,34 @@ def _peer_worker(rank, world, port, q):
     d_out = torch.zeros_like(d_in)
     d_tag = torch.zeros(16, dtype=torch.uint8, device=dev)
     d_aad = torch.from_numpy(aad).to(dev)
-    for _ in range(4):
-        px.crypt(0, iv, d_aad, sh, d_in, d_out, n, d_tag)
+    for rep in range(12):
+        px.crypt(0, iv, d_aad, sh, d_in, d_out, n, d_tag, defer=rep >= 4)
+    px.join()
     torch.cuda.synchronize()
     want_ct, want_tag = o.gcm_crypt(key, iv, aad.tobytes(), pt, threads=4)
     ok = (d_out.cpu().numpy().tobytes() == want_ct[sh.byte_offset:sh.byte_offset + sh.n_bytes]
           and d_tag.cpu().numpy().tobytes() == want_tag and not eng.peer_timed_out())
-    q.put((rank, ok))
+    # host-buffer form of the same exchange
+    h_out = np.zeros(sh.n_bytes, dtype=np.uint8)
+    tag_h = px.crypt_host(0, iv, aad, sh, pt[sh.byte_offset:sh.byte_offset + sh.n_bytes].copy(), h_out, n)
+    ok = ok and tag_h == want_tag and h_out.tobytes() == want_ct[sh.byte_offset:sh.byte_offset + sh.n_bytes]
+    # regime 1: independent messages split over the ranks (parallel.batch_split), no collective
+    from aesgcm_b200.parallel import batch_split
+    n_msgs, length = 4001, 1500
+    ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+    msgs = rng.integers(0, 256, n_msgs * length, dtype=np.uint8)
+    lo, hi = batch_split(n_msgs, world, rank)
+    b_in = torch.from_numpy(msgs[lo * length:hi * length].copy()).to(dev)
+    b_out = torch.zeros_like(b_in)
+    b_tags = torch.zeros(16 * (hi - lo), dtype=torch.uint8, device=dev)
+    eng.batch_crypt_uniform_device(0, torch.from_numpy(ivs[12 * lo:12 * hi].copy()).to(dev), None, 0, 0, b_in, b_out, length,
+                                   length, b_tags, n_msgs=hi - lo)
+    torch.cuda.synchronize()
+    off = (np.arange(hi - lo + 1) * length).astype(np.uint64)
+    w_ct, w_tags = o.gcm_batch(np.frombuffer(key, dtype=np.uint8), 32, True, ivs[12 * lo:12 * hi], None, None,
+                               msgs[lo * length:hi * length], off, threads=4)
+    ok = ok and (b_out.cpu().numpy() == w_ct).all() and (b_tags.cpu().numpy() == w_tags).all()
+    q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
 
