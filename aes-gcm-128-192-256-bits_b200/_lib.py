@@ -46,6 +46,20 @@ SIGNATURES = {
     "agcm_peer_status": (c_int, [c_vp, ctypes.POINTER(c_int)]),
     "agcm_stream_crypt_peer": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u64, c_u64, c_u8p,
                                        c_u8p, c_vp]),
+    "agcm_stream_decrypt_verified": (c_int, [c_vp, c_u8p, c_sz, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u8p, c_u8p, c_vp]),
+    "agcm_stream_decrypt_verified_host": (c_int, [c_vp, c_u8p, c_sz, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u8p,
+                                                  ctypes.POINTER(c_int)]),
+    "agcm_derive_j0": (c_int, [c_vp, c_u8p, c_sz, c_u8p]),
+    "agcm_gctr_j0": (c_int, [c_vp, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_vp]),
+    "agcm_stream_part_j0": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_vp]),
+    "agcm_stream_finish_j0": (c_int, [c_vp, c_int, c_u8p, c_u8p, c_int, c_u8p, c_u64, c_u64, c_u8p, c_u8p, c_vp]),
+    "agcm_stream_crypt_peer_j0": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u64, c_u64,
+                                          c_u8p, c_u8p, c_vp, c_int]),
+    "agcm_batch_derive_j0": (c_int, [c_vp, c_u8p, c_u8p, c_u64, c_sz, c_u8p, c_vp]),
+    "agcm_batch_crypt_j0": (c_int, [c_vp, c_int, c_int, c_u64, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
+                                    c_sz, c_vp]),
+    "agcm_batch_crypt_uniform_j0": (c_int, [c_vp, c_int, c_int, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u8p, c_u64, c_u64,
+                                            c_u8p, c_u8p, c_sz, c_vp]),
     "agcm_peer_join": (c_int, [c_vp, c_vp]),
     "agcm_stream_crypt_peer_async": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u64, c_u64,
                                              c_u8p, c_u8p, c_vp]),

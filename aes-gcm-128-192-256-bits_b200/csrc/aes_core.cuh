@@ -127,18 +127,16 @@ AG_HD AesCtrConst aes_ctr_precompute(const uint32_t* rk, uint32_t iv0, uint32_t 
     return c;
 }
 
-// keystream block for counter value ctr (host order); NR compile-time so that the
-// stage keys (kernel parameters = constant bank) become instruction operands.
-template <int NR, class TE>
-AG_HD void aes_ctr_block(const uint32_t* rk, const AesCtrConst& cc, uint32_t ctr, TE&& te, uint32_t out[4])
+// ---- rounds R0 .. NR-1 (16 lookups each: SubBytes+ShiftRows+MixColumns folded into Te_r, then the
+// stage key) and the last round (SubBytes+ShiftRows only: S sits in byte 0 of Te2, byte 1 of Te3,
+// byte 2 of Te0 and byte 3 of Te1) on a state that already went through rounds 1 .. R0-1.
+// R0 / NR compile-time so that the stage keys (kernel parameters = constant bank) become
+// instruction operands.  config/config_aes_round.py:120-126, src/aes_last_round.vhd:76.
+template <int R0, int NR, class TE>
+AG_HD void aes_rounds_from(const uint32_t* rk, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, TE&& te, uint32_t out[4])
 {
-    const uint32_t s3i = ag_bswap32(ctr) ^ rk[3];
-    uint32_t s0 = cc.k[0] ^ te(3, s3i, 3);
-    uint32_t s1 = cc.k[1] ^ te(2, s3i, 2);
-    uint32_t s2 = cc.k[2] ^ te(1, s3i, 1);
-    uint32_t s3 = cc.k[3] ^ te(0, s3i, 0);
 #pragma unroll
-    for (int r = 2; r < NR; ++r) {
+    for (int r = R0; r < NR; ++r) {
         uint32_t t0 = te(0, s0, 0) ^ te(1, s1, 1) ^ te(2, s2, 2) ^ te(3, s3, 3) ^ rk[4 * r + 0];
         uint32_t t1 = te(0, s1, 0) ^ te(1, s2, 1) ^ te(2, s3, 2) ^ te(3, s0, 3) ^ rk[4 * r + 1];
         uint32_t t2 = te(0, s2, 0) ^ te(1, s3, 1) ^ te(2, s0, 2) ^ te(3, s1, 3) ^ rk[4 * r + 2];
@@ -156,6 +154,19 @@ AG_HD void aes_ctr_block(const uint32_t* rk, const AesCtrConst& cc, uint32_t ctr
              (te(1, s1, 3) & 0xff000000u) ^ rk[4 * NR + 2];
     out[3] = (te(2, s3, 0) & 0x000000ffu) ^ (te(3, s0, 1) & 0x0000ff00u) ^ (te(0, s1, 2) & 0x00ff0000u) ^
              (te(1, s2, 3) & 0xff000000u) ^ rk[4 * NR + 3];
+}
+
+// keystream block for counter value ctr (host order); NR compile-time so that the
+// stage keys (kernel parameters = constant bank) become instruction operands.
+template <int NR, class TE>
+AG_HD void aes_ctr_block(const uint32_t* rk, const AesCtrConst& cc, uint32_t ctr, TE&& te, uint32_t out[4])
+{
+    const uint32_t s3i = ag_bswap32(ctr) ^ rk[3];
+    uint32_t s0 = cc.k[0] ^ te(3, s3i, 3);
+    uint32_t s1 = cc.k[1] ^ te(2, s3i, 2);
+    uint32_t s2 = cc.k[2] ^ te(1, s3i, 1);
+    uint32_t s3 = cc.k[3] ^ te(0, s3i, 0);
+    aes_rounds_from<2, NR>(rk, s0, s1, s2, s3, te, out);
 }
 
 // ---- counter mode for a lane whose counter keeps its low byte (and, almost always, its
@@ -194,25 +205,7 @@ AG_HD void aes_ctr_block_cached(const uint32_t* rk, const AesCtrConst& cc, AesCt
     uint32_t s1 = c.q[1] ^ te(0, r1, 0) ^ te(1, r2, 1);
     uint32_t s2 = c.q[2] ^ te(0, r2, 0) ^ te(3, r1, 3);
     uint32_t s3 = c.q[3] ^ te(2, r1, 2) ^ te(3, r2, 3);
-#pragma unroll
-    for (int r = 3; r < NR; ++r) {
-        uint32_t t0 = te(0, s0, 0) ^ te(1, s1, 1) ^ te(2, s2, 2) ^ te(3, s3, 3) ^ rk[4 * r + 0];
-        uint32_t t1 = te(0, s1, 0) ^ te(1, s2, 1) ^ te(2, s3, 2) ^ te(3, s0, 3) ^ rk[4 * r + 1];
-        uint32_t t2 = te(0, s2, 0) ^ te(1, s3, 1) ^ te(2, s0, 2) ^ te(3, s1, 3) ^ rk[4 * r + 2];
-        uint32_t t3 = te(0, s3, 0) ^ te(1, s0, 1) ^ te(2, s1, 2) ^ te(3, s2, 3) ^ rk[4 * r + 3];
-        s0 = t0;
-        s1 = t1;
-        s2 = t2;
-        s3 = t3;
-    }
-    out[0] = (te(2, s0, 0) & 0x000000ffu) ^ (te(3, s1, 1) & 0x0000ff00u) ^ (te(0, s2, 2) & 0x00ff0000u) ^
-             (te(1, s3, 3) & 0xff000000u) ^ rk[4 * NR + 0];
-    out[1] = (te(2, s1, 0) & 0x000000ffu) ^ (te(3, s2, 1) & 0x0000ff00u) ^ (te(0, s3, 2) & 0x00ff0000u) ^
-             (te(1, s0, 3) & 0xff000000u) ^ rk[4 * NR + 1];
-    out[2] = (te(2, s2, 0) & 0x000000ffu) ^ (te(3, s3, 1) & 0x0000ff00u) ^ (te(0, s0, 2) & 0x00ff0000u) ^
-             (te(1, s1, 3) & 0xff000000u) ^ rk[4 * NR + 2];
-    out[3] = (te(2, s3, 0) & 0x000000ffu) ^ (te(3, s0, 1) & 0x0000ff00u) ^ (te(0, s1, 2) & 0x00ff0000u) ^
-             (te(1, s2, 3) & 0xff000000u) ^ rk[4 * NR + 3];
+    aes_rounds_from<3, NR>(rk, s0, s1, s2, s3, te, out);
 }
 
 // ---- counter mode for a lane that walks CONSECUTIVE (or small-stride) counters of one
@@ -249,25 +242,7 @@ AG_HD void aes_ctr_block_seq(const uint32_t* rk, const AesCtrConst& cc, AesCtrSe
     uint32_t s1 = c.q[1] ^ te(3, a, 3);
     uint32_t s2 = c.q[2] ^ te(2, a, 2);
     uint32_t s3 = c.q[3] ^ te(1, a, 1);
-#pragma unroll
-    for (int r = 3; r < NR; ++r) {
-        uint32_t t0 = te(0, s0, 0) ^ te(1, s1, 1) ^ te(2, s2, 2) ^ te(3, s3, 3) ^ rk[4 * r + 0];
-        uint32_t t1 = te(0, s1, 0) ^ te(1, s2, 1) ^ te(2, s3, 2) ^ te(3, s0, 3) ^ rk[4 * r + 1];
-        uint32_t t2 = te(0, s2, 0) ^ te(1, s3, 1) ^ te(2, s0, 2) ^ te(3, s1, 3) ^ rk[4 * r + 2];
-        uint32_t t3 = te(0, s3, 0) ^ te(1, s0, 1) ^ te(2, s1, 2) ^ te(3, s2, 3) ^ rk[4 * r + 3];
-        s0 = t0;
-        s1 = t1;
-        s2 = t2;
-        s3 = t3;
-    }
-    out[0] = (te(2, s0, 0) & 0x000000ffu) ^ (te(3, s1, 1) & 0x0000ff00u) ^ (te(0, s2, 2) & 0x00ff0000u) ^
-             (te(1, s3, 3) & 0xff000000u) ^ rk[4 * NR + 0];
-    out[1] = (te(2, s1, 0) & 0x000000ffu) ^ (te(3, s2, 1) & 0x0000ff00u) ^ (te(0, s3, 2) & 0x00ff0000u) ^
-             (te(1, s0, 3) & 0xff000000u) ^ rk[4 * NR + 1];
-    out[2] = (te(2, s2, 0) & 0x000000ffu) ^ (te(3, s3, 1) & 0x0000ff00u) ^ (te(0, s0, 2) & 0x00ff0000u) ^
-             (te(1, s1, 3) & 0xff000000u) ^ rk[4 * NR + 2];
-    out[3] = (te(2, s3, 0) & 0x000000ffu) ^ (te(3, s0, 1) & 0x0000ff00u) ^ (te(0, s1, 2) & 0x00ff0000u) ^
-             (te(1, s2, 3) & 0xff000000u) ^ rk[4 * NR + 3];
+    aes_rounds_from<3, NR>(rk, s0, s1, s2, s3, te, out);
 }
 
 // One name for both per-lane caches, selected by the cache type the caller keeps.

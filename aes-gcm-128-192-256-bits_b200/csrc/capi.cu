@@ -87,6 +87,8 @@ struct agcm_ctx {
     uint8_t* d_chunk_partials = nullptr;
     uint8_t* d_aad_stage = nullptr;
     size_t aad_stage_cap = 0;
+    uint8_t* d_verify = nullptr;     // whole ciphertext of a verify-then-release host decrypt, grown on demand
+    size_t verify_cap = 0;
     bool pipeline_ready = false;
     size_t chunk_bytes = 32u << 20;
 };
@@ -188,7 +190,7 @@ struct FuseFinish {
 // the same launch.  parts_raw: per-CTA scratch (AG_MAX_CTA x 4 words); counter: its ticket.
 int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
                uint64_t n_bytes, uint64_t blocks_after, uint32_t* parts_raw, uint8_t* d_partial16, cudaStream_t st,
-               uint32_t* counter, const FuseFinish* ff = nullptr, uint32_t peer_epoch = 0)
+               uint32_t* counter, const FuseFinish* ff = nullptr, uint32_t peer_epoch = 0, const uint8_t* gate = nullptr)
 {
     if (n_bytes == 0) {
         if (d_partial16) AG_CUDA(c, cudaMemsetAsync(d_partial16, 0, 16, st));
@@ -206,6 +208,7 @@ int run_stream(agcm_ctx* c, int mode, const uint8_t iv[12], uint64_t first_block
     p.key = c->d_key;
     p.te0 = c->d_te0;
     p.partials = parts_raw;
+    p.gate = gate;
     if (mode != AG_MODE_CTR_ONLY) {
         p.done_counter = counter;
         p.scale_e = blocks_after;
@@ -520,6 +523,7 @@ void agcm_ctx_destroy(agcm_ctx* c)
     memset(c->h_key_in, 0, sizeof(c->h_key_in));
     cudaFree(c->d_chunk_partials);
     cudaFree(c->d_aad_stage);
+    cudaFree(c->d_verify);
     cudaFree(c->d_te0);
     cudaFree(c->d_key);
     cudaFree(c->d_parts);
@@ -746,6 +750,7 @@ int agcm_peer_setup(agcm_ctx* c, int rank, int world, const uint64_t* h_peer_ptr
     if (!c->d_peer_bufs) AG_CUDA(c, cudaMalloc(&c->d_peer_bufs, sizeof(uint8_t*) * AG_PEER_MAX));
     if (!c->d_peer_status) AG_CUDA(c, cudaMalloc(&c->d_peer_status, sizeof(uint32_t)));
     if (!c->h_peer_status) AG_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_peer_status), sizeof(uint32_t), cudaHostAllocMapped));
+    AG_CUDA(c, ag_preload_peer_kernels());
     if (!c->peer_side) {
         AG_CUDA(c, cudaStreamCreateWithFlags(&c->peer_side, cudaStreamNonBlocking));
         for (uint32_t i = 0; i < AG_PEER_RING; ++i) {
@@ -892,6 +897,90 @@ int agcm_stream_crypt_peer_async(agcm_ctx* c, int decrypt, const uint8_t h_iv12[
                              d_tag, d_ok, stream, true);
 }
 
+// ---- IVs of any length on the shard / peer / gctr entry points: the caller derives J0 once
+// (agcm_derive_j0) and passes it instead of the 12 IV bytes.  The counter field of J0 replaces
+// the constant 1 of the 96-bit case for the duration of the call.
+namespace {
+struct J0Scope {
+    agcm_ctx* c;
+    J0Scope(agcm_ctx* ctx, const uint8_t j0[16]) : c(ctx)
+    {
+        if (c && j0) c->j0ctr = ((uint32_t)j0[12] << 24) | ((uint32_t)j0[13] << 16) | ((uint32_t)j0[14] << 8) | (uint32_t)j0[15];
+    }
+    ~J0Scope() { if (c) c->j0ctr = 1; }
+};
+}  // namespace
+
+int agcm_derive_j0(agcm_ctx* c, const uint8_t* h_iv, size_t iv_len, uint8_t h_j0[16])
+{
+    if (!c || !h_iv || !h_j0) return AGCM_E_BAD_ARG;
+    if (iv_len == 12) {
+        memcpy(h_j0, h_iv, 12);
+        h_j0[12] = h_j0[13] = h_j0[14] = 0;
+        h_j0[15] = 1;
+        return AGCM_OK;
+    }
+    AG_CUDA(c, cudaSetDevice(c->device));
+    return derive_j0(c, h_iv, iv_len, h_j0, nullptr);
+}
+
+int agcm_gctr_j0(agcm_ctx* c, const uint8_t h_j0[16], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
+                 uint64_t n_bytes, void* stream)
+{
+    if (!c || !h_j0) return AGCM_E_BAD_ARG;
+    J0Scope scope(c, h_j0);
+    return agcm_gctr(c, h_j0, first_block, d_in, d_out, n_bytes, stream);
+}
+
+int agcm_stream_part_j0(agcm_ctx* c, int decrypt, const uint8_t h_j0[16], uint64_t first_block, const uint8_t* d_in,
+                        uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, uint8_t* d_partial16, void* stream)
+{
+    if (!c || !h_j0) return AGCM_E_BAD_ARG;
+    J0Scope scope(c, h_j0);
+    return agcm_stream_part(c, decrypt, h_j0, first_block, d_in, d_out, n_bytes, blocks_after, d_partial16, stream);
+}
+
+int agcm_stream_finish_j0(agcm_ctx* c, int decrypt, const uint8_t h_j0[16], const uint8_t* d_partials16, int n_parts,
+                          const uint8_t* d_aad, uint64_t aad_len, uint64_t ct_len, uint8_t* d_tag, uint8_t* d_ok, void* stream)
+{
+    if (!c || !h_j0) return AGCM_E_BAD_ARG;
+    J0Scope scope(c, h_j0);
+    return agcm_stream_finish(c, decrypt, h_j0, d_partials16, n_parts, d_aad, aad_len, ct_len, d_tag, d_ok, stream);
+}
+
+int agcm_stream_crypt_peer_j0(agcm_ctx* c, int decrypt, const uint8_t h_j0[16], uint64_t first_block, const uint8_t* d_in,
+                              uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, const uint8_t* d_aad, uint64_t aad_len,
+                              uint64_t total_len, uint8_t* d_tag, uint8_t* d_ok, void* stream, int deferred)
+{
+    if (!c || !h_j0) return AGCM_E_BAD_ARG;
+    J0Scope scope(c, h_j0);
+    return stream_crypt_peer(c, decrypt, h_j0, first_block, d_in, d_out, n_bytes, blocks_after, d_aad, aad_len, total_len, d_tag,
+                             d_ok, stream, deferred != 0);
+}
+
+int agcm_stream_decrypt_verified(agcm_ctx* c, const uint8_t* h_iv, size_t iv_len, const uint8_t* d_aad, uint64_t aad_len,
+                                 const uint8_t* d_ct, uint8_t* d_pt, uint64_t n_bytes, const uint8_t* d_tag, uint8_t* d_ok,
+                                 void* stream)
+{
+    if (!c || !h_iv || !d_tag || !d_ok || (n_bytes && (!d_ct || !d_pt)) || (aad_len && !d_aad)) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (((n_bytes + 15) >> 4) > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t j0[16];
+    int rc = agcm_derive_j0(c, h_iv, iv_len, j0);
+    if (rc) return rc;
+    J0Scope scope(c, j0);
+    // pass 1: GHASH over the ciphertext only (about 4x the rate of the fused pass), then the tag check
+    uint8_t* part = c->d_scratch + SC_PART_CT;
+    rc = run_stream(c, AG_MODE_GHASH_ONLY, j0, 0, d_ct, nullptr, n_bytes, 0, c->d_parts, part, st, c->d_counters);
+    if (rc) return rc;
+    rc = run_finish(c, 1, j0, part, 1, d_aad, aad_len, n_bytes, const_cast<uint8_t*>(d_tag), d_ok, st);
+    if (rc) return rc;
+    // pass 2: GCTR, gated on the device by the flag pass 1 just wrote (no host round trip)
+    return run_stream(c, AG_MODE_CTR_ONLY, j0, 0, d_ct, d_pt, n_bytes, 0, c->d_parts, nullptr, st, c->d_counters, nullptr, 0, d_ok);
+}
+
 int agcm_gctr(agcm_ctx* c, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
               uint64_t n_bytes, void* stream)
 {
@@ -955,16 +1044,17 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
     return AGCM_OK;
 }
 
-int agcm_batch_crypt(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len_hint, const uint8_t* d_iv12,
-                     const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
-                     uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
+static int batch_offsets(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len_hint, const uint8_t* d_iv, int iv_is_j0,
+                         const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
+                         uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
 {
     if (!c) return AGCM_E_BAD_ARG;
     if (n_msgs && (!d_in_off || !d_in || !d_out)) return AGCM_E_BAD_ARG;
     if ((d_aad == nullptr) != (d_aad_off == nullptr)) return AGCM_E_BAD_ARG;
     BatchParams p;
     memset(&p, 0, sizeof(p));
-    p.iv = d_iv12;
+    p.iv = d_iv;
+    p.iv_is_j0 = iv_is_j0 ? 1u : 0u;
     p.aad = d_aad;
     p.aad_off = d_aad_off;
     p.in = d_in;
@@ -975,17 +1065,20 @@ int agcm_batch_crypt(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len_hint,
     return batch_common(c, decrypt, lanes, avg_len_hint, p, n_msgs, stream);
 }
 
-int agcm_batch_crypt_uniform(agcm_ctx* c, int decrypt, int lanes, const uint8_t* d_iv12, const uint8_t* d_aad,
-                             uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out, uint64_t len,
-                             uint64_t stride, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
+static int batch_uniform(agcm_ctx* c, int decrypt, int lanes, const uint8_t* d_iv, int iv_is_j0, const uint8_t* d_aad,
+                         uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out, uint64_t len,
+                         uint64_t stride, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
 {
     if (!c) return AGCM_E_BAD_ARG;
     if (n_msgs && len && (!d_in || !d_out)) return AGCM_E_BAD_ARG;
     if (stride < len || (aad_len && (!d_aad || aad_stride < aad_len))) return AGCM_E_BAD_LEN;
-    if (((len + 15) >> 4) > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
+    // counter range AND the 32-bit block index of the unified AAD | payload | length sequence
+    if (((len + 15) >> 4) > kMaxBlocks || ((aad_len + 15) >> 4) + ((len + 15) >> 4) + 1 > 0xFFFFFFFFull)
+        return AGCM_E_COUNTER_OVERFLOW;
     BatchParams p;
     memset(&p, 0, sizeof(p));
-    p.iv = d_iv12;
+    p.iv = d_iv;
+    p.iv_is_j0 = iv_is_j0 ? 1u : 0u;
     p.aad = aad_len ? d_aad : nullptr;
     p.in = d_in;
     p.out = d_out;
@@ -998,6 +1091,50 @@ int agcm_batch_crypt_uniform(agcm_ctx* c, int decrypt, int lanes, const uint8_t*
     const bool aligned16 = ((((uintptr_t)d_in | (uintptr_t)d_out) | stride) & 15) == 0;
     // work estimate for the layout choice: an AAD block costs about a quarter of a payload block (no AES)
     return batch_common(c, decrypt, lanes, len + (d_aad ? aad_len / 4 : 0), p, n_msgs, stream, aligned16);
+}
+
+int agcm_batch_crypt(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len_hint, const uint8_t* d_iv12,
+                     const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
+                     uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
+{
+    return batch_offsets(c, decrypt, lanes, avg_len_hint, d_iv12, 0, d_aad, d_aad_off, d_in, d_in_off, d_out, d_tag, d_ok, n_msgs,
+                         stream);
+}
+
+int agcm_batch_crypt_j0(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len_hint, const uint8_t* d_j0,
+                        const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
+                        uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
+{
+    return batch_offsets(c, decrypt, lanes, avg_len_hint, d_j0, 1, d_aad, d_aad_off, d_in, d_in_off, d_out, d_tag, d_ok, n_msgs,
+                         stream);
+}
+
+int agcm_batch_crypt_uniform(agcm_ctx* c, int decrypt, int lanes, const uint8_t* d_iv12, const uint8_t* d_aad,
+                             uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out, uint64_t len,
+                             uint64_t stride, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
+{
+    return batch_uniform(c, decrypt, lanes, d_iv12, 0, d_aad, aad_len, aad_stride, d_in, d_out, len, stride, d_tag, d_ok, n_msgs,
+                         stream);
+}
+
+int agcm_batch_crypt_uniform_j0(agcm_ctx* c, int decrypt, int lanes, const uint8_t* d_j0, const uint8_t* d_aad,
+                                uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out, uint64_t len,
+                                uint64_t stride, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
+{
+    return batch_uniform(c, decrypt, lanes, d_j0, 1, d_aad, aad_len, aad_stride, d_in, d_out, len, stride, d_tag, d_ok, n_msgs,
+                         stream);
+}
+
+int agcm_batch_derive_j0(agcm_ctx* c, const uint8_t* d_iv, const uint64_t* d_iv_off, uint64_t iv_len, size_t n_msgs,
+                         uint8_t* d_j0, void* stream)
+{
+    if (!c || (n_msgs && (!d_iv || !d_j0))) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (!d_iv_off && iv_len == 0) return AGCM_E_BAD_LEN;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    AG_CUDA(c, ag_launch_batch_j0(c->d_key, d_iv, d_iv_off, iv_len, n_msgs, d_j0, (cudaStream_t)stream));
+    if (n_msgs) c->launches++;
+    return AGCM_OK;
 }
 
 static int perkey_common(agcm_ctx* c, int mode, int decrypt, BatchParams& p, size_t n_msgs, void* stream)
@@ -1044,7 +1181,8 @@ int agcm_batch_crypt_perkey_uniform(agcm_ctx* c, int mode, int decrypt, const ui
     if (!c) return AGCM_E_BAD_ARG;
     if (n_msgs && len && (!d_in || !d_out)) return AGCM_E_BAD_ARG;
     if (stride < len || (aad_len && (!d_aad || aad_stride < aad_len))) return AGCM_E_BAD_LEN;
-    if (((len + 15) >> 4) > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
+    if (((len + 15) >> 4) > kMaxBlocks || ((aad_len + 15) >> 4) + ((len + 15) >> 4) + 1 > 0xFFFFFFFFull)
+        return AGCM_E_COUNTER_OVERFLOW;
     BatchParams p;
     memset(&p, 0, sizeof(p));
     p.keys = d_keys;
@@ -1075,6 +1213,17 @@ void agcm_host_free(void* p)
     if (p) cudaFreeHost(p);
 }
 
+// granule of the host pipeline: the tuned size, grown for very long ranges so the partial list stays bounded
+static uint64_t pick_chunk(const agcm_ctx* c, uint64_t n_bytes)
+{
+    uint64_t b = c->chunk_bytes;
+    while ((n_bytes + b - 1) / b > SC_PARTS_MAX && b < kChunkBytesMax) {
+        b <<= 1;
+        if (b > kChunkBytesMax) b = kChunkBytesMax;   // a non-power-of-two AGCM_CHUNK_MB must not outgrow d_stage
+    }
+    return b;
+}
+
 // chunked H2D -> fused kernel -> D2H of one counter range; the per-chunk partials
 // (each scaled for everything after it, including `blocks_after0`) land in
 // c->d_chunk_partials[0..n_chunks).  Leaves the slot streams running.
@@ -1082,12 +1231,7 @@ static int host_pipeline(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uin
                          uint8_t* h_out, uint64_t n_bytes, uint64_t blocks_after0, uint64_t* n_chunks_out)
 {
     const uint64_t nblocks = (n_bytes + 15) >> 4;
-    // granule: the tuned size, grown for very long ranges so the partial list stays bounded
-    uint64_t kChunkBytes = c->chunk_bytes;
-    while ((n_bytes + kChunkBytes - 1) / kChunkBytes > SC_PARTS_MAX && kChunkBytes < kChunkBytesMax) {
-        kChunkBytes <<= 1;
-        if (kChunkBytes > kChunkBytesMax) kChunkBytes = kChunkBytesMax;   // a non-power-of-two AGCM_CHUNK_MB must not outgrow d_stage
-    }
+    const uint64_t kChunkBytes = pick_chunk(c, n_bytes);
     const uint64_t n_chunks = (n_bytes + kChunkBytes - 1) / kChunkBytes;
     if (n_chunks > kMaxChunks || n_chunks > SC_PARTS_MAX) return AGCM_E_BAD_LEN;
     const int mode = decrypt ? AG_MODE_DEC : AG_MODE_ENC;
@@ -1256,6 +1400,66 @@ int agcm_stream_crypt_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], c
     else AG_CUDA(c, cudaMemcpyAsync(h_tag, d_tag, 16, cudaMemcpyDeviceToHost, c->hs[0]));
     AG_CUDA(c, cudaStreamSynchronize(c->hs[0]));
     if (h_ok) *h_ok = okb ? 1 : 0;
+    return AGCM_OK;
+}
+
+int agcm_stream_decrypt_verified_host(agcm_ctx* c, const uint8_t* h_iv, size_t iv_len, const uint8_t* h_aad, uint64_t aad_len,
+                                      const uint8_t* h_ct, uint8_t* h_pt, uint64_t n_bytes, const uint8_t h_tag[16], int* h_ok)
+{
+    if (!c || !h_iv || !h_tag || !h_ok || (n_bytes && (!h_ct || !h_pt)) || (aad_len && !h_aad)) return AGCM_E_BAD_ARG;
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (((n_bytes + 15) >> 4) > kMaxBlocks) return AGCM_E_COUNTER_OVERFLOW;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    int rc = ensure_pipeline(c);
+    if (rc) return rc;
+    rc = reserve_aad_stage(c, aad_len);
+    if (rc) return rc;
+    if (n_bytes > c->verify_cap) {   // the ciphertext stays in HBM between the two passes
+        AG_CUDA(c, cudaFree(c->d_verify));
+        c->d_verify = nullptr;
+        c->verify_cap = 0;
+        AG_CUDA(c, cudaMalloc(&c->d_verify, n_bytes));
+        c->verify_cap = n_bytes;
+    }
+    uint8_t j0[16];
+    rc = agcm_derive_j0(c, h_iv, iv_len, j0);
+    if (rc) return rc;
+    J0Scope scope(c, j0);
+    const uint64_t nblocks = (n_bytes + 15) >> 4, chunk = pick_chunk(c, n_bytes);
+    const uint64_t n_chunks = (n_bytes + chunk - 1) / chunk;
+    if (n_chunks > SC_PARTS_MAX) return AGCM_E_BAD_LEN;
+    // pass 1: copy in and absorb, chunk by chunk (the copy of chunk k+1 overlaps the GHASH of chunk k)
+    if (aad_len) AG_CUDA(c, cudaMemcpyAsync(c->d_aad_stage, h_aad, aad_len, cudaMemcpyHostToDevice, c->hs[0]));
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        const int s = (int)(k % kSlots);
+        const uint64_t off = k * chunk, nb = (n_bytes - off) < chunk ? (n_bytes - off) : chunk;
+        const uint64_t after = nblocks - (off >> 4) - ((nb + 15) >> 4);
+        AG_CUDA(c, cudaMemcpyAsync(c->d_verify + off, h_ct + off, nb, cudaMemcpyHostToDevice, c->hs[s]));
+        rc = run_stream(c, AG_MODE_GHASH_ONLY, j0, 0, c->d_verify + off, nullptr, nb, after, c->d_stage_parts[s],
+                        c->d_chunk_partials + 16 * k, c->hs[s], c->d_counters + 1 + s);
+        if (rc) return rc;
+    }
+    for (int s = 1; s < kSlots; ++s) AG_CUDA(c, cudaStreamSynchronize(c->hs[s]));
+    uint8_t* d_tag = c->d_scratch + SC_TAG;
+    uint8_t* d_ok = c->d_scratch + SC_OK;
+    AG_CUDA(c, cudaMemcpyAsync(d_tag, h_tag, 16, cudaMemcpyHostToDevice, c->hs[0]));
+    rc = run_finish(c, 1, j0, c->d_chunk_partials, (int)n_chunks, c->d_aad_stage, aad_len, n_bytes, d_tag, d_ok, c->hs[0]);
+    if (rc) return rc;
+    uint8_t okb = 0;
+    AG_CUDA(c, cudaMemcpyAsync(&okb, d_ok, 1, cudaMemcpyDeviceToHost, c->hs[0]));
+    AG_CUDA(c, cudaStreamSynchronize(c->hs[0]));
+    *h_ok = okb ? 1 : 0;
+    if (!okb) return AGCM_OK;   // not authentic: no plaintext byte leaves the device
+    // pass 2: GCTR in place, chunk by chunk, copy out
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        const int s = (int)(k % kSlots);
+        const uint64_t off = k * chunk, nb = (n_bytes - off) < chunk ? (n_bytes - off) : chunk;
+        rc = run_stream(c, AG_MODE_CTR_ONLY, j0, off >> 4, c->d_verify + off, c->d_verify + off, nb, 0, c->d_stage_parts[s], nullptr,
+                        c->hs[s], c->d_counters + 1 + s);
+        if (rc) return rc;
+        AG_CUDA(c, cudaMemcpyAsync(h_pt + off, c->d_verify + off, nb, cudaMemcpyDeviceToHost, c->hs[s]));
+    }
+    for (int s = 0; s < kSlots; ++s) AG_CUDA(c, cudaStreamSynchronize(c->hs[s]));
     return AGCM_OK;
 }
 

@@ -140,6 +140,8 @@ struct StreamParams {
     // peer_bufs[w] = rank w's exchange buffer mapped in this process (AG_PEER_* layout)
     uint8_t* const* peer_bufs;
     uint32_t peer_rank, peer_world, peer_epoch;
+    // verify-then-release decrypt: the whole grid returns at once, output untouched, when *gate == 0
+    const uint8_t* gate;
 };
 
 // Exchange buffer of one rank: a ring of AG_PEER_RING epochs x AG_PEER_MAX slots of 16 B written
@@ -244,7 +246,8 @@ struct BatchParams {
     const KeyDev* key;
     const uint32_t* te0;
     const uint8_t* keys;       // per-message raw keys (n_msgs x key_bytes) for k_batch_perkey, else null
-    const uint8_t* iv;         // n_msgs x 12
+    const uint8_t* iv;         // n_msgs x 12 (96-bit IVs), or n_msgs x 16 pre-counter blocks J0 when iv_is_j0
+    uint32_t iv_is_j0;         // 1: `iv` holds J0 per message (any IV length, SP 800-38D 7.1; agcm_batch_derive_j0)
     const uint8_t* aad;        // may be null when there is no AAD
     const uint64_t* aad_off;   // n_msgs+1 offsets, or null => uniform (aad_stride, aad_len)
     const uint8_t* in;
@@ -267,7 +270,8 @@ struct MsgDesc {
     const uint8_t* aad;
     uint64_t len, aad_len;              // what THIS unit reads: payload bytes, AAD bytes
     uint64_t total_len, total_aad_len;  // the whole message (the length block, gcm_ghash.vhd:257)
-    uint32_t ctr_off;                   // payload block index of the unit's first block (counter = 2 + ctr_off + j)
+    uint32_t ctr_off;                   // payload block index of the unit's first block (counter = j0ctr + 1 + ctr_off + j)
+    uint32_t j0ctr;                     // counter field of J0: 1 for a 96-bit IV (src/aes_icb.vhd:34,99)
     uint32_t last;                      // the unit ends the message: it absorbs the length block and makes E_K(J0)
 };
 
@@ -285,8 +289,22 @@ AG_HD MsgDesc ag_batch_msg(const BatchParams& p, uint64_t m)
     d.total_len = d.len;
     d.total_aad_len = d.aad_len;
     d.ctr_off = 0;
+    d.j0ctr = 1;
     d.last = 1;
     return d;
+}
+
+// Message m's counter-block prefix as three LE words, and (J0 mode) the counter field of its J0.
+AG_HD void ag_batch_iv(const BatchParams& p, uint64_t m, uint32_t iv[3], uint32_t* j0ctr)
+{
+    const uint8_t* ivp = p.iv + (p.iv_is_j0 ? 16 : 12) * m;
+    iv[0] = iv[1] = iv[2] = 0;
+    for (int j = 0; j < 4; ++j) {
+        iv[0] |= (uint32_t)ivp[j] << (8 * j);
+        iv[1] |= (uint32_t)ivp[4 + j] << (8 * j);
+        iv[2] |= (uint32_t)ivp[8 + j] << (8 * j);
+    }
+    *j0ctr = p.iv_is_j0 ? (((uint32_t)ivp[12] << 24) | ((uint32_t)ivp[13] << 16) | ((uint32_t)ivp[14] << 8) | (uint32_t)ivp[15]) : 1u;
 }
 
 // Segment `seg` of S of message w, the single-GPU form of the counter-range shards of
@@ -364,7 +382,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
             uint32_t x[4] = {0, 0, 0, 0};
             if (!is_len) ag_load_block(d.in + 16 * (uint64_t)j, nv, x);   // in flight during the AES rounds
             uint32_t ks[4];
-            aes_ctr_block_auto<NR>(rk, cc, cache, is_len ? 1u : 2u + d.ctr_off + j, te, ks);
+            aes_ctr_block_auto<NR>(rk, cc, cache, is_len ? d.j0ctr : d.j0ctr + 1u + d.ctr_off + j, te, ks);   // inc32: wraps mod 2^32
             if (is_len) {
                 ej0[0] = ks[0]; ej0[1] = ks[1]; ej0[2] = ks[2]; ej0[3] = ks[3];
                 // [len(A)]64 || [len(C)]64 in bits, big-endian (gcm_ghash.vhd:257)

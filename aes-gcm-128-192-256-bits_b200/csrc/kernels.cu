@@ -412,6 +412,7 @@ template <int NR, int MODE, bool ALIGNED>
 __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_constant__ StreamParams p)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+    if (MODE == AG_MODE_CTR_ONLY && p.gate && __ldcg(p.gate) == 0) return;   // tag did not verify: release nothing
     if (MODE != AG_MODE_GHASH_ONLY) stage_te0(p.te0);
     if (MODE != AG_MODE_CTR_ONLY) fill_gh_tables(p.key->tab[7], nullptr);
     __syncthreads();
@@ -491,6 +492,39 @@ __global__ void __launch_bounds__(32) k_pow(const KeyDev* kd, uint64_t e, uint32
     if (threadIdx.x == 0) { out[0] = r.w[0]; out[1] = r.w[1]; out[2] = r.w[2]; out[3] = r.w[3]; }
 }
 
+// J0 per message for IVs of any length (SP 800-38D 7.1 step 2), one thread per IV: a 96-bit IV
+// gives IV || 0^31 1 (src/aes_icb.vhd:34,118), any other length GHASH_H(IV || 0^(s+64) || [len(IV)]_64)
+// with the serial recurrence of src/gcm_ghash.vhd:269-272.  16 bytes out per message.
+__global__ void k_batch_j0(const KeyDev* kd, const uint8_t* __restrict__ iv, const uint64_t* __restrict__ iv_off,
+                           uint64_t iv_len, uint64_t n, uint8_t* __restrict__ j0)
+{
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n) return;
+    const uint64_t off = iv_off ? iv_off[m] : m * iv_len;
+    const uint64_t len = iv_off ? iv_off[m + 1] - off : iv_len;
+    const uint8_t* p = iv + off;
+    uint8_t* dst = j0 + 16 * m;
+    if (len == 12) {
+        for (int j = 0; j < 12; ++j) dst[j] = p[j];
+        dst[12] = dst[13] = dst[14] = 0;
+        dst[15] = 1;
+        return;
+    }
+    const gf128 h = kd->H;
+    gf128 y = gf_zero();
+    for (uint64_t o = 0; o < len; o += 16) {
+        uint32_t x[4];
+        ag_load_block(p + o, (len - o) < 16 ? (uint32_t)(len - o) : 16u, x);
+        y = gf_mul(gf_xor(y, gf_from_le_words(x[0], x[1], x[2], x[3])), h);
+    }
+    const uint64_t bits = len * 8;
+    y.w[2] ^= (uint32_t)(bits >> 32);
+    y.w[3] ^= (uint32_t)bits;
+    y = gf_mul(y, h);
+    const uint32_t o4[4] = {ag_bswap32(y.w[0]), ag_bswap32(y.w[1]), ag_bswap32(y.w[2]), ag_bswap32(y.w[3])};
+    ag_store_block(dst, 16, o4);
+}
+
 // out16 = xor of n 16-byte partials (natural byte order in and out)
 __global__ void __launch_bounds__(32) k_xor_parts(const uint8_t* __restrict__ parts, uint32_t n, uint8_t* __restrict__ out)
 {
@@ -548,18 +582,15 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
         cache.key = 0xFFFFFFFFu;  // invalid: the key only ever holds 24 bits
         uint32_t e[4] = {0, 0, 0, 0};  // E_K(J0): produced by lane G-1 (the one that meets the length block)
         if (valid) {
-            const MsgDesc d = ag_batch_msg(p, m);
-            const uint8_t* ivp = p.iv + 12 * m;
-            uint32_t iv0 = 0, iv1 = 0, iv2 = 0;
-            if (((uintptr_t)ivp & 3) == 0) {
-                const uint32_t* q = reinterpret_cast<const uint32_t*>(ivp);
+            MsgDesc d = ag_batch_msg(p, m);
+            uint32_t iv0, iv1, iv2;
+            if (!p.iv_is_j0 && ((uintptr_t)(p.iv + 12 * m) & 3) == 0) {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(p.iv + 12 * m);
                 iv0 = q[0]; iv1 = q[1]; iv2 = q[2];
             } else {
-                for (int j = 0; j < 4; ++j) {
-                    iv0 |= (uint32_t)ivp[j] << (8 * j);
-                    iv1 |= (uint32_t)ivp[4 + j] << (8 * j);
-                    iv2 |= (uint32_t)ivp[8 + j] << (8 * j);
-                }
+                uint32_t ivw[3];
+                ag_batch_iv(p, m, ivw, &d.j0ctr);
+                iv0 = ivw[0]; iv1 = ivw[1]; iv2 = ivw[2];
             }
             cc = aes_ctr_precompute(p.rk, iv0, iv1, iv2, te);
             y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, (uint32_t)G, te, gh_g, e);
@@ -648,13 +679,9 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
         uint64_t after = 0;
         MsgDesc d = ag_batch_msg(p, m);
         if (S > 1) d = ag_batch_segment(d, seg, S, &after);
-        const uint8_t* ivp = p.iv + 12 * m;
-        uint32_t iv0 = 0, iv1 = 0, iv2 = 0;
-        for (int j = 0; j < 4; ++j) {
-            iv0 |= (uint32_t)ivp[j] << (8 * j);
-            iv1 |= (uint32_t)ivp[4 + j] << (8 * j);
-            iv2 |= (uint32_t)ivp[8 + j] << (8 * j);
-        }
+        uint32_t ivw[3];
+        ag_batch_iv(p, m, ivw, &d.j0ctr);
+        const uint32_t iv0 = ivw[0], iv1 = ivw[1], iv2 = ivw[2];
         const AesCtrConst cc = aes_ctr_precompute(p.rk, iv0, iv1, iv2, te);
         // lanes step their counter by nt (512: a multiple of 256): the stream kernel's cache fits
         AesCtrCache cache;
@@ -1023,10 +1050,31 @@ cudaError_t ag_launch_pow(const KeyDev* kd, uint64_t e, uint32_t* out, cudaStrea
     return cudaGetLastError();
 }
 
+cudaError_t ag_launch_batch_j0(const KeyDev* kd, const uint8_t* iv, const uint64_t* iv_off, uint64_t iv_len, uint64_t n,
+                               uint8_t* j0, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    k_batch_j0<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kd, iv, iv_off, iv_len, n, j0);
+    return cudaGetLastError();
+}
+
 cudaError_t ag_launch_xor_parts(const uint8_t* parts, uint32_t n, uint8_t* out, cudaStream_t st)
 {
     k_xor_parts<<<1, 32, 0, st>>>(parts, n, out);
     return cudaGetLastError();
+}
+
+// CUDA loads a kernel lazily at its first launch, and that load can wait for running kernels to
+// drain.  A first launch of k_peer_post / k_peer_finish while a finish kernel of the same process
+// spins for a peer flag would then stall until the timeout: load them at agcm_peer_setup instead.
+cudaError_t ag_preload_peer_kernels()
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, k_peer_post);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_peer_finish);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_pow);
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, k_xor_parts);
+    return e;
 }
 
 cudaError_t ag_launch_peer_finish(const PeerFinishParams& p, cudaStream_t st)

@@ -51,7 +51,10 @@ cudaError_t ag_launch_key_setup(KeyDev* kd, const KeyIn& in, const uint32_t* te0
 cudaError_t ag_launch_pow(const KeyDev* kd, uint64_t e, uint32_t* out4, cudaStream_t st);
 cudaError_t ag_launch_finish(const FinishParams& p, cudaStream_t st);
 cudaError_t ag_launch_peer_finish(const PeerFinishParams& p, cudaStream_t st);
+cudaError_t ag_preload_peer_kernels();
 cudaError_t ag_launch_peer_post(uint8_t* const* peer_bufs, uint32_t rank, uint32_t world, uint32_t epoch,
                                 const uint8_t* partial16, cudaStream_t st);
+cudaError_t ag_launch_batch_j0(const KeyDev* kd, const uint8_t* iv, const uint64_t* iv_off, uint64_t iv_len, uint64_t n,
+                               uint8_t* j0, cudaStream_t st);
 cudaError_t ag_launch_xor_parts(const uint8_t* parts16, uint32_t n, uint8_t* out16, cudaStream_t st);
 size_t ag_smem_bytes();

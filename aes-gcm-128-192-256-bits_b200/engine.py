@@ -57,6 +57,7 @@ def _dptr(t):
 class GcmEngine:
     def __init__(self, device=0, n_cta=0, threads=0):
         self._L = _lib.lib()
+        self._j0_cache = {}
         self._ctx = ctypes.c_void_p()
         rc = self._L.agcm_ctx_create_ex(ctypes.byref(self._ctx), int(device), int(n_cta), int(threads))
         if rc:
@@ -106,7 +107,35 @@ class GcmEngine:
             raise _lib.AgcmError(_lib.E_BAD_MODE, "key of %d bytes" % n)
         self._ck(self._L.agcm_set_key(self._ctx, mode, int(bool(pre_expanded)), _addr(k), n))
         self.mode = mode
+        kb = (bool(pre_expanded), k.tobytes())
+        if kb != getattr(self, "_key_loaded", None):   # the library itself keeps H when the same key is loaded again
+            self._key_loaded = kb
+            self._j0_cache = {}
         return self
+
+    def derive_j0(self, iv):
+        """The pre-counter block J0 of an IV of any length (SP 800-38D 7.1), computed on the device;
+        96-bit IVs give IV || 00000001.  Cached per (key, IV)."""
+        ivb = bytes(_np_u8(iv).tobytes())
+        j0 = getattr(self, "_j0_cache", {}).get(ivb)
+        if j0 is None:
+            a = np.frombuffer(ivb, dtype=np.uint8)
+            out = np.zeros(16, dtype=np.uint8)
+            if a.size == 0:
+                raise _lib.AgcmError(_lib.E_BAD_LEN, "empty IV")
+            self._ck(self._L.agcm_derive_j0(self._ctx, _addr(a), a.size, _addr(out)))
+            j0 = out.tobytes()
+            if len(self._j0_cache) > 64:
+                self._j0_cache.clear()
+            self._j0_cache[ivb] = j0
+        return j0
+
+    def _iv_or_j0(self, iv):
+        """(array, is_j0): the 12 IV bytes for the plain entry points, else J0 for the *_j0 forms."""
+        ivb = _np_u8(iv)
+        if ivb.size == 12:
+            return ivb, False
+        return np.frombuffer(self.derive_j0(ivb), dtype=np.uint8), True
 
     def round_keys(self):
         out = np.zeros(240, dtype=np.uint8)
@@ -151,6 +180,26 @@ class GcmEngine:
                 raise AuthenticationError("MAC check failed")
             return pt
         return pt, ok
+
+    def decrypt_verified(self, iv, aad, ct, tag, out=None, raise_on_fail=True):
+        """Verify-then-release: GHASH + tag check first, GCTR only when the tag matches; on a
+        mismatch no plaintext byte is produced (`out` untouched).  -> pt, or (pt | None, ok)."""
+        ivb, a, d, tb = _np_u8(iv), _np_u8(aad), _np_u8(ct), _np_u8(tag)
+        if tb.size != 16:
+            raise _lib.AgcmError(_lib.E_BAD_LEN, "tag must be 16 bytes")
+        ret_bytes = out is None
+        o = np.zeros(d.size, dtype=np.uint8) if out is None else _np_u8(out)
+        if o.size < d.size:
+            raise _lib.AgcmError(_lib.E_BAD_LEN, "output buffer too small")
+        ok = ctypes.c_int(0)
+        self._ck(self._L.agcm_stream_decrypt_verified_host(self._ctx, _addr(ivb), ivb.size, _addr(a), a.size, _addr(d),
+                                                           _addr(o), d.size, _addr(tb), ctypes.byref(ok)))
+        if not ok.value:
+            if raise_on_fail:
+                raise AuthenticationError("MAC check failed")
+            return None, False
+        res = o[: d.size].tobytes() if ret_bytes else o[: d.size]
+        return res if raise_on_fail else (res, True)
 
     def _crypt_host(self, decrypt, iv, aad, data, tag, out):
         ivb = _np_u8(iv)   # 96 bits as in the reference IP (src/gcm_pkg.vhd:17), or any other length (SP 800-38D J0)
@@ -234,18 +283,27 @@ class GcmEngine:
                                               0 if aad is None else aad.numel(), _dptr(data_in), _dptr(data_out), n,
                                               _dptr(tag), _dptr(ok), _stream(stream)))
 
+    def stream_decrypt_verified_device(self, iv, aad, ct, pt, tag, ok, n_bytes=None, stream=None):
+        """Device form of decrypt_verified: `pt` is written only if `tag` matches (then ok[0] = 1)."""
+        ivb = _np_u8(iv)
+        n = ct.numel() if n_bytes is None else int(n_bytes)
+        self._ck(self._L.agcm_stream_decrypt_verified(self._ctx, _addr(ivb), ivb.size, _dptr(aad),
+                                                      0 if aad is None else aad.numel(), _dptr(ct), _dptr(pt), n, _dptr(tag),
+                                                      _dptr(ok), _stream(stream)))
+
     def stream_part_device(self, decrypt, iv, first_block, data_in, data_out, blocks_after, partial16, n_bytes=None,
                            stream=None):
-        ivb = _np_u8(iv)
+        ivb, j0 = self._iv_or_j0(iv)
         n = data_in.numel() if n_bytes is None else int(n_bytes)
-        self._ck(self._L.agcm_stream_part(self._ctx, int(decrypt), _addr(ivb), int(first_block), _dptr(data_in),
-                                          _dptr(data_out), n, int(blocks_after), _dptr(partial16), _stream(stream)))
+        fn = self._L.agcm_stream_part_j0 if j0 else self._L.agcm_stream_part
+        self._ck(fn(self._ctx, int(decrypt), _addr(ivb), int(first_block), _dptr(data_in), _dptr(data_out), n,
+                    int(blocks_after), _dptr(partial16), _stream(stream)))
 
     def stream_finish_device(self, decrypt, iv, partials16, n_parts, aad, ct_len, tag, ok=None, stream=None):
-        ivb = _np_u8(iv)
-        self._ck(self._L.agcm_stream_finish(self._ctx, int(decrypt), _addr(ivb), _dptr(partials16), int(n_parts),
-                                            _dptr(aad), 0 if aad is None else aad.numel(), int(ct_len), _dptr(tag),
-                                            _dptr(ok), _stream(stream)))
+        ivb, j0 = self._iv_or_j0(iv)
+        fn = self._L.agcm_stream_finish_j0 if j0 else self._L.agcm_stream_finish
+        self._ck(fn(self._ctx, int(decrypt), _addr(ivb), _dptr(partials16), int(n_parts), _dptr(aad),
+                    0 if aad is None else aad.numel(), int(ct_len), _dptr(tag), _dptr(ok), _stream(stream)))
 
     def peer_setup(self, rank, world, peer_ptrs):
         """peer_ptrs: device addresses (ints) of every rank's exchange buffer, mapped in this process."""
@@ -261,40 +319,53 @@ class GcmEngine:
                                  n_bytes=None, stream=None, defer=False):
         """One rank's shard + peer-memory exchange + tag finish (every rank calls it).  defer=True:
         do not make `stream` wait for the finish -- call peer_join() before reading tag / ok."""
-        ivb = _np_u8(iv)
+        ivb, j0 = self._iv_or_j0(iv)
         n = (0 if data_in is None else data_in.numel()) if n_bytes is None else int(n_bytes)
-        fn = self._L.agcm_stream_crypt_peer_async if defer else self._L.agcm_stream_crypt_peer
-        self._ck(fn(self._ctx, int(decrypt), _addr(ivb), int(first_block), _dptr(data_in), _dptr(data_out), n,
-                    int(blocks_after), _dptr(aad), 0 if aad is None else aad.numel(), int(total_len), _dptr(tag), _dptr(ok),
-                    _stream(stream)))
+        args = (self._ctx, int(decrypt), _addr(ivb), int(first_block), _dptr(data_in), _dptr(data_out), n, int(blocks_after),
+                _dptr(aad), 0 if aad is None else aad.numel(), int(total_len), _dptr(tag), _dptr(ok), _stream(stream))
+        if j0:
+            self._ck(self._L.agcm_stream_crypt_peer_j0(*args, int(bool(defer))))
+        else:
+            self._ck((self._L.agcm_stream_crypt_peer_async if defer else self._L.agcm_stream_crypt_peer)(*args))
 
     def peer_join(self, stream=None):
         """`stream` waits for every deferred peer finish issued so far (no host synchronisation)."""
         self._ck(self._L.agcm_peer_join(self._ctx, _stream(stream)))
 
     def gctr_device(self, iv, first_block, data_in, data_out, n_bytes=None, stream=None):
-        ivb = _np_u8(iv)
+        ivb, j0 = self._iv_or_j0(iv)
         n = data_in.numel() if n_bytes is None else int(n_bytes)
-        self._ck(self._L.agcm_gctr(self._ctx, _addr(ivb), int(first_block), _dptr(data_in), _dptr(data_out), n,
-                                   _stream(stream)))
+        fn = self._L.agcm_gctr_j0 if j0 else self._L.agcm_gctr
+        self._ck(fn(self._ctx, _addr(ivb), int(first_block), _dptr(data_in), _dptr(data_out), n, _stream(stream)))
 
     def ghash_device(self, data_in, y16, n_bytes=None, stream=None):
         n = data_in.numel() if n_bytes is None else int(n_bytes)
         self._ck(self._L.agcm_ghash(self._ctx, _dptr(data_in), n, _dptr(y16), _stream(stream)))
 
+    def batch_derive_j0_device(self, ivs, iv_off=None, iv_len=0, n_msgs=None, j0=None, stream=None):
+        """n IVs of any lengths (iv_off: CUDA int64 [n+1] byte offsets, or fixed iv_len) -> CUDA uint8 [n, 16] J0 blocks
+        for batch_crypt_device(..., j0=True)."""
+        import torch
+        n = (iv_off.numel() - 1) if iv_off is not None else (ivs.numel() // int(iv_len) if n_msgs is None else int(n_msgs))
+        if j0 is None:
+            j0 = torch.empty((n, 16), dtype=torch.uint8, device=ivs.device)
+        self._ck(self._L.agcm_batch_derive_j0(self._ctx, _dptr(ivs), _dptr(iv_off), int(iv_len), n, _dptr(j0), _stream(stream)))
+        return j0
+
     def batch_crypt_device(self, decrypt, ivs, aad, aad_off, data_in, in_off, data_out, tags, ok=None, lanes=0,
-                           avg_len_hint=0, stream=None):
+                           avg_len_hint=0, stream=None, j0=False):
+        """ivs: [n, 12] IVs, or (j0=True) the [n, 16] J0 blocks of batch_derive_j0_device."""
         n = in_off.numel() - 1
-        self._ck(self._L.agcm_batch_crypt(self._ctx, int(decrypt), int(lanes), int(avg_len_hint), _dptr(ivs), _dptr(aad),
-                                          _dptr(aad_off), _dptr(data_in), _dptr(in_off), _dptr(data_out), _dptr(tags),
-                                          _dptr(ok), n, _stream(stream)))
+        fn = self._L.agcm_batch_crypt_j0 if j0 else self._L.agcm_batch_crypt
+        self._ck(fn(self._ctx, int(decrypt), int(lanes), int(avg_len_hint), _dptr(ivs), _dptr(aad), _dptr(aad_off),
+                    _dptr(data_in), _dptr(in_off), _dptr(data_out), _dptr(tags), _dptr(ok), n, _stream(stream)))
 
     def batch_crypt_uniform_device(self, decrypt, ivs, aad, aad_len, aad_stride, data_in, data_out, length, stride, tags,
-                                   ok=None, n_msgs=None, lanes=0, stream=None):
-        n = ivs.numel() // 12 if n_msgs is None else int(n_msgs)
-        self._ck(self._L.agcm_batch_crypt_uniform(self._ctx, int(decrypt), int(lanes), _dptr(ivs), _dptr(aad),
-                                                  int(aad_len), int(aad_stride), _dptr(data_in), _dptr(data_out),
-                                                  int(length), int(stride), _dptr(tags), _dptr(ok), n, _stream(stream)))
+                                   ok=None, n_msgs=None, lanes=0, stream=None, j0=False):
+        n = ivs.numel() // (16 if j0 else 12) if n_msgs is None else int(n_msgs)
+        fn = self._L.agcm_batch_crypt_uniform_j0 if j0 else self._L.agcm_batch_crypt_uniform
+        self._ck(fn(self._ctx, int(decrypt), int(lanes), _dptr(ivs), _dptr(aad), int(aad_len), int(aad_stride), _dptr(data_in),
+                    _dptr(data_out), int(length), int(stride), _dptr(tags), _dptr(ok), n, _stream(stream)))
 
     def batch_crypt_perkey_device(self, mode, decrypt, keys, ivs, aad, aad_off, data_in, in_off, data_out, tags, ok=None,
                                   stream=None):

@@ -26,6 +26,24 @@ from .engine import GcmEngine
 
 _KS_WINDOW = 1 << 16  # bytes of keystream fetched per device call
 
+# One engine per device for all model instances (a testbench creates a model per packet; an engine
+# owns a context, its streams and ~200 MiB of staging buffers).  Callers that drive several models
+# concurrently pass their own `engine`.
+_engines = {}
+
+
+def shared_engine(device=0):
+    eng = _engines.get(device)
+    if eng is None:
+        eng = _engines[device] = GcmEngine(device)
+    return eng
+
+
+def close_shared_engines():
+    for eng in _engines.values():
+        eng.close()
+    _engines.clear()
+
 
 class gcm:
     def __init__(self, key, icb, ed, device=0, engine=None, prefetch=True):
@@ -36,11 +54,14 @@ class gcm:
 
         _key = int(key['data'], 16).to_bytes(key['n_bytes'], byteorder='big')
         _icb = int(icb['data'], 16).to_bytes(icb['n_bytes'], byteorder='big')
-        if len(_icb) != 12:
-            raise ValueError("the IV must be 96 bits (src/gcm_pkg.vhd:17)")
-        self._own_engine = engine is None
-        self.model = engine if engine is not None else GcmEngine(device)
-        self.model.set_key(_key)          # raw 16/24/32 B, or 176/208/240 B pre-expanded stages
+        if len(_icb) == 0:
+            raise ValueError("empty IV")
+        # The IP fixes the IV at 96 bits (src/gcm_pkg.vhd:17); pycryptodome's AES.new(nonce=...), which
+        # the reference model hands icb['n_bytes'] bytes to (tb/gcm_model.py:14-18), takes any length:
+        # so does the engine (J0 by GHASH on the device, SP 800-38D 7.1).
+        self.model = engine if engine is not None else shared_engine(device)
+        self._key = _key                  # raw 16/24/32 B, or 176/208/240 B pre-expanded stages
+        self.model.set_key(_key)
         self._iv = _icb
         self._aad = bytearray()
         self._text = bytearray()          # everything fed to load_plain_text / load_cipher_text
@@ -54,6 +75,11 @@ class gcm:
         self._prefetch = bool(prefetch)
 
     # ------------------------------------------------------------------
+    def _bind(self):
+        # the engine may be shared with other model instances: (re)load this model's key; loading the
+        # key that is already loaded returns at once (H is kept, src/gcm_ghash.vhd:123)
+        self.model.set_key(self._key)
+
     def _keystream(self, pos, n):
         """n bytes of keystream for message byte offset pos (device GCTR over zeros)."""
         out = bytearray()
@@ -66,6 +92,7 @@ class gcm:
                     self._zeros = torch.zeros(_KS_WINDOW, dtype=torch.uint8, device=dev)
                     self._ksbuf = torch.empty(_KS_WINDOW, dtype=torch.uint8, device=dev)
                 first_block = pos // 16
+                self._bind()
                 with torch.cuda.device(self.model.device):
                     self.model.gctr_device(self._iv, first_block, self._zeros, self._ksbuf)
                     self._ks = self._ksbuf.cpu().numpy().tobytes()
@@ -83,6 +110,7 @@ class gcm:
         lead = pos % 16                       # keep the counter block-aligned for a mid-block call
         buf = np.zeros(lead + len(data), dtype=np.uint8)
         buf[lead:] = np.frombuffer(data, dtype=np.uint8)
+        self._bind()
         with torch.cuda.device(self.model.device):
             d = torch.from_numpy(buf).cuda()
             o = torch.empty_like(d)
@@ -124,6 +152,7 @@ class gcm:
         'dec': the engine verifies `tag`; on success the received tag is appended, on failure
         its bitwise complement, so that the scoreboard is guaranteed to see a mismatch."""
         aad, text = bytes(self._aad), bytes(self._text)
+        self._bind()
         if self.ed == 'enc':
             out, computed = self.model.encrypt(self._iv, aad, text)
             authentic = True

@@ -21,14 +21,18 @@
  *     used from different threads at the same time.
  *   - Return 0 on success, a negative AGCM_E_* otherwise.  Nothing throws.
  *   - mode = key size in bits: 128 / 192 / 256 (src/aes_pkg.vhd:31-33 Nr=10/12/14).
- *   - IV is 96 bits as in the IP (the two *_iv entry points take any length); the counter
+ *   - IV is 96 bits as in the IP; IVs of any other length (pycryptodome's AES.new(nonce=...), which the
+ *     reference model calls at tb/gcm_model.py:18, accepts them) go through the *_iv entry points or,
+ *     for shards / batches / GCTR, through agcm_derive_j0 / agcm_batch_derive_j0 + the *_j0 forms; the counter
  *     block is IV || cnt32, cnt = 1 for J0 and 2.. for data (src/aes_icb.vhd:34,99-100,118).  More than 2^32-2 data
  *     blocks per IV is AGCM_E_COUNTER_OVERFLOW (the IP raises its overflow flag,
  *     src/aes_icb.vhd:65,114,119).
  *   - There is no CPU fallback.  Every call needs a CUDA device of compute
  *     capability 10.x.
  *   - Limits: payload per IV <= (2^32-2) x 16 bytes (the 32-bit block counter); a batched
- *     message holds fewer than 2^32 blocks of AAD + payload; agcm_stream_finish takes up to
+ *     message holds fewer than 2^32 blocks of AAD + payload + 1 (checked for the uniform forms; for the
+ *     offset forms the offsets live in device memory and the limit is the caller's to keep: UNCHECKED);
+ *     agcm_stream_finish takes up to
  *     1024 shard partials; agcm_peer_setup up to 16 ranks; the host-buffer stream call up to
  *     1024 x 64 MiB per call.  AAD of any length (bytes 4097.. run through the grid-wide GHASH).
  *   - Device buffers may have any byte alignment; 16-byte alignment selects the 128-bit
@@ -109,6 +113,18 @@ int agcm_get_h(const agcm_ctx* ctx, uint8_t h_h16[16]);
 int agcm_stream_crypt(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], const uint8_t* d_aad, uint64_t aad_len,
                       const uint8_t* d_in, uint8_t* d_out, uint64_t n_bytes, uint8_t* d_tag, uint8_t* d_ok, void* stream);
 
+/* RELEASE OF UNVERIFIED PLAINTEXT: like the reference model (tb/gcm_model.py:29-30 hands out every
+ * block at load_cipher_text time, the tag is only checked at get_tag), every decrypt call above and
+ * below writes the plaintext BEFORE the tag is known to match -- on the host-buffer paths each chunk
+ * is copied back while later chunks are still in flight.  Callers that must not see unauthenticated
+ * plaintext use the two-pass form:
+ * agcm_stream_decrypt_verified: pass 1 = GHASH over the ciphertext + tag check (about 4x the rate of
+ * the fused pass), pass 2 = GCTR gated ON THE DEVICE by the flag pass 1 wrote: when the tag does
+ * not match, *d_ok = 0 and d_pt is not written at all.  IV of any length (host pointer). */
+int agcm_stream_decrypt_verified(agcm_ctx* ctx, const uint8_t* h_iv, size_t iv_len, const uint8_t* d_aad, uint64_t aad_len,
+                                 const uint8_t* d_ct, uint8_t* d_pt, uint64_t n_bytes, const uint8_t* d_tag, uint8_t* d_ok,
+                                 void* stream);
+
 /* The same for an IV of ANY length (SP 800-38D 7.1: J0 = GHASH_H(IV || 0^(s+64) || [len(IV)]_64),
  * derived on the device; iv_len == 12 is the plain call above).  The reference IP fixes the IV at
  * 96 bits (src/gcm_pkg.vhd:17), so this goes beyond it; pycryptodome's AES.new(nonce=...), which
@@ -132,6 +148,24 @@ int agcm_stream_part(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], uint6
 int agcm_stream_finish(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], const uint8_t* d_partials16, int n_parts,
                        const uint8_t* d_aad, uint64_t aad_len, uint64_t ct_len, uint8_t* d_tag, uint8_t* d_ok,
                        void* stream);
+
+/* ---- IVs that are not 96 bits on the shard / peer / GCTR / batch entry points -----------------
+ * agcm_derive_j0: J0 = IV || 0^31 1 for a 96-bit IV, else GHASH_H(IV || 0^(s+64) || [len(IV)]_64)
+ * computed on the device (synchronous, host pointers).  The *_j0 forms take that 16-byte J0 in
+ * place of the 12 IV bytes: the counter block of data block i is inc32^(i+1)(J0), the tag mask
+ * E_K(J0).  For a 96-bit IV they are identical to the plain forms. */
+int agcm_derive_j0(agcm_ctx* ctx, const uint8_t* h_iv, size_t iv_len, uint8_t h_j0[16]);
+int agcm_gctr_j0(agcm_ctx* ctx, const uint8_t h_j0[16], uint64_t first_block, const uint8_t* d_in, uint8_t* d_out,
+                 uint64_t n_bytes, void* stream);
+int agcm_stream_part_j0(agcm_ctx* ctx, int decrypt, const uint8_t h_j0[16], uint64_t first_block, const uint8_t* d_in,
+                        uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, uint8_t* d_partial16, void* stream);
+int agcm_stream_finish_j0(agcm_ctx* ctx, int decrypt, const uint8_t h_j0[16], const uint8_t* d_partials16, int n_parts,
+                          const uint8_t* d_aad, uint64_t aad_len, uint64_t ct_len, uint8_t* d_tag, uint8_t* d_ok,
+                          void* stream);
+/* agcm_stream_crypt_peer (deferred == 0) / agcm_stream_crypt_peer_async (deferred != 0) with a J0 */
+int agcm_stream_crypt_peer_j0(agcm_ctx* ctx, int decrypt, const uint8_t h_j0[16], uint64_t first_block, const uint8_t* d_in,
+                              uint8_t* d_out, uint64_t n_bytes, uint64_t blocks_after, const uint8_t* d_aad, uint64_t aad_len,
+                              uint64_t total_len, uint8_t* d_tag, uint8_t* d_ok, void* stream, int deferred);
 
 /* ---- sharded message, partials exchanged over peer memory (NVLink) ---------------------------
  * agcm_peer_setup: h_peer_ptrs[w] = device address, valid in THIS process, of rank w's exchange
@@ -185,6 +219,18 @@ int agcm_batch_crypt_uniform(agcm_ctx* ctx, int decrypt, int lanes, const uint8_
                              uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out, uint64_t len,
                              uint64_t stride, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);
 
+/* Batches whose IVs are not all 96 bits: agcm_batch_derive_j0 turns n IVs (d_iv_off: n+1 byte
+ * offsets into d_iv, or NULL = fixed iv_len bytes each) into n 16-byte J0 blocks, one thread per IV;
+ * the *_j0 batch forms take d_j0 (n x 16) where the plain forms take d_iv12 (n x 12). */
+int agcm_batch_derive_j0(agcm_ctx* ctx, const uint8_t* d_iv, const uint64_t* d_iv_off, uint64_t iv_len, size_t n_msgs,
+                         uint8_t* d_j0, void* stream);
+int agcm_batch_crypt_j0(agcm_ctx* ctx, int decrypt, int lanes, uint64_t avg_len_hint, const uint8_t* d_j0,
+                        const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
+                        uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);
+int agcm_batch_crypt_uniform_j0(agcm_ctx* ctx, int decrypt, int lanes, const uint8_t* d_j0, const uint8_t* d_aad,
+                                uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out, uint64_t len,
+                                uint64_t stride, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);
+
 /* ---- many independent messages, one DISTINCT key per message ----------------------
  * BASELINE config 4.  d_keys holds n_msgs raw keys of mode/8 bytes; each thread runs
  * the aes_kexp schedule on the fly, one stage per round (config/config_aes_kexp.py:
@@ -211,6 +257,14 @@ int agcm_stream_crypt_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12],
 int agcm_stream_crypt_iv_host(agcm_ctx* ctx, int decrypt, const uint8_t* h_iv, size_t iv_len, const uint8_t* h_aad,
                               uint64_t aad_len, const uint8_t* h_in, uint8_t* h_out, uint64_t n_bytes,
                               uint8_t h_tag[16], int* h_ok);
+/* Verify-then-release decrypt from host buffers (see agcm_stream_decrypt_verified): the ciphertext is
+ * copied into HBM once (n_bytes of device memory, kept by the context) and absorbed chunk by chunk;
+ * only when the tag matches does the GCTR pass run and the plaintext travel back.  On a mismatch
+ * *h_ok = 0 and h_pt is untouched.  The default agcm_stream_crypt_host(decrypt = 1) streams instead:
+ * one pass, plaintext chunks written back before the tag is known. */
+int agcm_stream_decrypt_verified_host(agcm_ctx* ctx, const uint8_t* h_iv, size_t iv_len, const uint8_t* h_aad,
+                                      uint64_t aad_len, const uint8_t* h_ct, uint8_t* h_pt, uint64_t n_bytes,
+                                      const uint8_t h_tag[16], int* h_ok);
 /* Host-buffer forms of agcm_stream_part / agcm_stream_finish (one rank's shard of a
  * sharded message; the 16-byte partials travel between ranks). */
 int agcm_stream_part_host(agcm_ctx* ctx, int decrypt, const uint8_t h_iv12[12], uint64_t first_block, const uint8_t* h_in,

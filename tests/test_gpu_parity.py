@@ -212,6 +212,124 @@ def test_long_iv_paths_vs_oracle(engine, engine_small, oracle, torch_mod):
         assert eng.encrypt(iv12, aad, pt[:1000]) == oracle.gcm_crypt(key, iv12, aad, pt[:1000]), (it, "96-bit after")
 
 
+def test_long_iv_shard_gctr_peer_and_batch_paths(engine, oracle, torch_mod):
+    """SURVEY 8 f-4 remainder: IVs that are not 96 bits on the counter-range shard calls
+    (agcm_stream_part_j0 / _finish_j0), the GCTR half, the peer exchange (world = 1 on this GPU) and
+    the batch entry points (agcm_batch_derive_j0 + agcm_batch_crypt_j0), against the oracle."""
+    torch = torch_mod
+    from aesgcm_b200.parallel import shard_plan
+    rng = np.random.default_rng(97)
+    key = _rb(rng, 24)
+    engine.set_key(key)
+    for ivl, n, alen in ((8, 16 * 151552 * 2 + 5, 20), (33, 5000, 0), (1, 17, 7)):
+        iv, aad, pt = _rb(rng, ivl), _rb(rng, alen), rng.integers(0, 256, n, dtype=np.uint8)
+        want_ct, want_tag = oracle.gcm_crypt_any_iv(key, iv, aad, pt.tobytes())
+        d_in, d_aad = _dev(torch, pt), (_dev(torch, aad) if alen else None)
+        for world in (1, 3):
+            d_out = torch.zeros_like(d_in)
+            parts = torch.zeros((world, 16), dtype=torch.uint8, device="cuda")
+            for sh in shard_plan(n, world):
+                sl = slice(sh.byte_offset, sh.byte_offset + sh.n_bytes)
+                engine.stream_part_device(0, iv, sh.first_block, d_in[sl], d_out[sl], sh.blocks_after, parts[sh.rank],
+                                          n_bytes=sh.n_bytes)
+            d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+            engine.stream_finish_device(0, iv, parts, world, d_aad, n, d_tag)
+            torch.cuda.synchronize()
+            assert d_out.cpu().numpy().tobytes() == want_ct and d_tag.cpu().numpy().tobytes() == want_tag, (ivl, world)
+        d_back = torch.zeros_like(d_in)
+        engine.gctr_device(iv, 0, _dev(torch, np.frombuffer(want_ct, dtype=np.uint8)), d_back)
+        torch.cuda.synchronize()
+        assert d_back.cpu().numpy().tobytes() == pt.tobytes(), ("gctr", ivl)
+        buf = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+        engine.peer_setup(0, 1, [buf.data_ptr()])
+        d_out = torch.zeros_like(d_in)
+        d_tag = torch.zeros(16, dtype=torch.uint8, device="cuda")
+        engine.stream_crypt_peer_device(0, iv, 0, d_in, d_out, 0, d_aad, n, d_tag, defer=True)
+        engine.peer_join()
+        torch.cuda.synchronize()
+        assert d_out.cpu().numpy().tobytes() == want_ct and d_tag.cpu().numpy().tobytes() == want_tag, ("peer", ivl)
+    # batch: every message its own IV length (1 .. 40 bytes, some exactly 12)
+    n_msgs = 300
+    ivlens = rng.integers(1, 41, n_msgs)
+    ivlens[::7] = 12
+    lens = rng.integers(0, 900, n_msgs)
+    alens = rng.integers(0, 50, n_msgs)
+    iv_off = np.concatenate([[0], np.cumsum(ivlens)]).astype(np.int64)
+    in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.int64)
+    ivs = rng.integers(0, 256, int(iv_off[-1]), dtype=np.uint8)
+    data = rng.integers(0, 256, int(in_off[-1]), dtype=np.uint8)
+    aad = rng.integers(0, 256, int(aad_off[-1]), dtype=np.uint8)
+    want = [oracle.gcm_crypt_any_iv(key, ivs[iv_off[i]:iv_off[i + 1]].tobytes(), aad[aad_off[i]:aad_off[i + 1]].tobytes(),
+                                    data[in_off[i]:in_off[i + 1]].tobytes()) for i in range(n_msgs)]
+    d_j0 = engine.batch_derive_j0_device(_dev(torch, ivs), torch.from_numpy(iv_off).cuda())
+    for lanes in (0, 1, 4, 32, 1024):
+        d_out = torch.zeros(data.size, dtype=torch.uint8, device="cuda")
+        d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_device(0, d_j0, _dev(torch, aad), torch.from_numpy(aad_off).cuda(), _dev(torch, data),
+                                  torch.from_numpy(in_off).cuda(), d_out, d_tags, lanes=lanes, j0=True)
+        torch.cuda.synchronize()
+        out, tags = d_out.cpu().numpy(), d_tags.cpu().numpy()
+        for i in range(n_msgs):
+            assert out[in_off[i]:in_off[i + 1]].tobytes() == want[i][0], (lanes, i)
+            assert tags[16 * i:16 * i + 16].tobytes() == want[i][1], (lanes, i)
+    # uniform form with a fixed 16-byte IV
+    n_u, length = 64, 1500
+    ivs_u = rng.integers(0, 256, 16 * n_u, dtype=np.uint8)
+    data_u = rng.integers(0, 256, n_u * length, dtype=np.uint8)
+    d_j0 = engine.batch_derive_j0_device(_dev(torch, ivs_u), None, 16)
+    d_out = torch.zeros(n_u * length, dtype=torch.uint8, device="cuda")
+    d_tags = torch.zeros(16 * n_u, dtype=torch.uint8, device="cuda")
+    engine.batch_crypt_uniform_device(0, d_j0, None, 0, 0, _dev(torch, data_u), d_out, length, length, d_tags, n_msgs=n_u, j0=True)
+    torch.cuda.synchronize()
+    for i in (0, 17, n_u - 1):
+        w = oracle.gcm_crypt_any_iv(key, ivs_u[16 * i:16 * i + 16].tobytes(), b"", data_u[i * length:(i + 1) * length].tobytes())
+        assert d_out[i * length:(i + 1) * length].cpu().numpy().tobytes() == w[0]
+        assert d_tags[16 * i:16 * i + 16].cpu().numpy().tobytes() == w[1]
+
+
+def test_decrypt_verified_releases_nothing_on_a_bad_tag(engine, oracle, torch_mod):
+    """agcm_stream_decrypt_verified(_host): GHASH + tag check first, GCTR gated by the flag.  An
+    authentic message decrypts; with one flipped bit in the tag, the ciphertext or the AAD, ok = 0
+    and the output buffer keeps its previous contents (device and host forms, chunked sizes, long
+    AAD, a non-96-bit IV)."""
+    torch = torch_mod
+    rng = np.random.default_rng(98)
+    for kb, ivl, n, alen in ((32, 12, (40 << 20) + 13, 16), (16, 12, 100, 5000), (24, 20, 16 * 151552 + 1, 0), (16, 12, 0, 9)):
+        key, iv, aad, pt = _rb(rng, kb), _rb(rng, ivl), _rb(rng, alen), rng.integers(0, 256, n, dtype=np.uint8)
+        engine.set_key(key)
+        if n > (1 << 22):
+            AESGCM = pytest.importorskip("cryptography.hazmat.primitives.ciphers.aead").AESGCM
+            o = AESGCM(key).encrypt(iv, pt.tobytes(), aad)
+            ct, tag = o[:-16], o[-16:]
+        else:
+            ct, tag = oracle.gcm_crypt_any_iv(key, iv, aad, pt.tobytes())
+        # host form
+        assert engine.decrypt_verified(iv, aad, ct, tag) == pt.tobytes()
+        bad_tag = bytes([tag[0] ^ 0x80]) + tag[1:]
+        out = np.full(max(n, 1), 0x5A, dtype=np.uint8)
+        res, ok = engine.decrypt_verified(iv, aad, ct, bad_tag, out=out[:n], raise_on_fail=False)
+        assert ok is False and res is None and (out == 0x5A).all()
+        if n:
+            bad_ct = bytearray(ct)
+            bad_ct[n // 2] ^= 1
+            res, ok = engine.decrypt_verified(iv, aad, bytes(bad_ct), tag, out=out[:n], raise_on_fail=False)
+            assert ok is False and (out == 0x5A).all()
+        with pytest.raises(ValueError):
+            engine.decrypt_verified(iv, aad + b"x", ct, tag)
+        # device form
+        d_ct = _dev(torch, np.frombuffer(ct, dtype=np.uint8)) if n else torch.zeros(1, dtype=torch.uint8, device="cuda")
+        d_aad = _dev(torch, aad) if alen else None
+        d_pt = torch.full((max(n, 1),), 0x5A, dtype=torch.uint8, device="cuda")
+        d_ok = torch.zeros(1, dtype=torch.uint8, device="cuda")
+        engine.stream_decrypt_verified_device(iv, d_aad, d_ct, d_pt, _dev(torch, np.frombuffer(bad_tag, dtype=np.uint8)), d_ok, n_bytes=n)
+        torch.cuda.synchronize()
+        assert int(d_ok.item()) == 0 and bool((d_pt == 0x5A).all())
+        engine.stream_decrypt_verified_device(iv, d_aad, d_ct, d_pt, _dev(torch, np.frombuffer(tag, dtype=np.uint8)), d_ok, n_bytes=n)
+        torch.cuda.synchronize()
+        assert int(d_ok.item()) == 1 and d_pt[:n].cpu().numpy().tobytes() == pt.tobytes()
+
+
 @pytest.mark.parametrize("kb", [16, 24, 32])
 def test_stream_random_sizes_vs_oracle(engine, oracle, kb):
     """Default persistent grid (#SMs x 1024): empty, sub-block, ragged, one partial row, >1 row."""
@@ -1009,7 +1127,15 @@ def test_error_codes(engine_lib, torch_mod):
                                       buf.data_ptr(), 0, 2, 0) == E.E_BAD_LEN                                         # stride < len
     assert L.agcm_batch_crypt_perkey_uniform(ctx, 64, 0, buf.data_ptr(), buf.data_ptr(), 0, 0, 0, buf.data_ptr(),
                                              buf.data_ptr(), 16, 16, buf.data_ptr(), 0, 1, 0) == E.E_BAD_MODE
+    # AAD blocks + payload blocks + the length block must fit the 32-bit index of the unified sequence
+    big = 16 * (2 ** 31)
+    assert L.agcm_batch_crypt_uniform(ctx, 0, 0, buf.data_ptr(), buf.data_ptr(), big, big, buf.data_ptr(), buf.data_ptr(), big, big,
+                                      buf.data_ptr(), 0, 1, 0) == E.E_COUNTER_OVERFLOW
+    assert L.agcm_batch_crypt_perkey_uniform(ctx, 256, 0, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), big, big, buf.data_ptr(),
+                                             buf.data_ptr(), big, big, buf.data_ptr(), 0, 1, 0) == E.E_COUNTER_OVERFLOW
+    assert L.agcm_peer_join(ctx, 0) == E.E_BAD_ARG                                                                     # no peer_setup yet
     assert L.agcm_strerror(E.E_NO_KEY) == b"no key set"
+    assert b"peer" in L.agcm_strerror(E.E_PEER_TIMEOUT)
     torch.cuda.synchronize()
     L.agcm_ctx_destroy(ctx)
 
@@ -1042,6 +1168,32 @@ def test_gcm_model_adapter_streaming_callbacks(oracle, ed):
         wrong = bytes(16)
         m.get_tag(wrong)
         assert m.tag == [bytes([0xFF] * 16)]
+
+
+def test_gcm_model_adapter_long_iv_and_shared_engine(oracle):
+    """tb/gcm_model.py:14-18 passes icb['n_bytes'] bytes of nonce to pycryptodome, whatever the
+    length: the adapter takes them too (prefetched keystream from inc32(J0)).  Two models with
+    different keys interleave their callbacks on the module's shared engine."""
+    from aesgcm_b200 import gcm_model
+    rng = np.random.default_rng(56)
+    cases = []
+    for kb, ivl, n, alen in ((16, 8, 100, 20), (32, 64, 70000 + 3, 0)):
+        key, iv, aad, text = _rb(rng, kb), _rb(rng, ivl), _rb(rng, alen), _rb(rng, n)
+        want_ct, want_tag = oracle.gcm_crypt_any_iv(key, iv, aad, text)
+        m = gcm_model.gcm({'data': key.hex().upper(), 'n_bytes': kb}, {'data': iv.hex().upper(), 'n_bytes': ivl}, 'enc')
+        cases.append((m, aad, text, want_ct, want_tag))
+    assert cases[0][0].model is cases[1][0].model          # one engine for both
+    for m, aad, _, _, _ in cases:
+        for i in range(0, len(aad), 16):
+            m.load_aad(aad[i:i + 16])
+    for i in range(0, max(len(c[2]) for c in cases), 16):    # interleaved, block by block
+        for m, _, text, want_ct, _ in cases:
+            if i < len(text):
+                m.load_plain_text(text[i:i + 16])
+                assert m.data_out[-1] == want_ct[i:i + 16]
+    for m, _, _, want_ct, want_tag in cases:
+        m.get_tag(want_tag)
+        assert b"".join(m.data_out) == want_ct and m.tag == [want_tag]
 
 
 def test_adapter_reproduces_reference_model_traces():
