@@ -2,6 +2,7 @@
 // checks, kernel parameter blocks, scratch buffers, and the chunked
 // host<->device pipeline.  All arithmetic happens in kernels.cu; there is no
 // CPU implementation of the datapath in this library.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -87,6 +88,8 @@ struct agcm_ctx {
     uint8_t* d_chunk_partials = nullptr;
     uint8_t* d_aad_stage = nullptr;
     size_t aad_stage_cap = 0;
+    uint32_t* d_tile_ticket = nullptr;   // k_batch_tile: next group of 32 messages (zeroed before each launch)
+    void* tmap_encode = nullptr;         // cuTensorMapEncodeTiled, resolved through the runtime (no link-time libcuda)
     uint8_t* d_verify = nullptr;     // whole ciphertext of a verify-then-release host decrypt, grown on demand
     size_t verify_cap = 0;
     bool pipeline_ready = false;
@@ -524,6 +527,7 @@ void agcm_ctx_destroy(agcm_ctx* c)
     cudaFree(c->d_chunk_partials);
     cudaFree(c->d_aad_stage);
     cudaFree(c->d_verify);
+    cudaFree(c->d_tile_ticket);
     cudaFree(c->d_te0);
     cudaFree(c->d_key);
     cudaFree(c->d_parts);
@@ -1044,6 +1048,72 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
     return AGCM_OK;
 }
 
+// ---- fixed-size records through the TMA-staged kernel (k_batch_tile) -----------------------------
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int tile_tensor_map(agcm_ctx* c, CUtensorMap* tm, const uint8_t* base, uint64_t len, uint64_t stride, uint64_t n_msgs)
+{
+    if (!c->tmap_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+            q != cudaDriverEntryPointSuccess)
+            return AGCM_E_CUDA;
+        c->tmap_encode = fn;
+    }
+    // the batch as a 2-D byte tensor: dim 0 = the bytes of a record (extent len), dim 1 = the messages (pitch = stride)
+    const cuuint64_t dims[2] = {len, n_msgs};
+    const cuuint64_t strides[1] = {stride};
+    const cuuint32_t box[2] = {AG_TILE_BOX_BYTES, AG_TILE_BOX_MSGS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = reinterpret_cast<tmap_encode_fn>(c->tmap_encode)(
+        tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? AGCM_OK : AGCM_E_CUDA;
+}
+
+// Can (and should) this uniform batch take the tiled kernel?  16-byte aligned buffers and pitch (TMA),
+// messages short enough that a message per lane is the right compute layout, and enough of them to
+// fill the persistent grid a few times over.
+static bool tile_eligible(const agcm_ctx* c, int lanes, const BatchParams& p, size_t n_msgs)
+{
+    if (lanes != 0 && lanes != 2048) return false;
+    if (p.len == 0 || p.len >= (1ull << 31) || n_msgs >= (1ull << 31) - 32) return false;
+    if ((((uintptr_t)p.in | (uintptr_t)p.out) & 15) || (p.stride & 15) || p.stride >= (1ull << 40)) return false;
+    if (lanes == 2048) return true;
+    if (getenv("AGCM_NO_TILE")) return false;
+    return p.len <= 16384 && n_msgs >= (size_t)c->ncta * (size_t)c->nt * 2;
+}
+
+static int batch_tile(agcm_ctx* c, int decrypt, BatchParams& p, size_t n_msgs, cudaStream_t st)
+{
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (!p.iv || !p.tag || (decrypt && !p.ok)) return AGCM_E_BAD_ARG;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
+    TileParams t;
+    memset(&t, 0, sizeof(t));
+    memcpy(p.rk, c->h_rk, sizeof(p.rk));
+    p.key = c->d_key;
+    p.te0 = c->d_te0;
+    p.n_msgs = n_msgs;
+    t.b = p;
+    int rc = tile_tensor_map(c, &t.tm_in, p.in, p.len, p.stride, n_msgs);
+    if (rc) return rc;
+    rc = tile_tensor_map(c, &t.tm_out, p.out, p.len, p.stride, n_msgs);
+    if (rc) return rc;
+    t.ticket = c->d_tile_ticket;
+    AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), st));
+    const uint64_t groups = (n_msgs + 31) / 32, per_cta = (uint64_t)AG_STREAM_NT_MAX / 32;
+    const uint64_t need = (groups + per_cta - 1) / per_cta;
+    const int ncta = (int)(need < (uint64_t)c->ncta ? need : (uint64_t)c->ncta);
+    AG_CUDA(c, ag_launch_batch_tile(t, c->nr, decrypt, ncta, st));
+    c->launches++;
+    return AGCM_OK;
+}
+
 static int batch_offsets(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len_hint, const uint8_t* d_iv, int iv_is_j0,
                          const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
                          uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream)
@@ -1089,6 +1159,8 @@ static int batch_uniform(agcm_ctx* c, int decrypt, int lanes, const uint8_t* d_i
     p.aad_len = aad_len;
     p.aad_stride = aad_stride;
     const bool aligned16 = ((((uintptr_t)d_in | (uintptr_t)d_out) | stride) & 15) == 0;
+    if (lanes == 2048 && !tile_eligible(c, lanes, p, n_msgs)) return AGCM_E_BAD_ARG;
+    if (n_msgs && tile_eligible(c, lanes, p, n_msgs)) return batch_tile(c, decrypt, p, n_msgs, (cudaStream_t)stream);
     // work estimate for the layout choice: an AAD block costs about a quarter of a payload block (no AES)
     return batch_common(c, decrypt, lanes, len + (d_aad ? aad_len / 4 : 0), p, n_msgs, stream, aligned16);
 }

@@ -24,6 +24,7 @@
 #include "gcm_core.cuh"
 #include "perkey_core.cuh"
 #include "kernels.h"
+#include "tma_util.cuh"
 
 namespace {
 
@@ -641,6 +642,156 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
 }
 
 // ===========================================================================
+// Batched FIXED-SIZE records under the shared key, one lane per message, records staged through
+// shared memory by TMA (BASELINE config 3: 2^20 x 1500 B at a 1504 B stride).
+//
+// Why: with a message per lane the compute layout is the cheapest there is (no lane combine, no
+// front padding, the Horner constant is H itself), but every 128-bit global load/store of a warp
+// touches 32 different lines -- ncu: ~48 of ~277 L1/shared data-pipe wavefronts per 32 blocks
+// (profiles/r1_ncu_batch.md), on the pipe that binds the kernel.  Here the batch is a 2-D tensor
+// [message][byte] (row pitch = the record stride); one elected lane per warp asks the TMA unit for
+// the box {32 bytes x 32 messages}: two blocks of each of the warp's 32 messages land as a dense,
+// 32B-swizzled 1 KB tile (conflict-free LDS.128/STS.128: 4 + 4 wavefronts per 32 blocks), the lanes
+// XOR the keystream in place, and the same box goes back with a TMA store.  The async proxy moves
+// the bytes; the LSU pipe only sees the tile accesses.  Out-of-range bytes of the box (past the
+// record length, past the last message) arrive as zeros and are clipped on the way out, which is
+// exactly the zero padding GHASH wants for a ragged last block (src/gcm_ghash.vhd:228-246).
+// Two tiles per warp (load of tile t+1 in flight while tile t is processed); groups of 32
+// messages are handed out by an atomic ticket, so no warp idles while another still has a queue.
+// ===========================================================================
+namespace {
+constexpr uint32_t SM_TILE_BAR = SM_MISC + 1024;          // 16 warps x 2 mbarriers
+constexpr uint32_t SM_TILE = SM_MISC + 2048;              // 16 warps x 2 tiles x 1 KB
+constexpr uint32_t TILE_BYTES = 1024;                     // 32 messages x 32 bytes
+constexpr size_t kTileSmemBytes = SM_TILE + (AG_STREAM_NT_MAX / 32) * 2 * TILE_BYTES;
+}  // namespace
+
+template <int NR, bool DEC>
+__global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid_constant__ TileParams P)
+{
+    const BatchParams& p = P.b;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    stage_te0(p.te0);
+    fill_gh_tables(p.key->tab[0], nullptr);   // Horner constant H (a message per lane)
+    const uint32_t bar0 = ag_smem_addr(ag_smem + SM_TILE_BAR + warp * 16), bar1 = bar0 + 8;
+    if (lane == 0) {
+        ag_mbar_init(bar0, 1);
+        ag_mbar_init(bar1, 1);
+        ag_fence_barrier_init();
+        ag_prefetch_tmap(&P.tm_in);
+        ag_prefetch_tmap(&P.tm_out);
+    }
+    __syncthreads();
+    expand_aes_tables();
+    __syncthreads();
+
+    TeSmem te{ag_smem, lane * 4};
+    GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
+    uint8_t* tiles = ag_smem + SM_TILE + warp * (2 * TILE_BYTES);
+    const uint32_t tile_sa = ag_smem_addr(tiles);
+    // this lane's two 16-byte chunks inside a tile (CU_TENSOR_MAP_SWIZZLE_32B: address bit 4 ^= bit 7)
+    const uint32_t sw = (lane >> 2) & 1;
+    const uint32_t coff0 = lane * 32 + ((0 ^ sw) << 4), coff1 = lane * 32 + ((1 ^ sw) << 4);
+    uint32_t par0 = 0, par1 = 0;
+
+    const uint32_t n_blocks = (uint32_t)((p.len + 15) >> 4), tail = (uint32_t)(p.len & 15);
+    const uint32_t n_tiles = (n_blocks + 1) >> 1;
+    const uint32_t a_blocks = (uint32_t)((p.aad_len + 15) >> 4), atail = (uint32_t)(p.aad_len & 15);
+    const uint32_t n_groups = (uint32_t)((p.n_msgs + 31) >> 5);
+    for (;;) {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(P.ticket, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= n_groups) break;
+        const int32_t row0 = (int32_t)(g * 32);
+        if (lane == 0 && n_tiles) {
+            ag_mbar_expect_tx(bar0, TILE_BYTES);
+            ag_tma_load_2d(tile_sa, &P.tm_in, 0, row0, bar0);
+        }
+        const uint64_t m_raw = (uint64_t)g * 32 + lane;
+        const bool valid = m_raw < p.n_msgs;
+        const uint64_t m = valid ? m_raw : p.n_msgs - 1;   // idle lanes of the last group shadow a real message
+        uint32_t ivw[3], j0ctr;
+        ag_batch_iv(p, m, ivw, &j0ctr);
+        const AesCtrConst cc = aes_ctr_precompute(p.rk, ivw[0], ivw[1], ivw[2], te);
+        AesCtrSeqCache cache;
+        cache.key = 0xFFFFFFFFu;
+        gf128 y = gf_zero();
+        // AAD first (gcm_ghash.vhd:259-272 order): short per-message headers, read in place
+        if (a_blocks) {
+            const uint8_t* ap = p.aad + m * p.aad_stride;
+            for (uint32_t i = 0; i < a_blocks; ++i) {
+                uint32_t x[4];
+                ag_load_block(ap + 16 * (uint64_t)i, (i == a_blocks - 1 && atail) ? atail : 16u, x);
+                y.w[0] ^= ag_bswap32(x[0]); y.w[1] ^= ag_bswap32(x[1]); y.w[2] ^= ag_bswap32(x[2]); y.w[3] ^= ag_bswap32(x[3]);
+                y = gf_mul_table(y, gh);
+            }
+        }
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            const uint32_t b = t & 1;
+            if (lane == 0 && t + 1 < n_tiles) {
+                ag_bulk_wait_read0();   // the store of tile t-1 has read the buffer tile t+1 lands in
+                ag_mbar_expect_tx(b ? bar0 : bar1, TILE_BYTES);
+                ag_tma_load_2d(tile_sa + (b ^ 1) * TILE_BYTES, &P.tm_in, (int32_t)((t + 1) * 32), row0, b ? bar0 : bar1);
+            }
+            if (b) { ag_mbar_wait(bar1, par1); par1 ^= 1; } else { ag_mbar_wait(bar0, par0); par0 ^= 1; }
+            uint8_t* tb = tiles + b * TILE_BYTES;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t j = 2 * t + k;
+                if (j < n_blocks) {   // uniform
+                    uint4* cp = reinterpret_cast<uint4*>(tb + (k ? coff1 : coff0));
+                    const uint4 xv = *cp;
+                    uint32_t ks[4];
+                    aes_ctr_block_seq<NR>(p.rk, cc, cache, j0ctr + 1u + j, te, ks);
+                    uint32_t o[4] = {xv.x ^ ks[0], xv.y ^ ks[1], xv.z ^ ks[2], xv.w ^ ks[3]};
+                    *cp = make_uint4(o[0], o[1], o[2], o[3]);   // bytes past the record length are clipped by the TMA store
+                    uint32_t s[4];
+                    if (DEC) {
+                        s[0] = xv.x; s[1] = xv.y; s[2] = xv.z; s[3] = xv.w;   // zero-filled past the record length
+                    } else {
+                        if (j == n_blocks - 1 && tail) ag_mask_block(o, tail);
+                        s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+                    }
+                    y.w[0] ^= ag_bswap32(s[0]); y.w[1] ^= ag_bswap32(s[1]); y.w[2] ^= ag_bswap32(s[2]); y.w[3] ^= ag_bswap32(s[3]);
+                    y = gf_mul_table(y, gh);
+                }
+            }
+            ag_fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                ag_tma_store_2d(&P.tm_out, (int32_t)(t * 32), row0, tile_sa + b * TILE_BYTES);
+                ag_bulk_commit();
+            }
+        }
+        // length block (gcm_ghash.vhd:257), last multiply, E_K(J0) (gcm_ghash.vhd:293)
+        {
+            const uint64_t ab = p.aad_len * 8, cb = p.len * 8;
+            y.w[0] ^= (uint32_t)(ab >> 32); y.w[1] ^= (uint32_t)ab; y.w[2] ^= (uint32_t)(cb >> 32); y.w[3] ^= (uint32_t)cb;
+            y = gf_mul_table(y, gh);
+            uint32_t e[4];
+            aes_ctr_block_seq<NR>(p.rk, cc, cache, j0ctr, te, e);
+            const uint32_t tg[4] = {ag_bswap32(y.w[0]) ^ e[0], ag_bswap32(y.w[1]) ^ e[1], ag_bswap32(y.w[2]) ^ e[2],
+                                    ag_bswap32(y.w[3]) ^ e[3]};
+            if (valid) {
+                uint8_t* tp = p.tag + 16 * m;
+                if (DEC) {
+                    uint32_t x[4];
+                    ag_load_block(tp, 16, x);
+                    const uint32_t diff = (x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3]);
+                    p.ok[m] = diff ? 0 : 1;
+                } else {
+                    ag_store_block(tp, 16, tg);
+                }
+            }
+        }
+        if (lane == 0) ag_bulk_wait_read0();   // both tiles are free again for the next group
+        __syncwarp();
+    }
+    if (lane == 0) ag_bulk_wait0();
+}
+
+// ===========================================================================
 // Batched LONG messages under the shared key: one CTA per message (G = blockDim.x
 // lanes).  Same front-padded strided Horner as k_batch, constant H^NT (tab[6]); lane
 // weights H^(NT-tid) by one bit-serial product per lane per message, then a CTA
@@ -1005,6 +1156,25 @@ static cudaError_t launch_batch_cta_t(const BatchParams& p, int ncta, int nt, cu
     if (e != cudaSuccess || p.split <= 1) return e;
     k_batch_split_finish<DEC><<<(unsigned)((p.n_msgs + 127) / 128), 128, 0, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int NR, bool DEC>
+static cudaError_t launch_batch_tile_t(const TileParams& p, int ncta, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_batch_tile<NR, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+    if (e != cudaSuccess) return e;
+    k_batch_tile<NR, DEC><<<ncta, AG_STREAM_NT_MAX, kTileSmemBytes, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_batch_tile(const TileParams& p, int nr, int decrypt, int ncta, cudaStream_t st)
+{
+    switch (nr) {
+        case 10: return decrypt ? launch_batch_tile_t<10, true>(p, ncta, st) : launch_batch_tile_t<10, false>(p, ncta, st);
+        case 12: return decrypt ? launch_batch_tile_t<12, true>(p, ncta, st) : launch_batch_tile_t<12, false>(p, ncta, st);
+        case 14: return decrypt ? launch_batch_tile_t<14, true>(p, ncta, st) : launch_batch_tile_t<14, false>(p, ncta, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t ag_launch_batch_cta(const BatchParams& p, int nr, int decrypt, int ncta, int nt, cudaStream_t st)

@@ -1,5 +1,6 @@
 // Internal launcher interface between kernels.cu and capi.cu (not installed).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "gcm_core.cuh"
@@ -35,6 +36,14 @@ struct PeerFinishParams {
 
 cudaError_t ag_launch_stream(const StreamParams& p, int nr, int mode, int ncta, int nt, cudaStream_t st);
 cudaError_t ag_launch_batch(const BatchParams& p, int nr, int decrypt, int g, int ncta, int nt, cudaStream_t st);
+// k_batch_tile: fixed-size records as a 2-D tensor [message][byte], staged by TMA
+struct TileParams {
+    BatchParams b;
+    CUtensorMap tm_in, tm_out;   // box {32 bytes, 32 messages}, CU_TENSOR_MAP_SWIZZLE_32B
+    uint32_t* ticket;            // zero at launch: next group of 32 messages
+};
+constexpr uint32_t AG_TILE_BOX_BYTES = 32, AG_TILE_BOX_MSGS = 32;
+cudaError_t ag_launch_batch_tile(const TileParams& p, int nr, int decrypt, int ncta, cudaStream_t st);
 cudaError_t ag_launch_batch_cta(const BatchParams& p, int nr, int decrypt, int ncta, int nt, cudaStream_t st);
 cudaError_t ag_launch_batch_perkey(const BatchParams& p, int nr, int decrypt, int max_cta, cudaStream_t st);
 cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_bytes, const uint32_t* te0,

@@ -634,6 +634,72 @@ def test_batch_split_over_ranks_single_gpu(engine, oracle, torch_mod):
         assert (gk_ct == wk_ct).all() and (gk_tags == wk_tags).all(), world
 
 
+def test_batch_tile_tma_staged_records(engine, oracle, torch_mod):
+    """k_batch_tile (lanes = 2048): fixed-size records staged through shared memory by 2-D TMA,
+    a message per lane.  Record lengths around the 16- and 32-byte tile edges (the out-of-range
+    bytes of a box must read as zeros and must not be written back), pitch > length with the
+    padding left untouched, message counts that are not a multiple of the 32-message group, AAD,
+    every key size, in place, decrypt with corrupted tags, and a non-96-bit IV batch (J0 form)."""
+    torch = torch_mod
+    rng = np.random.default_rng(123)
+    cases = [(16, 1500, 1504, 0, 1000), (24, 1500, 1504, 0, 4097), (32, 1500, 1520, 64, 333), (16, 16, 16, 0, 70),
+             (24, 5, 16, 20, 65), (32, 33, 48, 0, 31), (16, 4096, 4096, 16, 129), (32, 31, 32, 7, 200), (24, 64, 64, 0, 32)]
+    for kb, length, stride, alen, n_msgs in cases:
+        key = _rb(rng, kb)
+        engine.set_key(key)
+        ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+        buf = rng.integers(0, 256, n_msgs * stride, dtype=np.uint8)
+        aad = rng.integers(0, 256, max(1, n_msgs * alen), dtype=np.uint8)
+        packed = buf.reshape(n_msgs, stride)[:, :length].reshape(-1).copy()
+        in_off = np.arange(n_msgs + 1, dtype=np.uint64) * length
+        aad_off = np.arange(n_msgs + 1, dtype=np.uint64) * alen
+        want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), kb, True, ivs, aad if alen else None,
+                                              aad_off if alen else None, packed, in_off, threads=8)
+        d_buf = _dev(torch, buf)
+        d_aad = _dev(torch, aad) if alen else None
+        d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_uniform_device(0, _dev(torch, ivs), d_aad, alen, alen, d_buf, d_buf, length, stride, d_tags,
+                                          n_msgs=n_msgs, lanes=2048)   # in place
+        torch.cuda.synchronize()
+        got = d_buf.cpu().numpy().reshape(n_msgs, stride)
+        assert (got[:, :length].reshape(-1) == want_ct).all(), (kb, length, stride)
+        assert (got[:, length:] == buf.reshape(n_msgs, stride)[:, length:]).all(), "padding between records was written"
+        assert (d_tags.cpu().numpy() == want_tags).all(), (kb, length, stride)
+        # decrypt into a second buffer, 1 tag in 16 corrupted
+        tags = want_tags.copy()
+        bad = np.arange(0, n_msgs, 16)
+        tags[16 * bad + 3] ^= 0x20
+        d_pt = torch.full((n_msgs * stride,), 0xEE, dtype=torch.uint8, device="cuda")
+        d_ok = torch.full((n_msgs,), 7, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_uniform_device(1, _dev(torch, ivs), d_aad, alen, alen, d_buf, d_pt, length, stride, _dev(torch, tags),
+                                          d_ok, n_msgs=n_msgs, lanes=2048)
+        torch.cuda.synchronize()
+        back = d_pt.cpu().numpy().reshape(n_msgs, stride)
+        assert (back[:, :length] == buf.reshape(n_msgs, stride)[:, :length]).all()
+        assert (back[:, length:] == 0xEE).all()
+        ok = d_ok.cpu().numpy()
+        assert (ok[bad] == 0).all() and int(ok.sum()) == n_msgs - bad.size
+    # J0 form: 16-byte IVs
+    key = _rb(rng, 16)
+    engine.set_key(key)
+    n_msgs, length = 100, 200
+    ivs16 = rng.integers(0, 256, 16 * n_msgs, dtype=np.uint8)
+    data = rng.integers(0, 256, n_msgs * 208, dtype=np.uint8)
+    d_j0 = engine.batch_derive_j0_device(_dev(torch, ivs16), None, 16)
+    d_out = torch.zeros(n_msgs * 208, dtype=torch.uint8, device="cuda")
+    d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+    engine.batch_crypt_uniform_device(0, d_j0, None, 0, 0, _dev(torch, data), d_out, length, 208, d_tags, n_msgs=n_msgs, lanes=2048,
+                                      j0=True)
+    torch.cuda.synchronize()
+    for i in (0, 50, 99):
+        w = oracle.gcm_crypt_any_iv(key, ivs16[16 * i:16 * i + 16].tobytes(), b"", data[i * 208:i * 208 + length].tobytes())
+        assert d_out[i * 208:i * 208 + length].cpu().numpy().tobytes() == w[0]
+        assert d_tags[16 * i:16 * i + 16].cpu().numpy().tobytes() == w[1]
+    # an unaligned pitch cannot take this kernel
+    with pytest.raises(Exception):
+        engine.batch_crypt_uniform_device(0, d_j0, None, 0, 0, _dev(torch, data), d_out, 200, 204, d_tags, n_msgs=10, lanes=2048)
+
+
 def test_batch_host_api_roundtrip(engine, oracle):
     rng = np.random.default_rng(9)
     key = _rb(rng, 32)
