@@ -1100,9 +1100,11 @@ static int batch_tile(agcm_ctx* c, int decrypt, BatchParams& p, size_t n_msgs, c
     p.te0 = c->d_te0;
     p.n_msgs = n_msgs;
     t.b = p;
-    int rc = tile_tensor_map(c, &t.tm_in, p.in, p.len, p.stride, n_msgs);
+    // 16-byte-granular extents (the pitch is a multiple of 16 and >= len, so both fit inside a record's pitch)
+    const uint64_t len_up = (p.len + 15) & ~15ull, len_down = p.len & ~15ull;
+    int rc = tile_tensor_map(c, &t.tm_in, p.in, len_up, p.stride, n_msgs);
     if (rc) return rc;
-    rc = tile_tensor_map(c, &t.tm_out, p.out, p.len, p.stride, n_msgs);
+    rc = tile_tensor_map(c, &t.tm_out, p.out, len_down ? len_down : 16, p.stride, n_msgs);   // len < 16: never stored through
     if (rc) return rc;
     t.ticket = c->d_tile_ticket;
     AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), st));
@@ -1268,6 +1270,36 @@ int agcm_batch_crypt_perkey_uniform(agcm_ctx* c, int mode, int decrypt, const ui
     p.stride = stride;
     p.aad_len = aad_len;
     p.aad_stride = aad_stride;
+    // fixed-size, 16-byte aligned records: stage them by TMA (k_batch_perkey_tile) when there are
+    // enough messages to fill the grid; AGCM_PERKEY_TILE=0 keeps the thread-per-message loads (A/B runs)
+    {
+        const char* ev = getenv("AGCM_PERKEY_TILE");
+        const bool force = ev && ev[0] == '1', off = ev && ev[0] == '0';
+        const bool fits = len && len < (1ull << 31) && n_msgs < (1ull << 31) - 32 && !(((uintptr_t)d_in | (uintptr_t)d_out) & 15) &&
+                          !(stride & 15) && stride < (1ull << 40);
+        if (fits && !off && (force || n_msgs >= (size_t)c->ncta * 448u * 2)) {
+            const int nr = mode_to_nr(mode);
+            if (!nr) return AGCM_E_BAD_MODE;
+            if (!p.keys || !p.iv || !p.tag || (decrypt && !p.ok)) return AGCM_E_BAD_ARG;
+            AG_CUDA(c, cudaSetDevice(c->device));
+            if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
+            TileParams t;
+            memset(&t, 0, sizeof(t));
+            p.te0 = c->d_te0;
+            p.n_msgs = n_msgs;
+            t.b = p;
+            const uint64_t len_up = (len + 15) & ~15ull, len_down = len & ~15ull;
+            int rc = tile_tensor_map(c, &t.tm_in, d_in, len_up, stride, n_msgs);
+            if (rc) return rc;
+            rc = tile_tensor_map(c, &t.tm_out, d_out, len_down ? len_down : 16, stride, n_msgs);
+            if (rc) return rc;
+            t.ticket = c->d_tile_ticket;
+            AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
+            AG_CUDA(c, ag_launch_batch_perkey_tile(t, nr, decrypt, c->ncta, (cudaStream_t)stream));
+            c->launches++;
+            return AGCM_OK;
+        }
+    }
     return perkey_common(c, mode, decrypt, p, n_msgs, stream);
 }
 

@@ -93,6 +93,22 @@ AG_HD void ag_store_block(uint8_t* p, uint32_t nvalid, const uint32_t x[4])
         }
 #endif
     }
+#if defined(__CUDA_ARCH__)
+    if (((uintptr_t)p & 3) == 0) {   // ragged tail at a word-aligned address: whole words first, then the odd bytes
+        uint32_t* q = reinterpret_cast<uint32_t*>(p);
+#pragma unroll
+        for (uint32_t w = 0; w < 4; ++w) {
+            if (nvalid >= 4 * w + 4) {
+                q[w] = x[w];
+            } else {
+#pragma unroll
+                for (uint32_t j = 4 * w; j < 4 * w + 3; ++j)
+                    if (j < nvalid) p[j] = (uint8_t)(x[w] >> (8 * (j & 3)));
+            }
+        }
+        return;
+    }
+#endif
 #pragma unroll
     for (uint32_t j = 0; j < 16; ++j)
         if (j < nvalid) p[j] = (uint8_t)(x[j >> 2] >> (8 * (j & 3)));

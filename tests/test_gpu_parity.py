@@ -700,6 +700,53 @@ def test_batch_tile_tma_staged_records(engine, oracle, torch_mod):
         engine.batch_crypt_uniform_device(0, d_j0, None, 0, 0, _dev(torch, data), d_out, 200, 204, d_tags, n_msgs=10, lanes=2048)
 
 
+def test_perkey_tile_tma_staged_records(engine, oracle, torch_mod, monkeypatch):
+    """k_batch_perkey_tile (distinct key per message, fixed-size records staged by TMA), forced on
+    small batches: every key size, ragged record lengths, AAD, message counts off the 32-message
+    group, decrypt with corrupted tags, output padding untouched; and the same inputs through the
+    thread-per-message kernel give the same bytes."""
+    torch = torch_mod
+    rng = np.random.default_rng(124)
+    for kb, length, stride, alen, n_msgs in ((32, 1500, 1504, 64, 1000), (16, 1500, 1504, 0, 67), (24, 40, 48, 20, 33),
+                                             (32, 16, 16, 0, 64), (16, 7, 16, 5, 50), (32, 4096, 4096, 64, 40)):
+        keys = rng.integers(0, 256, kb * n_msgs, dtype=np.uint8)
+        ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+        buf = rng.integers(0, 256, n_msgs * stride, dtype=np.uint8)
+        aad = rng.integers(0, 256, max(1, n_msgs * alen), dtype=np.uint8)
+        packed = buf.reshape(n_msgs, stride)[:, :length].reshape(-1).copy()
+        in_off = np.arange(n_msgs + 1, dtype=np.uint64) * length
+        aad_off = np.arange(n_msgs + 1, dtype=np.uint64) * alen
+        want_ct, want_tags = oracle.gcm_batch(keys, kb, False, ivs, aad if alen else None, aad_off if alen else None, packed,
+                                              in_off, threads=8)
+        d_keys, d_ivs, d_in = _dev(torch, keys), _dev(torch, ivs), _dev(torch, buf)
+        d_aad = _dev(torch, aad) if alen else None
+        outs = {}
+        for tile in ("1", "0"):
+            monkeypatch.setenv("AGCM_PERKEY_TILE", tile)
+            d_out = torch.full((n_msgs * stride,), 0xEE, dtype=torch.uint8, device="cuda")
+            d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+            engine.batch_crypt_perkey_uniform_device(8 * kb, 0, d_keys, d_ivs, d_aad, alen, alen, d_in, d_out, length, stride,
+                                                     d_tags, n_msgs=n_msgs)
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy().reshape(n_msgs, stride)
+            assert (got[:, :length].reshape(-1) == want_ct).all(), (tile, kb, length)
+            assert (got[:, length:] == 0xEE).all(), (tile, "padding written")
+            assert (d_tags.cpu().numpy() == want_tags).all(), (tile, kb, length)
+            outs[tile] = d_out
+        monkeypatch.setenv("AGCM_PERKEY_TILE", "1")
+        tags = want_tags.copy()
+        bad = np.arange(1, n_msgs, 9)
+        tags[16 * bad] ^= 1
+        d_back = torch.zeros(n_msgs * stride, dtype=torch.uint8, device="cuda")
+        d_ok = torch.full((n_msgs,), 9, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_perkey_uniform_device(8 * kb, 1, d_keys, d_ivs, d_aad, alen, alen, outs["1"], d_back, length, stride,
+                                                 _dev(torch, tags), d_ok, n_msgs=n_msgs)
+        torch.cuda.synchronize()
+        assert (d_back.cpu().numpy().reshape(n_msgs, stride)[:, :length] == buf.reshape(n_msgs, stride)[:, :length]).all()
+        ok = d_ok.cpu().numpy()
+        assert (ok[bad] == 0).all() and int(ok.sum()) == n_msgs - bad.size
+
+
 def test_batch_host_api_roundtrip(engine, oracle):
     rng = np.random.default_rng(9)
     key = _rb(rng, 32)

@@ -23,7 +23,9 @@ for s in $STEPS; do
       timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2>&1; echo "benchref rc=$?"; cat $OUT/${TAG}_bench_ref.json ;;
     tile)
       timeout 600 python -m pytest tests -m gpu -q -x --timeout 600 -k "tile or config3" > $OUT/${TAG}_tile.log 2>&1; echo "tile rc=$?"; tail -15 $OUT/${TAG}_tile.log
-      timeout 600 python tools/bench_variants.py --only packets > $OUT/${TAG}_packets.log 2>&1; echo "packets rc=$?"; cat $OUT/${TAG}_packets.log ;;
+      timeout 600 python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_packets.log 2>&1; echo "packets rc=$?"; cat $OUT/${TAG}_packets.log
+      timeout 600 python tools/bench_variants.py --only perkey > $OUT/${TAG}_perkey.log 2>&1; echo "perkey rc=$?"; cat $OUT/${TAG}_perkey.log
+      AGCM_PERKEY_TILE=0 timeout 600 python tools/bench_variants.py --only perkey > $OUT/${TAG}_perkey_notile.log 2>&1; echo "perkey (no tile) rc=$?"; cat $OUT/${TAG}_perkey_notile.log ;;
     variants)
       timeout 900 python tools/bench_variants.py > $OUT/${TAG}_variants.log 2>&1; echo "variants rc=$?"; cat $OUT/${TAG}_variants.log ;;
     launches)
