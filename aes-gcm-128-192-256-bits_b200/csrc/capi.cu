@@ -1035,6 +1035,11 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
             p.seg_parts = c->d_seg_parts;
         }
         const int ncta_m = (int)(n_units < (uint64_t)c->ncta ? n_units : (uint64_t)c->ncta);
+        if (n_units > (uint64_t)ncta_m && n_units < 0xFFFFFFFFull) {   // more units than CTAs: hand them out dynamically
+            if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
+            AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
+            p.ticket = c->d_tile_ticket;
+        }
         AG_CUDA(c, ag_launch_batch_cta(p, c->nr, decrypt, ncta_m, c->nt, (cudaStream_t)stream));
         c->launches += p.split > 1 ? 2 : 1;
         return AGCM_OK;
@@ -1084,7 +1089,7 @@ static bool tile_eligible(const agcm_ctx* c, int lanes, const BatchParams& p, si
     if ((((uintptr_t)p.in | (uintptr_t)p.out) & 15) || (p.stride & 15) || p.stride >= (1ull << 40)) return false;
     if (lanes == 2048) return true;
     if (getenv("AGCM_NO_TILE")) return false;
-    return p.len <= 16384 && n_msgs >= (size_t)c->ncta * (size_t)c->nt * 2;
+    return p.len + p.aad_len <= 16384 && n_msgs >= (size_t)c->ncta * (size_t)c->nt * 2;
 }
 
 static int batch_tile(agcm_ctx* c, int decrypt, BatchParams& p, size_t n_msgs, cudaStream_t st)
@@ -1106,6 +1111,12 @@ static int batch_tile(agcm_ctx* c, int decrypt, BatchParams& p, size_t n_msgs, c
     if (rc) return rc;
     rc = tile_tensor_map(c, &t.tm_out, p.out, len_down ? len_down : 16, p.stride, n_msgs);   // len < 16: never stored through
     if (rc) return rc;
+    if (p.aad && p.aad_len && !((uintptr_t)p.aad & 15) && !(p.aad_stride & 15) && p.aad_len < (1ull << 31) &&
+        p.aad_stride < (1ull << 40)) {
+        rc = tile_tensor_map(c, &t.tm_aad, p.aad, (p.aad_len + 15) & ~15ull, p.aad_stride, n_msgs);
+        if (rc) return rc;
+        t.aad_tiled = 1;
+    }
     t.ticket = c->d_tile_ticket;
     AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), st));
     const uint64_t groups = (n_msgs + 31) / 32, per_cta = (uint64_t)AG_STREAM_NT_MAX / 32;

@@ -277,6 +277,9 @@ struct BatchParams {
     // (1 = whole messages); seg_parts holds n_msgs x split scaled partials then n_msgs x E_K(J0)
     uint32_t split;
     uint32_t* seg_parts;
+    // k_batch_cta: units (messages or segments) are handed out by this counter (zero at launch);
+    // null = static round-robin over the CTAs
+    uint32_t* ticket;
 };
 
 // One message, or one counter-range segment of it (ag_batch_segment).
@@ -379,7 +382,26 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
     bool have = t >= pad;
     uint32_t nxt[4] = {0, 0, 0, 0};
     if (rows && have && i < a) ag_load_block(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt);
-    for (uint32_t u = 0; u < rows; ++u) {
+    // Rows 0 .. aad_rows-1 hold AAD blocks only (row u spans blocks uG-pad .. uG+G-1-pad): they run in
+    // a loop of their own -- prefetch, one table product, one XOR, like k_stream<GHASH_ONLY> -- so
+    // that bulk AAD is not dragged through the AES-sized body of the general loop below.
+    const uint32_t aad_rows = (uint32_t)(((uint64_t)a + pad) / G);
+    uint32_t u = 0;
+    for (; u < aad_rows; ++u) {
+        const bool hv = have;
+        const uint32_t s0 = nxt[0], s1 = nxt[1], s2 = nxt[2], s3 = nxt[3];
+        i += G;
+        have = true;
+        if (u + 1 < rows && i < a) ag_load_block(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt);
+        if (u) y = gf_mul_table(y, gh_g);
+        if (hv) {
+            y.w[0] ^= ag_bswap32(s0);
+            y.w[1] ^= ag_bswap32(s1);
+            y.w[2] ^= ag_bswap32(s2);
+            y.w[3] ^= ag_bswap32(s3);
+        }
+    }
+    for (; u < rows; ++u) {
         const uint32_t ic = i;
         const bool hv = have;
         uint32_t s[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};

@@ -682,6 +682,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
         ag_fence_barrier_init();
         ag_prefetch_tmap(&P.tm_in);
         ag_prefetch_tmap(&P.tm_out);
+        if (P.aad_tiled) ag_prefetch_tmap(&P.tm_aad);
     }
     __syncthreads();
     expand_aes_tables();
@@ -699,6 +700,9 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
     const uint32_t n_blocks = (uint32_t)((p.len + 15) >> 4), tail = (uint32_t)(p.len & 15), n_full = (uint32_t)(p.len >> 4);
     const uint32_t n_tiles = (n_blocks + 1) >> 1;
     const uint32_t a_blocks = (uint32_t)((p.aad_len + 15) >> 4), atail = (uint32_t)(p.aad_len & 15);
+    // the unified sequence AAD | CT (gcm_ghash.vhd:259-272) as ONE stream of tiles through the two buffers
+    const uint32_t a_tiles = P.aad_tiled ? (a_blocks + 1) >> 1 : 0;
+    const uint32_t tot_tiles = a_tiles + n_tiles;
     const uint32_t n_groups = (uint32_t)((p.n_msgs + 31) >> 5);
     for (;;) {
         uint32_t g = 0;
@@ -706,10 +710,13 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= n_groups) break;
         const int32_t row0 = (int32_t)(g * 32);
-        if (lane == 0 && n_tiles) {
-            ag_mbar_expect_tx(bar0, TILE_BYTES);
-            ag_tma_load_2d(tile_sa, &P.tm_in, 0, row0, bar0);
-        }
+        auto issue = [&](uint32_t T, uint32_t buf) {   // lane 0 only
+            const uint32_t bar = buf ? bar1 : bar0;
+            ag_mbar_expect_tx(bar, TILE_BYTES);
+            if (T < a_tiles) ag_tma_load_2d(tile_sa + buf * TILE_BYTES, &P.tm_aad, (int32_t)(T * 32), row0, bar);
+            else ag_tma_load_2d(tile_sa + buf * TILE_BYTES, &P.tm_in, (int32_t)((T - a_tiles) * 32), row0, bar);
+        };
+        if (lane == 0 && tot_tiles) issue(0, 0);
         const uint64_t m_raw = (uint64_t)g * 32 + lane;
         const bool valid = m_raw < p.n_msgs;
         const uint64_t m = valid ? m_raw : p.n_msgs - 1;   // idle lanes of the last group shadow a real message
@@ -719,8 +726,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
         AesCtrSeqCache cache;
         cache.key = 0xFFFFFFFFu;
         gf128 y = gf_zero();
-        // AAD first (gcm_ghash.vhd:259-272 order): short per-message headers, read in place
-        if (a_blocks) {
+        if (a_blocks && !P.aad_tiled) {   // AAD the TMA cannot address (alignment): read in place
             const uint8_t* ap = p.aad + m * p.aad_stride;
             for (uint32_t i = 0; i < a_blocks; ++i) {
                 uint32_t x[4];
@@ -729,15 +735,30 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
                 y = gf_mul_table(y, gh);
             }
         }
-        for (uint32_t t = 0; t < n_tiles; ++t) {
-            const uint32_t b = t & 1;
-            if (lane == 0 && t + 1 < n_tiles) {
-                ag_bulk_wait_read0();   // the store of tile t-1 has read the buffer tile t+1 lands in
-                ag_mbar_expect_tx(b ? bar0 : bar1, TILE_BYTES);
-                ag_tma_load_2d(tile_sa + (b ^ 1) * TILE_BYTES, &P.tm_in, (int32_t)((t + 1) * 32), row0, b ? bar0 : bar1);
+        for (uint32_t T = 0; T < tot_tiles; ++T) {
+            const uint32_t b = T & 1;
+            if (lane == 0 && T + 1 < tot_tiles) {
+                ag_bulk_wait_read0();   // the store of tile T-1 has read the buffer tile T+1 lands in
+                issue(T + 1, b ^ 1);
             }
             if (b) { ag_mbar_wait(bar1, par1); par1 ^= 1; } else { ag_mbar_wait(bar0, par0); par0 ^= 1; }
             uint8_t* tb = tiles + b * TILE_BYTES;
+            if (T < a_tiles) {   // uniform: an AAD tile is absorbed, nothing goes back
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint32_t j = 2 * T + k;
+                    if (j < a_blocks) {
+                        const uint4 xv = *reinterpret_cast<const uint4*>(tb + (k ? coff1 : coff0));
+                        uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
+                        if (j == a_blocks - 1 && atail) ag_mask_block(x, atail);
+                        y.w[0] ^= ag_bswap32(x[0]); y.w[1] ^= ag_bswap32(x[1]); y.w[2] ^= ag_bswap32(x[2]); y.w[3] ^= ag_bswap32(x[3]);
+                        y = gf_mul_table(y, gh);
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
+            const uint32_t t = T - a_tiles;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const uint32_t j = 2 * t + k;
@@ -837,7 +858,19 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
     // S partials and E_K(J0) go to seg_parts, and k_batch_split_finish XORs them into the tag.
     const uint32_t S = p.split;
     const uint64_t n_units = p.n_msgs * S;
-    for (uint64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+    // units go to whichever CTA is free next (atomic ticket): with static round-robin every CTA
+    // waits for the one that drew the most (or the longest) units
+    uint32_t* s_unit = reinterpret_cast<uint32_t*>(ag_smem + SM_MISC + 1824);
+    for (uint64_t it = 0;; ++it) {
+        uint64_t u;
+        if (p.ticket) {
+            if (tid == 0) *s_unit = atomicAdd(p.ticket, 1u);
+            __syncthreads();
+            u = *s_unit;
+        } else {
+            u = blockIdx.x + it * gridDim.x;
+        }
+        if (u >= n_units) break;
         const uint64_t m = u / S;
         const uint32_t seg = (uint32_t)(u - m * S);
         uint64_t after = 0;

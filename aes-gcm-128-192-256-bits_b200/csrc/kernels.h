@@ -40,6 +40,8 @@ cudaError_t ag_launch_batch(const BatchParams& p, int nr, int decrypt, int g, in
 struct TileParams {
     BatchParams b;
     CUtensorMap tm_in, tm_out;   // box {32 bytes, 32 messages}, CU_TENSOR_MAP_SWIZZLE_32B
+    CUtensorMap tm_aad;          // the AAD records as a tensor of their own (k_batch_tile, when aad_tiled)
+    uint32_t aad_tiled;
     uint32_t* ticket;            // zero at launch: next group of 32 messages
 };
 constexpr uint32_t AG_TILE_BOX_BYTES = 32, AG_TILE_BOX_MSGS = 32;

@@ -642,23 +642,27 @@ def test_batch_tile_tma_staged_records(engine, oracle, torch_mod):
     every key size, in place, decrypt with corrupted tags, and a non-96-bit IV batch (J0 form)."""
     torch = torch_mod
     rng = np.random.default_rng(123)
-    cases = [(16, 1500, 1504, 0, 1000), (24, 1500, 1504, 0, 4097), (32, 1500, 1520, 64, 333), (16, 16, 16, 0, 70),
-             (24, 5, 16, 20, 65), (32, 33, 48, 0, 31), (16, 4096, 4096, 16, 129), (32, 31, 32, 7, 200), (24, 64, 64, 0, 32)]
-    for kb, length, stride, alen, n_msgs in cases:
+    # (key bytes, record length, record pitch, AAD length, AAD pitch, messages); an AAD pitch that is a multiple
+    # of 16 sends the AAD through TMA tiles as well, any other pitch reads it in place
+    cases = [(16, 1500, 1504, 0, 0, 1000), (24, 1500, 1504, 0, 0, 4097), (32, 1500, 1520, 64, 64, 333), (16, 16, 16, 0, 0, 70),
+             (24, 5, 16, 20, 20, 65), (32, 33, 48, 0, 0, 31), (16, 4096, 4096, 16, 16, 129), (32, 31, 32, 7, 7, 200),
+             (24, 64, 64, 0, 0, 32), (16, 100, 112, 20, 32, 77), (32, 48, 48, 1000, 1008, 45), (24, 16, 16, 33, 48, 64)]
+    for kb, length, stride, alen, astride, n_msgs in cases:
         key = _rb(rng, kb)
         engine.set_key(key)
         ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
         buf = rng.integers(0, 256, n_msgs * stride, dtype=np.uint8)
-        aad = rng.integers(0, 256, max(1, n_msgs * alen), dtype=np.uint8)
+        aad_buf = rng.integers(0, 256, max(1, n_msgs * astride), dtype=np.uint8)
+        aad = aad_buf[:n_msgs * astride].reshape(n_msgs, max(astride, 1))[:, :alen].reshape(-1).copy() if alen else aad_buf
         packed = buf.reshape(n_msgs, stride)[:, :length].reshape(-1).copy()
         in_off = np.arange(n_msgs + 1, dtype=np.uint64) * length
         aad_off = np.arange(n_msgs + 1, dtype=np.uint64) * alen
         want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), kb, True, ivs, aad if alen else None,
                                               aad_off if alen else None, packed, in_off, threads=8)
         d_buf = _dev(torch, buf)
-        d_aad = _dev(torch, aad) if alen else None
+        d_aad = _dev(torch, aad_buf) if alen else None
         d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
-        engine.batch_crypt_uniform_device(0, _dev(torch, ivs), d_aad, alen, alen, d_buf, d_buf, length, stride, d_tags,
+        engine.batch_crypt_uniform_device(0, _dev(torch, ivs), d_aad, alen, astride, d_buf, d_buf, length, stride, d_tags,
                                           n_msgs=n_msgs, lanes=2048)   # in place
         torch.cuda.synchronize()
         got = d_buf.cpu().numpy().reshape(n_msgs, stride)
@@ -671,7 +675,7 @@ def test_batch_tile_tma_staged_records(engine, oracle, torch_mod):
         tags[16 * bad + 3] ^= 0x20
         d_pt = torch.full((n_msgs * stride,), 0xEE, dtype=torch.uint8, device="cuda")
         d_ok = torch.full((n_msgs,), 7, dtype=torch.uint8, device="cuda")
-        engine.batch_crypt_uniform_device(1, _dev(torch, ivs), d_aad, alen, alen, d_buf, d_pt, length, stride, _dev(torch, tags),
+        engine.batch_crypt_uniform_device(1, _dev(torch, ivs), d_aad, alen, astride, d_buf, d_pt, length, stride, _dev(torch, tags),
                                           d_ok, n_msgs=n_msgs, lanes=2048)
         torch.cuda.synchronize()
         back = d_pt.cpu().numpy().reshape(n_msgs, stride)

@@ -26,6 +26,11 @@ for s in $STEPS; do
       timeout 600 python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_packets.log 2>&1; echo "packets rc=$?"; cat $OUT/${TAG}_packets.log
       timeout 600 python tools/bench_variants.py --only perkey > $OUT/${TAG}_perkey.log 2>&1; echo "perkey rc=$?"; cat $OUT/${TAG}_perkey.log
       AGCM_PERKEY_TILE=0 timeout 600 python tools/bench_variants.py --only perkey > $OUT/${TAG}_perkey_notile.log 2>&1; echo "perkey (no tile) rc=$?"; cat $OUT/${TAG}_perkey_notile.log ;;
+    perkey)
+      timeout 600 python tools/bench_variants.py --only perkey > $OUT/${TAG}_perkey.log 2>&1; echo "perkey rc=$?"; cat $OUT/${TAG}_perkey.log
+      AGCM_PERKEY_TILE=0 timeout 600 python tools/bench_variants.py --only perkey > $OUT/${TAG}_perkey_notile.log 2>&1; echo "perkey (no tile) rc=$?"; cat $OUT/${TAG}_perkey_notile.log ;;
+    sweep5)
+      timeout 1500 python tools/sweep_config5.py --out $OUT/${TAG}_config5.json > $OUT/${TAG}_config5.log 2>&1; echo "sweep5 rc=$?"; tail -75 $OUT/${TAG}_config5.log ;;
     variants)
       timeout 900 python tools/bench_variants.py > $OUT/${TAG}_variants.log 2>&1; echo "variants rc=$?"; cat $OUT/${TAG}_variants.log ;;
     launches)
