@@ -366,6 +366,7 @@ int ensure_pipeline(agcm_ctx* c)
 int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, bool aligned16 = true)
 {
     if (lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32) return lanes;
+    if (lanes > 4096 && lanes <= 4096 + 65536) return lanes;  // one warp per 1/S of a message (k_batch_warp), S = lanes - 4096
     if (lanes == 1024) return 1024;  // one CTA per message
     if (lanes > 1024 && lanes <= 1024 + 256 && ((lanes - 1024) & (lanes - 1025)) == 0) return lanes;  // ... per 1/S of a message
     if (lanes != 0) return -1;
@@ -377,6 +378,17 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, 
     // persistent grid is occupied, but never more lanes than blocks in a message.
     const uint64_t total_lanes = (uint64_t)c->ncta * c->nt;
     const uint64_t blocks = (avg_len + 15) / 16 + 1;
+    // From 32 KiB of work per message: one WARP per unit (k_batch_warp), units handed out by ticket,
+    // lane combine deferred to a second launch.  A unit is a message or one of S counter-range
+    // segments of it; S keeps a unit near 64-256 rows of 32 blocks and gives every warp at least ~8
+    // units to draw, so neither the per-unit overhead (a row or two) nor the tail matters.
+    if (blocks >= 2048 && !getenv("AGCM_NO_WARP_UNITS")) {
+        const uint64_t warps = total_lanes / 32;
+        uint64_t S = 1;
+        while (blocks / S > 8192 && S < 65536) S <<= 1;
+        while (n_msgs * S < 8 * warps && blocks / S >= 4096 && S < 65536) S <<= 1;
+        return (int)(4096 + S);
+    }
     uint64_t g = 1;
     while (g < 32 && (8 * g) * (8 * g) <= 2 * blocks) g <<= 1;
     if (blocks >= 4096) g = 32;
@@ -1020,6 +1032,30 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
     p.key = c->d_key;
     p.te0 = c->d_te0;
     p.n_msgs = n_msgs;
+    if (g > 4096) {
+        p.split = (uint32_t)(g - 4096);
+        const uint64_t n_units = (uint64_t)n_msgs * p.split;
+        if (n_units >= 0xFFFFFFFFull) return AGCM_E_BAD_LEN;
+        const size_t parts_bytes = ((size_t)(n_units + n_msgs) * 16 + 255) & ~(size_t)255;
+        const size_t need = parts_bytes + (size_t)n_units * 512;
+        if (need > c->seg_parts_bytes) {
+            AG_CUDA(c, cudaFree(c->d_seg_parts));
+            c->d_seg_parts = nullptr;
+            c->seg_parts_bytes = 0;
+            AG_CUDA(c, cudaMalloc(&c->d_seg_parts, need));
+            c->seg_parts_bytes = need;
+        }
+        p.seg_parts = c->d_seg_parts;
+        p.seg_acc = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(c->d_seg_parts) + parts_bytes);
+        if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
+        AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
+        p.ticket = c->d_tile_ticket;
+        const uint64_t per_cta = (uint64_t)AG_STREAM_NT_MAX / 32, need_cta = (n_units + per_cta - 1) / per_cta;
+        const int ncta_w = (int)(need_cta < (uint64_t)c->ncta ? need_cta : (uint64_t)c->ncta);
+        AG_CUDA(c, ag_launch_batch_warp(p, c->nr, decrypt, ncta_w, (cudaStream_t)stream));
+        c->launches += 3;
+        return AGCM_OK;
+    }
     if (g >= 1024) {
         p.split = g == 1024 ? 1u : (uint32_t)(g - 1024);
         const uint64_t n_units = (uint64_t)n_msgs * p.split;
@@ -1620,6 +1656,7 @@ int agcm_batch_crypt_uniform_host(agcm_ctx* c, int decrypt, int lanes, const uin
     if (g < 0) return AGCM_E_BAD_ARG;
     // the chunks run concurrently on the pipeline's streams and the segment layout keeps its
     // partials in one scratch buffer per context: whole-message layouts only on this path
+    if (g > 4096) g = 32;     // (the warp-unit layout as well)
     if (g > 1024) g = 1024;
     uint64_t k = 0;
     for (uint64_t m0 = 0; m0 < n_msgs; m0 += m_chunk, ++k) {

@@ -280,6 +280,8 @@ struct BatchParams {
     // k_batch_cta: units (messages or segments) are handed out by this counter (zero at launch);
     // null = static round-robin over the CTAs
     uint32_t* ticket;
+    // k_batch_warp: raw lane accumulators, n_msgs x split units x 32 lanes x 16 B (BE words)
+    uint4* seg_acc;
 };
 
 // One message, or one counter-range segment of it (ag_batch_segment).

@@ -940,6 +940,98 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
     }
 }
 
+// ===========================================================================
+// Batched MID-SIZE and LONG messages under the shared key: one WARP per unit, where a unit is a
+// whole message or one of `split` counter-range segments of it (ag_batch_segment, the single-GPU
+// form of the shards of parallel.py).  Units are handed out warp by warp through an atomic ticket,
+// so the grid stays busy to the last unit whatever the number or the sizes of the messages; and
+// the per-unit epilogue is deferred: a warp just DUMPS its 32 raw lane accumulators (512 B,
+// coalesced).  The lane weights H^(32-t) -- one ~1100-instruction generic product per lane and
+// unit when done in place, which is what made fine segments unaffordable for k_batch /
+// k_batch_cta -- are applied by k_batch_warp_reduce with one LANE per unit: a 32-step Horner with
+// the H table, 32 units side by side per warp.  Linearity of GHASH in its input, as in
+// src/gcm_ghash.vhd:317-344.  Table: T_a = H^32.
+// ===========================================================================
+template <int NR, bool DEC>
+__global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid_constant__ BatchParams p)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    stage_te0(p.te0);
+    fill_gh_tables(p.key->tab[5], nullptr);
+    __syncthreads();
+    expand_aes_tables();
+    __syncthreads();
+    TeSmem te{ag_smem, lane * 4};
+    GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
+    const uint32_t S = p.split;
+    const uint64_t n_units = p.n_msgs * S;
+    for (;;) {
+        uint32_t tk = 0;
+        if (lane == 0) tk = atomicAdd(p.ticket, 1u);
+        const uint64_t u = __shfl_sync(0xffffffffu, tk, 0);
+        if (u >= n_units) break;
+        const uint64_t m = u / S;
+        const uint32_t seg = (uint32_t)(u - m * S);
+        uint64_t after = 0;
+        MsgDesc d = ag_batch_msg(p, m);
+        if (S > 1) d = ag_batch_segment(d, seg, S, &after);
+        uint32_t ivw[3];
+        ag_batch_iv(p, m, ivw, &d.j0ctr);
+        const AesCtrConst cc = aes_ctr_precompute(p.rk, ivw[0], ivw[1], ivw[2], te);
+        AesCtrSeqCache cache;
+        cache.key = 0xFFFFFFFFu;
+        uint32_t e[4] = {0, 0, 0, 0};
+        const gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, lane, 32u, te, gh, e);
+        p.seg_acc[u * 32 + lane] = make_uint4(y.w[0], y.w[1], y.w[2], y.w[3]);
+        if (d.last && lane == 31) {   // the lane that met the length block also produced E_K(J0)
+            uint32_t* de = p.seg_parts + 4 * (n_units + m);
+            de[0] = e[0]; de[1] = e[1]; de[2] = e[2]; de[3] = e[3];
+        }
+        __syncwarp();
+    }
+}
+
+// One lane per unit: R = sum_t Y_t H^(32-t) by a serial Horner over the dumped accumulators with
+// the H table, then the scaling by H^(blocks after the unit) (product of the H^(2^k) of the set
+// bits); the scaled partial goes where k_batch_split_finish expects it.
+__global__ void __launch_bounds__(128) k_batch_warp_reduce(const __grid_constant__ BatchParams p)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    fill_gh_tables(p.key->tab[0], nullptr);
+    __syncthreads();
+    GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
+    const uint32_t S = p.split;
+    const uint64_t n_units = p.n_msgs * S;
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + tid;
+    if (u >= n_units) return;
+    gf128 r = gf_zero();
+    const uint4* acc = p.seg_acc + u * 32;
+#pragma unroll 1
+    for (int t = 0; t < 32; ++t) {
+        const uint4 q = __ldcg(acc + t);
+        r.w[0] ^= q.x; r.w[1] ^= q.y; r.w[2] ^= q.z; r.w[3] ^= q.w;
+        r = gf_mul_table(r, gh);
+    }
+    if (S > 1) {
+        const uint64_t m = u / S;
+        uint64_t after = 0;
+        (void)ag_batch_segment(ag_batch_msg(p, m), (uint32_t)(u - m * S), S, &after);
+        if (after) {
+            gf128 f = gf_one();
+            bool first = true;
+#pragma unroll 1
+            for (int k = 0; k < 40; ++k)
+                if ((after >> k) & 1) {
+                    f = first ? p.key->pow2[k] : gf_mul(f, p.key->pow2[k]);
+                    first = false;
+                }
+            r = gf_mul(r, f);
+        }
+    }
+    uint32_t* dst = p.seg_parts + 4 * u;
+    dst[0] = r.w[0]; dst[1] = r.w[1]; dst[2] = r.w[2]; dst[3] = r.w[3];
+}
+
 // Tag finish of the split layout: one thread per message XORs its S scaled partials
 // (linearity of GHASH in its input, the same algebra as gcm_ghash.vhd:330-332) and E_K(J0).
 template <bool DEC>
@@ -1402,6 +1494,33 @@ cudaError_t ag_launch_batch_tile(const TileParams& p, int nr, int decrypt, int n
         case 10: return decrypt ? launch_batch_tile_t<10, true>(p, ncta, st) : launch_batch_tile_t<10, false>(p, ncta, st);
         case 12: return decrypt ? launch_batch_tile_t<12, true>(p, ncta, st) : launch_batch_tile_t<12, false>(p, ncta, st);
         case 14: return decrypt ? launch_batch_tile_t<14, true>(p, ncta, st) : launch_batch_tile_t<14, false>(p, ncta, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int NR, bool DEC>
+static cudaError_t launch_batch_warp_t(const BatchParams& p, int ncta, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_batch_warp<NR, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_batch_warp_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    k_batch_warp<NR, DEC><<<ncta, AG_STREAM_NT_MAX, kSmemBytes, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const uint64_t n_units = p.n_msgs * p.split;
+    k_batch_warp_reduce<<<(unsigned)((n_units + 127) / 128), 128, kSmemBytes, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_batch_split_finish<DEC><<<(unsigned)((p.n_msgs + 127) / 128), 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t ag_launch_batch_warp(const BatchParams& p, int nr, int decrypt, int ncta, cudaStream_t st)
+{
+    switch (nr) {
+        case 10: return decrypt ? launch_batch_warp_t<10, true>(p, ncta, st) : launch_batch_warp_t<10, false>(p, ncta, st);
+        case 12: return decrypt ? launch_batch_warp_t<12, true>(p, ncta, st) : launch_batch_warp_t<12, false>(p, ncta, st);
+        case 14: return decrypt ? launch_batch_warp_t<14, true>(p, ncta, st) : launch_batch_warp_t<14, false>(p, ncta, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -47,6 +47,8 @@ struct TileParams {
 constexpr uint32_t AG_TILE_BOX_BYTES = 32, AG_TILE_BOX_MSGS = 32;
 cudaError_t ag_launch_batch_tile(const TileParams& p, int nr, int decrypt, int ncta, cudaStream_t st);
 cudaError_t ag_launch_batch_perkey_tile(const TileParams& p, int nr, int decrypt, int max_cta, cudaStream_t st);
+// k_batch_warp + k_batch_warp_reduce + k_batch_split_finish (p.split, p.seg_parts, p.seg_acc, p.ticket set)
+cudaError_t ag_launch_batch_warp(const BatchParams& p, int nr, int decrypt, int ncta, cudaStream_t st);
 cudaError_t ag_launch_batch_cta(const BatchParams& p, int nr, int decrypt, int ncta, int nt, cudaStream_t st);
 cudaError_t ag_launch_batch_perkey(const BatchParams& p, int nr, int decrypt, int max_cta, cudaStream_t st);
 cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_bytes, const uint32_t* te0,

@@ -203,13 +203,15 @@ int agcm_stream_crypt_peer_async(agcm_ctx* ctx, int decrypt, const uint8_t h_iv1
  * d_in[in_off[i]..in_off[i+1]) -> d_out at the same offsets, tag at d_tag[16i..]
  * (produced for encrypt, expected for decrypt), d_ok[i] (decrypt only).
  * d_aad / d_aad_off may be NULL (no AAD).  lanes = threads cooperating on one
- * message (1,2,4,8,16,32; 1024 = one whole CTA per message, for few long messages;
- * 1024+S, S a power of two up to 256 = one CTA per 1/S of a message: counter-range segments whose
- * scaled GHASH partials a second launch XORs into the tag, for so few long messages
- * that whole messages would leave CTAs idle) or 0 = choose from n_msgs and
- * avg_len_hint.  Every choice produces the same bytes.  The segment layout keeps its
- * partials in a per-context scratch buffer (grown on demand, which synchronises the
- * device the first time): one such call in flight per context. */
+ * message (1,2,4,8,16,32; 1024 = one whole CTA per message; 1024+S, S a power of two up to 256 =
+ * one CTA per 1/S of a message: counter-range segments whose scaled GHASH partials a second launch
+ * XORs into the tag; 4096+S, 1 <= S <= 65536 = one WARP per 1/S of a message, units handed out by
+ * an atomic ticket and the lane combine deferred to a second launch -- the layout chosen for
+ * messages from about 32 KiB; 2048 = the TMA-staged message-per-lane kernel, uniform form only,
+ * 16-byte aligned buffers and pitch) or 0 = choose from n_msgs and avg_len_hint.  Every choice
+ * produces the same bytes.  The segment / unit layouts keep their partials in a per-context
+ * scratch buffer (grown on demand, which synchronises the device the first time): one such call
+ * in flight per context. */
 int agcm_batch_crypt(agcm_ctx* ctx, int decrypt, int lanes, uint64_t avg_len_hint, const uint8_t* d_iv12,
                      const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
                      uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);

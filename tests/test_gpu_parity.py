@@ -263,7 +263,7 @@ def test_long_iv_shard_gctr_peer_and_batch_paths(engine, oracle, torch_mod):
     want = [oracle.gcm_crypt_any_iv(key, ivs[iv_off[i]:iv_off[i + 1]].tobytes(), aad[aad_off[i]:aad_off[i + 1]].tobytes(),
                                     data[in_off[i]:in_off[i + 1]].tobytes()) for i in range(n_msgs)]
     d_j0 = engine.batch_derive_j0_device(_dev(torch, ivs), torch.from_numpy(iv_off).cuda())
-    for lanes in (0, 1, 4, 32, 1024):
+    for lanes in (0, 1, 4, 32, 1024, 4097, 4100):
         d_out = torch.zeros(data.size, dtype=torch.uint8, device="cuda")
         d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
         engine.batch_crypt_device(0, d_j0, _dev(torch, aad), torch.from_numpy(aad_off).cuda(), _dev(torch, data),
@@ -454,7 +454,7 @@ def test_batch_ragged_offsets_all_lane_counts(engine, oracle, torch_mod, kb):
     want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), kb, True, ivs, aad, aad_off, data, in_off, threads=8)
     d_ivs, d_aad, d_data = _dev(torch, ivs), _dev(torch, aad), _dev(torch, data)
     d_in_off, d_aad_off = torch.from_numpy(in_off.view(np.int64)).cuda(), torch.from_numpy(aad_off.view(np.int64)).cuda()
-    for lanes in (1, 2, 4, 8, 16, 32, 0):
+    for lanes in (1, 2, 4, 8, 16, 32, 0, 4097, 4099, 4104):
         d_ct = torch.zeros_like(d_data)
         d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
         engine.batch_crypt_device(0, d_ivs, d_aad, d_aad_off, d_data, d_in_off, d_ct, d_tags, lanes=lanes, avg_len_hint=200)
@@ -496,7 +496,7 @@ def test_batch_cta_per_message(engine, oracle, torch_mod):
     want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), 32, True, ivs, aad, aad_off, data, in_off, threads=8)
     d_in_off, d_aad_off = torch.from_numpy(in_off.view(np.int64)).cuda(), torch.from_numpy(aad_off.view(np.int64)).cuda()
     d_data, d_aad, d_ivs = _dev(torch, data), _dev(torch, aad), _dev(torch, ivs)
-    for lanes in (1024, 0, 32, 1026, 1028, 1032, 1040):
+    for lanes in (1024, 0, 32, 1026, 1028, 1032, 1040, 4097, 4098, 4101, 4096 + 64, 4096 + 1000):
         d_ct = torch.zeros_like(d_data)
         d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
         engine.batch_crypt_device(0, d_ivs, d_aad, d_aad_off, d_data, d_in_off, d_ct, d_tags, lanes=lanes,
