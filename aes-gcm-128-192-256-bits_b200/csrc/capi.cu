@@ -383,10 +383,12 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, 
     // segments of it; S keeps a unit near 64-256 rows of 32 blocks and gives every warp at least ~8
     // units to draw, so neither the per-unit overhead (a row or two) nor the tail matters.
     if (blocks >= 2048 && !getenv("AGCM_NO_WARP_UNITS")) {
+        // S only matters for offset batches (uniform ones are partitioned exactly): near 128 rows of
+        // 32 blocks per unit, and at least ~16 units per warp to draw when the messages are few
         const uint64_t warps = total_lanes / 32;
         uint64_t S = 1;
         while (blocks / S > 8192 && S < 65536) S <<= 1;
-        while (n_msgs * S < 8 * warps && blocks / S >= 4096 && S < 65536) S <<= 1;
+        while (n_msgs * S < 16 * warps && blocks / S >= 2048 && S < 65536) S <<= 1;
         return (int)(4096 + S);
     }
     uint64_t g = 1;
@@ -1033,11 +1035,28 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
     p.te0 = c->d_te0;
     p.n_msgs = n_msgs;
     if (g > 4096) {
-        p.split = (uint32_t)(g - 4096);
-        const uint64_t n_units = (uint64_t)n_msgs * p.split;
-        if (n_units >= 0xFFFFFFFFull) return AGCM_E_BAD_LEN;
-        const size_t parts_bytes = ((size_t)(n_units + n_msgs) * 16 + 255) & ~(size_t)255;
-        const size_t need = parts_bytes + (size_t)n_units * 512;
+        // a warp per unit (k_batch_warp): balanced static partition for uniform batches, `split`
+        // segments per message by ticket for offset batches
+        const uint64_t per_cta = (uint64_t)AG_STREAM_NT_MAX / 32;
+        const bool uniform = !p.in_off && !p.aad_off;
+        int ncta_w = c->ncta;
+        if (uniform) {
+            const uint64_t warps = (uint64_t)ncta_w * per_cta;
+            const uint64_t total = ag_msg_weight(p.aad ? p.aad_len : 0, p.len) * (uint64_t)n_msgs;
+            p.quota = ((total + warps - 1) / warps + 127) & ~127ull;   // whole rows of payload blocks
+            p.n_ids = warps + n_msgs;
+            p.split = 1;
+        } else {
+            p.split = (uint32_t)(g - 4096);
+            p.n_ids = (uint64_t)n_msgs * p.split;
+            if (p.n_ids >= 0xFFFFFFFFull) return AGCM_E_BAD_LEN;
+            const uint64_t need_cta = (p.n_ids + per_cta - 1) / per_cta;
+            if (need_cta < (uint64_t)ncta_w) ncta_w = (int)need_cta;
+        }
+        // scratch: [unit_desc n_ids x 16 | msg_acc n_msgs x 16] (zeroed per launch) [msg_ej0 n_msgs x 16] [seg_acc n_ids x 512]
+        const size_t zero_bytes = ((size_t)(p.n_ids + n_msgs) * 16 + 255) & ~(size_t)255;
+        const size_t ej0_bytes = ((size_t)n_msgs * 16 + 255) & ~(size_t)255;
+        const size_t need = zero_bytes + ej0_bytes + (size_t)p.n_ids * 512;
         if (need > c->seg_parts_bytes) {
             AG_CUDA(c, cudaFree(c->d_seg_parts));
             c->d_seg_parts = nullptr;
@@ -1045,13 +1064,17 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
             AG_CUDA(c, cudaMalloc(&c->d_seg_parts, need));
             c->seg_parts_bytes = need;
         }
-        p.seg_parts = c->d_seg_parts;
-        p.seg_acc = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(c->d_seg_parts) + parts_bytes);
-        if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
-        AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
-        p.ticket = c->d_tile_ticket;
-        const uint64_t per_cta = (uint64_t)AG_STREAM_NT_MAX / 32, need_cta = (n_units + per_cta - 1) / per_cta;
-        const int ncta_w = (int)(need_cta < (uint64_t)c->ncta ? need_cta : (uint64_t)c->ncta);
+        uint8_t* base = reinterpret_cast<uint8_t*>(c->d_seg_parts);
+        p.unit_desc = reinterpret_cast<uint64_t*>(base);
+        p.msg_acc = reinterpret_cast<uint32_t*>(base + (size_t)p.n_ids * 16);
+        p.msg_ej0 = reinterpret_cast<uint32_t*>(base + zero_bytes);
+        p.seg_acc = reinterpret_cast<uint4*>(base + zero_bytes + ej0_bytes);
+        AG_CUDA(c, cudaMemsetAsync(base, 0, zero_bytes, (cudaStream_t)stream));
+        if (!uniform) {
+            if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
+            AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
+            p.ticket = c->d_tile_ticket;
+        }
         AG_CUDA(c, ag_launch_batch_warp(p, c->nr, decrypt, ncta_w, (cudaStream_t)stream));
         c->launches += 3;
         return AGCM_OK;

@@ -280,8 +280,17 @@ struct BatchParams {
     // k_batch_cta: units (messages or segments) are handed out by this counter (zero at launch);
     // null = static round-robin over the CTAs
     uint32_t* ticket;
-    // k_batch_warp: raw lane accumulators, n_msgs x split units x 32 lanes x 16 B (BE words)
+    // k_batch_warp (a warp per unit): raw lane accumulators (32 x 16 B per unit id, BE words), unit
+    // descriptors {message + 1 (0 = unused id), blocks after the unit}, per-message XOR accumulators
+    // and E_K(J0) (n_msgs x 16 B each)
     uint4* seg_acc;
+    uint64_t* unit_desc;
+    uint32_t* msg_acc;
+    uint32_t* msg_ej0;
+    // uniform batches: static BALANCED partition -- warp w owns weight positions [w*quota, (w+1)*quota)
+    // of the concatenated messages (ag_msg_weight each); 0 = units of `split` segments by ticket
+    uint64_t quota;
+    uint64_t n_ids;            // unit ids in use: n_warps + n_msgs (balanced) or n_msgs * split (ticket)
 };
 
 // One message, or one counter-range segment of it (ag_batch_segment).
@@ -328,25 +337,32 @@ AG_HD void ag_batch_iv(const BatchParams& p, uint64_t m, uint32_t iv[3], uint32_
     *j0ctr = p.iv_is_j0 ? (((uint32_t)ivp[12] << 24) | ((uint32_t)ivp[13] << 16) | ((uint32_t)ivp[14] << 8) | (uint32_t)ivp[15]) : 1u;
 }
 
-// Segment `seg` of S of message w, the single-GPU form of the counter-range shards of
-// parallel.py: a contiguous range of the unified sequence AAD | CT (so bulk AAD is shared out
-// too), the length block and E_K(J0) with segment S-1.  *after = blocks of the
-// unified sequence that follow the segment: its GHASH partial is scaled by H^after before the
-// S partials are XORed.  AAD and CT are each zero-padded to whole blocks by the reference
-// (gcm_ghash.vhd:228-244), so cutting at block boundaries changes nothing.
-AG_HD MsgDesc ag_batch_segment(const MsgDesc& w, uint32_t seg, uint32_t S, uint64_t* after)
+// A unit of work smaller than a message: the part of message w whose WEIGHT positions fall in
+// [w0, w1), the single-GPU form of the counter-range shards of parallel.py.  Positions run over the
+// unified sequence AAD | CT (so bulk AAD is shared out too) with an AAD block (GHASH only) weighing
+// 1 and a payload block (AES + GHASH) 4, followed by AG_FINISH_WEIGHT positions that stand for the
+// length block and E_K(J0): the unit whose range reaches the end of them closes the message
+// (d.last).  *after = blocks of the unified sequence that follow the unit: its GHASH partial is
+// scaled by H^after before the partials of a message are XORed.  AAD and CT are each zero-padded
+// to whole blocks by the reference (gcm_ghash.vhd:228-244), so cutting at block boundaries changes
+// nothing; adjacent ranges share their boundary block index, so units tile a message exactly.
+constexpr uint64_t AG_FINISH_WEIGHT = 8;
+
+AG_HD uint64_t ag_msg_weight(uint64_t aad_len, uint64_t len)
 {
-    const uint64_t a = (w.aad_len + 15) >> 4, n = (w.len + 15) >> 4, tot = a + n;
-    // equal WORK per segment, not equal blocks: an AAD block (GHASH only) weighs 1, a payload
-    // block (AES + GHASH) 4; boundary k sits at weight k * per of the total a + 4n
-    const uint64_t W = a + 4 * n, per = (W + S - 1) / S;
-    uint64_t w0 = (uint64_t)seg * per, w1 = w0 + per;
+    return ((aad_len + 15) >> 4) + 4 * ((len + 15) >> 4) + AG_FINISH_WEIGHT;
+}
+
+AG_HD MsgDesc ag_batch_range(const MsgDesc& w, uint64_t w0, uint64_t w1, uint64_t* after)
+{
+    const uint64_t a = (w.aad_len + 15) >> 4, n = (w.len + 15) >> 4, tot = a + n, W = a + 4 * n;
+    const bool last = w1 >= W + AG_FINISH_WEIGHT;
     if (w0 > W) w0 = W;
     if (w1 > W) w1 = W;
     uint64_t u0 = w0 <= a ? w0 : a + (w0 - a + 3) / 4;
     uint64_t u1 = w1 <= a ? w1 : a + (w1 - a + 3) / 4;
     if (u0 > tot) u0 = tot;
-    if (u1 > tot || seg == S - 1) u1 = tot;
+    if (u1 > tot || last) u1 = tot;
     const uint64_t a0 = u0 < a ? u0 : a, a1 = u1 < a ? u1 : a;          // AAD blocks [a0, a1)
     const uint64_t c0 = (u0 > a ? u0 : a) - a, c1 = (u1 > a ? u1 : a) - a;  // CT blocks [c0, c1)
     MsgDesc d = w;
@@ -356,9 +372,21 @@ AG_HD MsgDesc ag_batch_segment(const MsgDesc& w, uint32_t seg, uint32_t S, uint6
     d.out = w.out + 16 * c0;
     d.len = (c1 > c0) ? ((c1 == n) ? w.len - 16 * c0 : 16 * (c1 - c0)) : 0;
     d.ctr_off = (uint32_t)c0;
-    d.last = (seg == S - 1) ? 1u : 0u;
-    *after = d.last ? 0 : (tot - u1) + 1;
+    d.last = last ? 1u : 0u;
+    *after = last ? 0 : (tot - u1) + 1;
     return d;
+}
+
+// Segment `seg` of S equal-WORK segments of message w (the length block and E_K(J0) with segment S-1).
+AG_HD MsgDesc ag_batch_segment(const MsgDesc& w, uint32_t seg, uint32_t S, uint64_t* after)
+{
+    const uint64_t a = (w.aad_len + 15) >> 4, n = (w.len + 15) >> 4;
+    const uint64_t W = a + 4 * n, per = (W + S - 1) / S;
+    uint64_t w0 = (uint64_t)seg * per, w1 = w0 + per;
+    if (w0 > W) w0 = W;
+    if (w1 > W) w1 = W;
+    if (seg == S - 1) w1 = W + AG_FINISH_WEIGHT;
+    return ag_batch_range(w, w0, w1, after);
 }
 
 // Lane t of G over the unified sequence [AAD blocks | CT blocks | length block]

@@ -942,14 +942,20 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
 
 // ===========================================================================
 // Batched MID-SIZE and LONG messages under the shared key: one WARP per unit, where a unit is a
-// whole message or one of `split` counter-range segments of it (ag_batch_segment, the single-GPU
-// form of the shards of parallel.py).  Units are handed out warp by warp through an atomic ticket,
-// so the grid stays busy to the last unit whatever the number or the sizes of the messages; and
-// the per-unit epilogue is deferred: a warp just DUMPS its 32 raw lane accumulators (512 B,
-// coalesced).  The lane weights H^(32-t) -- one ~1100-instruction generic product per lane and
-// unit when done in place, which is what made fine segments unaffordable for k_batch /
-// k_batch_cta -- are applied by k_batch_warp_reduce with one LANE per unit: a 32-step Horner with
-// the H table, 32 units side by side per warp.  Linearity of GHASH in its input, as in
+// message or a counter-range part of it (ag_batch_range, the single-GPU form of the shards of
+// parallel.py).  Two ways of cutting:
+//   * uniform batches: a static BALANCED partition.  The messages are laid end to end on a weight
+//     axis (AAD block 1, payload block 4, finish 8) and warp w owns positions [w*quota, (w+1)*quota):
+//     every warp gets the same work to within a row, whatever the number and size of the messages,
+//     and there are at most n_warps + n_msgs units, so the per-unit overhead is paid once or twice
+//     per warp;
+//   * offset (ragged) batches: `split` equal-work segments per message, handed out by ticket.
+// The per-unit epilogue is deferred: a warp DUMPS its 32 raw lane accumulators (512 B, coalesced).
+// The lane weights H^(32-t) -- one ~1100-instruction generic product per lane and unit when done in
+// place, which is what made fine cuts unaffordable for k_batch / k_batch_cta -- are applied by
+// k_batch_warp_reduce with one LANE per unit (a 32-step Horner with the H table, 32 units side by
+// side per warp), which also scales by H^after and XORs the unit into its message's accumulator;
+// k_batch_warp_finish turns accumulators into tags.  Linearity of GHASH in its input, as in
 // src/gcm_ghash.vhd:317-344.  Table: T_a = H^32.
 // ===========================================================================
 template <int NR, bool DEC>
@@ -963,6 +969,43 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid
     __syncthreads();
     TeSmem te{ag_smem, lane * 4};
     GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
+
+    auto run_unit = [&](uint64_t id, uint64_t m, const MsgDesc& d, uint64_t after) {
+        uint32_t ivw[3];
+        MsgDesc du = d;
+        ag_batch_iv(p, m, ivw, &du.j0ctr);
+        const AesCtrConst cc = aes_ctr_precompute(p.rk, ivw[0], ivw[1], ivw[2], te);
+        AesCtrSeqCache cache;
+        cache.key = 0xFFFFFFFFu;
+        uint32_t e[4] = {0, 0, 0, 0};
+        const gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, du, lane, 32u, te, gh, e);
+        p.seg_acc[id * 32 + lane] = make_uint4(y.w[0], y.w[1], y.w[2], y.w[3]);
+        if (lane == 0) {
+            p.unit_desc[2 * id] = m + 1;
+            p.unit_desc[2 * id + 1] = after;
+        }
+        if (du.last && lane == 31) {   // the lane that met the length block also produced E_K(J0)
+            uint32_t* de = p.msg_ej0 + 4 * m;
+            de[0] = e[0]; de[1] = e[1]; de[2] = e[2]; de[3] = e[3];
+        }
+        __syncwarp();
+    };
+
+    if (p.quota) {
+        const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+        const uint64_t wm = ag_msg_weight(p.aad ? p.aad_len : 0, p.len), total = wm * p.n_msgs;
+        const uint64_t g0 = w * p.quota;
+        uint64_t g1 = g0 + p.quota;
+        if (g1 > total) g1 = total;
+        for (uint64_t m = g0 / wm; m * wm < g1; ++m) {   // uniform per warp
+            const uint64_t lo = m * wm, r0 = (g0 > lo ? g0 : lo) - lo, r1 = (g1 < lo + wm ? g1 : lo + wm) - lo;
+            uint64_t after = 0;
+            const MsgDesc d = ag_batch_range(ag_batch_msg(p, m), r0, r1, &after);
+            if (!d.last && d.len == 0 && d.aad_len == 0) continue;   // a cut inside one block: nothing of it is mine
+            run_unit(w + m, m, d, after);
+        }
+        return;
+    }
     const uint32_t S = p.split;
     const uint64_t n_units = p.n_msgs * S;
     for (;;) {
@@ -971,65 +1014,66 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid
         const uint64_t u = __shfl_sync(0xffffffffu, tk, 0);
         if (u >= n_units) break;
         const uint64_t m = u / S;
-        const uint32_t seg = (uint32_t)(u - m * S);
         uint64_t after = 0;
         MsgDesc d = ag_batch_msg(p, m);
-        if (S > 1) d = ag_batch_segment(d, seg, S, &after);
-        uint32_t ivw[3];
-        ag_batch_iv(p, m, ivw, &d.j0ctr);
-        const AesCtrConst cc = aes_ctr_precompute(p.rk, ivw[0], ivw[1], ivw[2], te);
-        AesCtrSeqCache cache;
-        cache.key = 0xFFFFFFFFu;
-        uint32_t e[4] = {0, 0, 0, 0};
-        const gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, lane, 32u, te, gh, e);
-        p.seg_acc[u * 32 + lane] = make_uint4(y.w[0], y.w[1], y.w[2], y.w[3]);
-        if (d.last && lane == 31) {   // the lane that met the length block also produced E_K(J0)
-            uint32_t* de = p.seg_parts + 4 * (n_units + m);
-            de[0] = e[0]; de[1] = e[1]; de[2] = e[2]; de[3] = e[3];
-        }
-        __syncwarp();
+        if (S > 1) d = ag_batch_segment(d, (uint32_t)(u - m * S), S, &after);
+        run_unit(u, m, d, after);
     }
 }
 
-// One lane per unit: R = sum_t Y_t H^(32-t) by a serial Horner over the dumped accumulators with
-// the H table, then the scaling by H^(blocks after the unit) (product of the H^(2^k) of the set
-// bits); the scaled partial goes where k_batch_split_finish expects it.
+// One lane per unit id: R = sum_t Y_t H^(32-t) by a serial Horner over the dumped accumulators with
+// the H table, scaling by H^(blocks after the unit) (product of the H^(2^k) of the set bits), XOR
+// into the message's accumulator.
 __global__ void __launch_bounds__(128) k_batch_warp_reduce(const __grid_constant__ BatchParams p)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     fill_gh_tables(p.key->tab[0], nullptr);
     __syncthreads();
     GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
-    const uint32_t S = p.split;
-    const uint64_t n_units = p.n_msgs * S;
-    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + tid;
-    if (u >= n_units) return;
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + tid;
+    if (id >= p.n_ids) return;
+    const uint64_t m1 = p.unit_desc[2 * id], after = p.unit_desc[2 * id + 1];
+    if (m1 == 0) return;
     gf128 r = gf_zero();
-    const uint4* acc = p.seg_acc + u * 32;
+    const uint4* acc = p.seg_acc + id * 32;
 #pragma unroll 1
     for (int t = 0; t < 32; ++t) {
         const uint4 q = __ldcg(acc + t);
         r.w[0] ^= q.x; r.w[1] ^= q.y; r.w[2] ^= q.z; r.w[3] ^= q.w;
         r = gf_mul_table(r, gh);
     }
-    if (S > 1) {
-        const uint64_t m = u / S;
-        uint64_t after = 0;
-        (void)ag_batch_segment(ag_batch_msg(p, m), (uint32_t)(u - m * S), S, &after);
-        if (after) {
-            gf128 f = gf_one();
-            bool first = true;
+    if (after) {
+        gf128 f = gf_one();
+        bool first = true;
 #pragma unroll 1
-            for (int k = 0; k < 40; ++k)
-                if ((after >> k) & 1) {
-                    f = first ? p.key->pow2[k] : gf_mul(f, p.key->pow2[k]);
-                    first = false;
-                }
-            r = gf_mul(r, f);
-        }
+        for (int k = 0; k < 40; ++k)
+            if ((after >> k) & 1) {
+                f = first ? p.key->pow2[k] : gf_mul(f, p.key->pow2[k]);
+                first = false;
+            }
+        r = gf_mul(r, f);
     }
-    uint32_t* dst = p.seg_parts + 4 * u;
-    dst[0] = r.w[0]; dst[1] = r.w[1]; dst[2] = r.w[2]; dst[3] = r.w[3];
+    uint32_t* dst = p.msg_acc + 4 * (m1 - 1);
+    atomicXor(dst + 0, r.w[0]); atomicXor(dst + 1, r.w[1]); atomicXor(dst + 2, r.w[2]); atomicXor(dst + 3, r.w[3]);
+}
+
+template <bool DEC>
+__global__ void k_batch_warp_finish(const __grid_constant__ BatchParams p)
+{
+    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= p.n_msgs) return;
+    const uint4 r = *reinterpret_cast<const uint4*>(p.msg_acc + 4 * m);
+    const uint4 e = *reinterpret_cast<const uint4*>(p.msg_ej0 + 4 * m);
+    uint32_t tg[4] = {ag_bswap32(r.x) ^ e.x, ag_bswap32(r.y) ^ e.y, ag_bswap32(r.z) ^ e.z, ag_bswap32(r.w) ^ e.w};
+    uint8_t* tp = p.tag + 16 * m;
+    if (DEC) {
+        uint32_t x[4];
+        ag_load_block(tp, 16, x);
+        const uint32_t diff = (x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3]);
+        p.ok[m] = diff ? 0 : 1;
+    } else {
+        ag_store_block(tp, 16, tg);
+    }
 }
 
 // Tag finish of the split layout: one thread per message XORs its S scaled partials
@@ -1507,11 +1551,10 @@ static cudaError_t launch_batch_warp_t(const BatchParams& p, int ncta, cudaStrea
     k_batch_warp<NR, DEC><<<ncta, AG_STREAM_NT_MAX, kSmemBytes, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const uint64_t n_units = p.n_msgs * p.split;
-    k_batch_warp_reduce<<<(unsigned)((n_units + 127) / 128), 128, kSmemBytes, st>>>(p);
+    k_batch_warp_reduce<<<(unsigned)((p.n_ids + 127) / 128), 128, kSmemBytes, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_batch_split_finish<DEC><<<(unsigned)((p.n_msgs + 127) / 128), 128, 0, st>>>(p);
+    k_batch_warp_finish<DEC><<<(unsigned)((p.n_msgs + 127) / 128), 128, 0, st>>>(p);
     return cudaGetLastError();
 }
 

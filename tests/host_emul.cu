@@ -203,6 +203,66 @@ void perkey_nk(const BatchParams& p)
 
 }  // namespace
 
+// k_batch_warp's BALANCED partition on a virtual grid of n_warps warps (uniform records): warp w
+// owns weight positions [w*quota, (w+1)*quota) of the concatenated messages; every unit's 32 lane
+// accumulators are combined as k_batch_warp_reduce does (serial Horner with H, times H^after) and
+// XORed into the message accumulator; k_batch_warp_finish's tag step at the end.
+template <int NR, bool DEC>
+static void batch_balanced_nr(const BatchParams& p, uint32_t n_warps, const gf128& H)
+{
+    std::vector<uint4> tab_g, tab_1;
+    build_table(gf_pow(H, 32), tab_g);
+    build_table(H, tab_1);
+    TeHost te{tables().te0};
+    GhHost gh_g{tab_g.data()}, gh_1{tab_1.data()};
+    const uint64_t wm = ag_msg_weight(p.aad ? p.aad_len : 0, p.len), total = wm * p.n_msgs;
+    const uint64_t quota = ((total + n_warps - 1) / n_warps + 127) & ~127ull;
+    std::vector<gf128> acc(p.n_msgs, gf_zero());
+    std::vector<uint32_t> ej0(4 * p.n_msgs, 0);
+    std::vector<int> closed(p.n_msgs, 0);
+    for (uint64_t w = 0; w < n_warps; ++w) {
+        const uint64_t g0 = w * quota;
+        uint64_t g1 = g0 + quota;
+        if (g1 > total) g1 = total;
+        for (uint64_t m = g0 / wm; m * wm < g1; ++m) {
+            const uint64_t lo = m * wm, r0 = (g0 > lo ? g0 : lo) - lo, r1 = (g1 < lo + wm ? g1 : lo + wm) - lo;
+            uint64_t after = 0;
+            MsgDesc d = ag_batch_range(ag_batch_msg(p, m), r0, r1, &after);
+            if (!d.last && d.len == 0 && d.aad_len == 0) continue;
+            const uint8_t* ivp = p.iv + 12 * m;
+            uint32_t iv[3] = {0, 0, 0};
+            for (int j = 0; j < 12; ++j) iv[j >> 2] |= (uint32_t)ivp[j] << (8 * (j & 3));
+            const AesCtrConst cc = aes_ctr_precompute(p.rk, iv[0], iv[1], iv[2], te);
+            gf128 r = gf_zero();
+            for (uint32_t t = 0; t < 32; ++t) {
+                AesCtrSeqCache cache;
+                cache.key = 0xFFFFFFFFu;
+                uint32_t el[4] = {0, 0, 0, 0};
+                gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, 32u, te, gh_g, el);
+                if (t == 31 && d.last) { memcpy(&ej0[4 * m], el, 16); closed[m]++; }
+                r = gf_xor(r, y);
+                r = gf_mul_table(r, gh_1);
+            }
+            if (after) r = gf_mul(r, gf_pow(H, after));
+            acc[m] = gf_xor(acc[m], r);
+        }
+    }
+    for (uint64_t m = 0; m < p.n_msgs; ++m) {
+        const gf128 r = acc[m];
+        uint32_t tg[4] = {ag_bswap32(r.w[0]) ^ ej0[4 * m], ag_bswap32(r.w[1]) ^ ej0[4 * m + 1], ag_bswap32(r.w[2]) ^ ej0[4 * m + 2],
+                          ag_bswap32(r.w[3]) ^ ej0[4 * m + 3]};
+        if (closed[m] != 1) tg[0] ^= 0xDEADBEEFu;   // every message is closed by exactly one unit
+        uint8_t* tp = p.tag + 16 * m;
+        if (DEC) {
+            uint32_t x[4];
+            ag_load_block(tp, 16, x);
+            p.ok[m] = ((x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3])) ? 0 : 1;
+        } else {
+            ag_store_block(tp, 16, tg);
+        }
+    }
+}
+
 extern "C" {
 
 int emul_batch_perkey(const uint8_t* keys, int key_bytes, int decrypt, const uint8_t* iv, const uint8_t* aad,
@@ -294,6 +354,37 @@ int emul_batch_split(const uint8_t* rk_bytes, int nr, int decrypt, int G, int S,
         case 10: decrypt ? batch_nr<10, true>(p, G, H, S) : batch_nr<10, false>(p, G, H, S); break;
         case 12: decrypt ? batch_nr<12, true>(p, G, H, S) : batch_nr<12, false>(p, G, H, S); break;
         case 14: decrypt ? batch_nr<14, true>(p, G, H, S) : batch_nr<14, false>(p, G, H, S); break;
+        default: return -1;
+    }
+    return 0;
+}
+
+int emul_batch_balanced(const uint8_t* rk_bytes, int nr, int decrypt, int n_warps, const uint8_t* iv, const uint8_t* aad,
+                        uint64_t aad_len, uint64_t aad_stride, const uint8_t* in, uint8_t* out, uint64_t len, uint64_t stride,
+                        uint8_t* tag, uint8_t* ok, uint64_t n_msgs)
+{
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    memcpy(p.rk, rk_bytes, (size_t)16 * (nr + 1));
+    p.iv = iv;
+    p.aad = aad_len ? aad : nullptr;
+    p.in = in;
+    p.out = out;
+    p.tag = tag;
+    p.ok = ok;
+    p.n_msgs = n_msgs;
+    p.len = len;
+    p.stride = stride;
+    p.aad_len = aad_len;
+    p.aad_stride = aad_stride;
+    const TeHost te{tables().te0};
+    uint32_t h[4];
+    aes_encrypt_words(p.rk, nr, 0, 0, 0, 0, te, h);
+    const gf128 H = gf_from_le_words(h[0], h[1], h[2], h[3]);
+    switch (nr) {
+        case 10: decrypt ? batch_balanced_nr<10, true>(p, n_warps, H) : batch_balanced_nr<10, false>(p, n_warps, H); break;
+        case 12: decrypt ? batch_balanced_nr<12, true>(p, n_warps, H) : batch_balanced_nr<12, false>(p, n_warps, H); break;
+        case 14: decrypt ? batch_balanced_nr<14, true>(p, n_warps, H) : batch_balanced_nr<14, false>(p, n_warps, H); break;
         default: return -1;
     }
     return 0;

@@ -141,6 +141,46 @@ def test_batch_split_segments(emul, oracle, S):
                 assert (tag == et).all(), (kb, G)
 
 
+@pytest.mark.parametrize("n_warps", [1, 3, 7, 40])
+def test_batch_balanced_partition(emul, oracle, n_warps):
+    """k_batch_warp's balanced partition of uniform records over a virtual grid: cuts inside the AAD,
+    inside the payload, inside one payload block's weight, inside the finish positions; more warps
+    than messages and more messages than warps; ragged tails; every message closed exactly once."""
+    rng = np.random.default_rng(500 + n_warps)
+    for kb, nm, length, alen in ((16, 5, 16 * 37 + 5, 16 * 11 + 3), (32, 2, 16 * 200, 0), (24, 9, 100, 700), (16, 3, 0, 50),
+                                 (32, 6, 16, 16), (24, 1, 16 * 129 + 1, 16 * 5)):
+        for dec in (0, 1):
+            stride, astride = length + 3, alen + 5
+            buf = rng.integers(0, 256, nm * stride + 1, dtype=np.uint8)
+            abuf = rng.integers(0, 256, nm * astride + 1, dtype=np.uint8)
+            ivs = rng.integers(0, 256, 12 * nm, dtype=np.uint8)
+            key = rng.integers(0, 256, kb, dtype=np.uint8)
+            rk = np.frombuffer(oracle.key_expand(key.tobytes()), dtype=np.uint8).copy()
+            nr = len(rk) // 16 - 1
+            packed = buf[:nm * stride].reshape(nm, stride)[:, :length].reshape(-1).copy()
+            apacked = abuf[:nm * astride].reshape(nm, astride)[:, :alen].reshape(-1).copy()
+            in_off = (np.arange(nm + 1) * length).astype(np.uint64)
+            aad_off = (np.arange(nm + 1) * alen).astype(np.uint64)
+            eo, et = oracle.gcm_batch(key, kb, True, ivs, apacked if alen else None, aad_off if alen else None, packed, in_off,
+                                      decrypt=bool(dec))
+            out = np.zeros_like(buf)
+            tag = np.zeros(16 * nm, np.uint8)
+            ok = np.zeros(nm, np.uint8)
+            if dec:
+                tag[:] = et
+                tag[16 * (nm - 1) + 2] ^= 0x40
+            rc = emul.emul_batch_balanced(u8p(rk), nr, dec, n_warps, u8p(ivs), u8p(abuf), ctypes.c_uint64(alen),
+                                          ctypes.c_uint64(astride), u8p(buf), u8p(out), ctypes.c_uint64(length),
+                                          ctypes.c_uint64(stride), u8p(tag), u8p(ok), ctypes.c_uint64(nm))
+            assert rc == 0
+            got = out[:nm * stride].reshape(nm, stride)[:, :length].reshape(-1)
+            assert (got == eo[:nm * length]).all(), (kb, nm, length, alen, dec)
+            if dec:
+                assert list(ok) == [1] * (nm - 1) + [0], (kb, nm, length, alen)
+            else:
+                assert (tag == et).all(), (kb, nm, length, alen)
+
+
 @pytest.mark.parametrize("kb", [16, 24, 32])
 def test_perkey_messages(emul, oracle, kb):
     """One distinct key per message: on-the-fly key schedule + private 4-bit GHASH table."""
