@@ -39,6 +39,12 @@ for s in $STEPS; do
     ncu)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream -s 3 -c 1 -f -o $OUT/${TAG}_prof \
         python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > $OUT/${TAG}_ncu_run.log 2>&1; echo "ncu rc=$?"; tail -3 $OUT/${TAG}_ncu_run.log ;;
+    ncutile)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch_tile -s 2 -c 1 -f -o $OUT/${TAG}_prof_tile \
+        python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_ncutile_run.log 2>&1; echo "ncutile rc=$?"; tail -3 $OUT/${TAG}_ncutile_run.log ;;
+    ncuwarp)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch_warp -s 1 -c 1 -f -o $OUT/${TAG}_prof_warp \
+        python tools/probe_aad_heavy.py > $OUT/${TAG}_ncuwarp_run.log 2>&1; echo "ncuwarp rc=$?"; tail -3 $OUT/${TAG}_ncuwarp_run.log ;;
     ncubatch)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch -s 2 -c 1 -f -o $OUT/${TAG}_prof_batch \
         python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_ncubatch_run.log 2>&1; echo "ncubatch rc=$?"; tail -3 $OUT/${TAG}_ncubatch_run.log ;;
