@@ -1053,10 +1053,12 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
             const uint64_t need_cta = (p.n_ids + per_cta - 1) / per_cta;
             if (need_cta < (uint64_t)ncta_w) ncta_w = (int)need_cta;
         }
-        // scratch: [unit_desc n_ids x 16 | msg_acc n_msgs x 16] (zeroed per launch) [msg_ej0 n_msgs x 16] [seg_acc n_ids x 512]
-        const size_t zero_bytes = ((size_t)(p.n_ids + n_msgs) * 16 + 255) & ~(size_t)255;
+        // scratch: [msg_acc n_msgs x 16 | msg_cnt n_msgs x 4] (zeroed per launch) [unit_desc n_ids x 16] [msg_ej0 n_msgs x 16]
+        // [seg_acc n_ids x 512]
+        const size_t zero_bytes = ((size_t)n_msgs * 20 + 255) & ~(size_t)255;
+        const size_t desc_bytes = ((size_t)p.n_ids * 16 + 255) & ~(size_t)255;
         const size_t ej0_bytes = ((size_t)n_msgs * 16 + 255) & ~(size_t)255;
-        const size_t need = zero_bytes + ej0_bytes + (size_t)p.n_ids * 512;
+        const size_t need = zero_bytes + desc_bytes + ej0_bytes + (size_t)p.n_ids * 512;
         if (need > c->seg_parts_bytes) {
             AG_CUDA(c, cudaFree(c->d_seg_parts));
             c->d_seg_parts = nullptr;
@@ -1065,10 +1067,11 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
             c->seg_parts_bytes = need;
         }
         uint8_t* base = reinterpret_cast<uint8_t*>(c->d_seg_parts);
-        p.unit_desc = reinterpret_cast<uint64_t*>(base);
-        p.msg_acc = reinterpret_cast<uint32_t*>(base + (size_t)p.n_ids * 16);
-        p.msg_ej0 = reinterpret_cast<uint32_t*>(base + zero_bytes);
-        p.seg_acc = reinterpret_cast<uint4*>(base + zero_bytes + ej0_bytes);
+        p.msg_acc = reinterpret_cast<uint32_t*>(base);
+        p.msg_cnt = reinterpret_cast<uint32_t*>(base + (size_t)n_msgs * 16);
+        p.unit_desc = reinterpret_cast<uint64_t*>(base + zero_bytes);
+        p.msg_ej0 = reinterpret_cast<uint32_t*>(base + zero_bytes + desc_bytes);
+        p.seg_acc = reinterpret_cast<uint4*>(base + zero_bytes + desc_bytes + ej0_bytes);
         AG_CUDA(c, cudaMemsetAsync(base, 0, zero_bytes, (cudaStream_t)stream));
         if (!uniform) {
             if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
@@ -1076,7 +1079,7 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
             p.ticket = c->d_tile_ticket;
         }
         AG_CUDA(c, ag_launch_batch_warp(p, c->nr, decrypt, ncta_w, (cudaStream_t)stream));
-        c->launches += 3;
+        c->launches++;
         return AGCM_OK;
     }
     if (g >= 1024) {

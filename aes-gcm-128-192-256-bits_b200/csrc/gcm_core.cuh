@@ -286,6 +286,7 @@ struct BatchParams {
     uint4* seg_acc;
     uint64_t* unit_desc;
     uint32_t* msg_acc;
+    uint32_t* msg_cnt;         // units of message m combined so far (the last one writes the tag)
     uint32_t* msg_ej0;
     // uniform batches: static BALANCED partition -- warp w owns weight positions [w*quota, (w+1)*quota)
     // of the concatenated messages (ag_msg_weight each); 0 = units of `split` segments by ticket

@@ -952,23 +952,89 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
 //   * offset (ragged) batches: `split` equal-work segments per message, handed out by ticket.
 // The per-unit epilogue is deferred: a warp DUMPS its 32 raw lane accumulators (512 B, coalesced).
 // The lane weights H^(32-t) -- one ~1100-instruction generic product per lane and unit when done in
-// place, which is what made fine cuts unaffordable for k_batch / k_batch_cta -- are applied by
-// k_batch_warp_reduce with one LANE per unit (a 32-step Horner with the H table, 32 units side by
-// side per warp), which also scales by H^after and XORs the unit into its message's accumulator;
-// k_batch_warp_finish turns accumulators into tags.  Linearity of GHASH in its input, as in
-// src/gcm_ghash.vhd:317-344.  Table: T_a = H^32.
+// place, which is what made fine cuts unaffordable for k_batch / k_batch_cta -- are applied in
+// combine rounds with one LANE per unit (a 32-step Horner with the H table, up to 16 units side by
+// side), which also scale by H^after and XOR the unit into its message's accumulator; the lane
+// that completes a message's last unit writes (or checks) the tag.  One launch.  Linearity of GHASH
+// in its input, as in src/gcm_ghash.vhd:317-344.  Tables: T_a = H^32, T_b = H.
 // ===========================================================================
 template <int NR, bool DEC>
 __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid_constant__ BatchParams p)
 {
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     stage_te0(p.te0);
-    fill_gh_tables(p.key->tab[5], nullptr);
+    fill_gh_tables(p.key->tab[5], p.key->tab[0]);   // T_a = H^32 (rows), T_b = H (unit combine)
     __syncthreads();
     expand_aes_tables();
     __syncthreads();
     TeSmem te{ag_smem, lane * 4};
     GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
+    GhSmem gh_1{ag_smem + SM_GH + 128, (lane & 7) * 16};
+    // units this warp has dumped but not yet combined (ids), 16 per warp
+    uint32_t* pend = reinterpret_cast<uint32_t*>(ag_smem + SM_MISC + 1024) + warp * 16;
+    uint32_t n_pend = 0;
+    const uint32_t S = p.split;
+    const uint64_t wm = ag_msg_weight(p.aad ? p.aad_len : 0, p.len);
+
+    // One more unit of message m is done (combined, or a cut that owned no block); whoever completes
+    // the count turns the accumulator into the tag.
+    auto arrive = [&](uint64_t m) {
+        uint32_t units = S;   // how many units the message was cut into
+        if (p.quota) units = (uint32_t)(((m + 1) * wm - 1) / p.quota - (m * wm) / p.quota + 1);
+        __threadfence();
+        const uint32_t done = atomicAdd(p.msg_cnt + m, 1u) + 1;
+        if (done != units) return;
+        __threadfence();
+        uint32_t* dst = p.msg_acc + 4 * m;
+        const uint32_t a0 = atomicOr(dst + 0, 0u), a1 = atomicOr(dst + 1, 0u), a2 = atomicOr(dst + 2, 0u), a3 = atomicOr(dst + 3, 0u);
+        const uint4 e = __ldcg(reinterpret_cast<const uint4*>(p.msg_ej0 + 4 * m));
+        const uint32_t tg[4] = {ag_bswap32(a0) ^ e.x, ag_bswap32(a1) ^ e.y, ag_bswap32(a2) ^ e.z, ag_bswap32(a3) ^ e.w};
+        uint8_t* tp = p.tag + 16 * m;
+        if (DEC) {
+            uint32_t x[4];
+            ag_load_block(tp, 16, x);
+            const uint32_t diff = (x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3]);
+            p.ok[m] = diff ? 0 : 1;
+        } else {
+            ag_store_block(tp, 16, tg);
+        }
+    };
+
+    // Combine round: lane i takes pending unit i.  R = sum_t Y_t H^(32-t) by a serial Horner over the
+    // dumped accumulators with the H table, times H^(blocks after the unit) (product of the H^(2^k)
+    // of the set bits), XOR into the message's accumulator; the lane that completes a message's last
+    // unit turns the accumulator into the tag.
+    auto combine = [&]() {
+        __syncwarp();
+        if (lane < n_pend) {
+            const uint64_t id = pend[lane];
+            const uint64_t m = __ldcg(p.unit_desc + 2 * id) - 1, after = __ldcg(p.unit_desc + 2 * id + 1);
+            gf128 r = gf_zero();
+            const uint4* acc = p.seg_acc + id * 32;
+#pragma unroll 1
+            for (int t = 0; t < 32; ++t) {
+                const uint4 q = __ldcg(acc + t);
+                r.w[0] ^= q.x; r.w[1] ^= q.y; r.w[2] ^= q.z; r.w[3] ^= q.w;
+                r = gf_mul_table(r, gh_1);
+            }
+            if (after) {
+                gf128 f = gf_one();
+                bool first = true;
+#pragma unroll 1
+                for (int k = 0; k < 40; ++k)
+                    if ((after >> k) & 1) {
+                        f = first ? p.key->pow2[k] : gf_mul(f, p.key->pow2[k]);
+                        first = false;
+                    }
+                r = gf_mul(r, f);
+            }
+            uint32_t* dst = p.msg_acc + 4 * m;
+            atomicXor(dst + 0, r.w[0]); atomicXor(dst + 1, r.w[1]); atomicXor(dst + 2, r.w[2]); atomicXor(dst + 3, r.w[3]);
+            arrive(m);
+        }
+        __syncwarp();
+        n_pend = 0;
+    };
 
     auto run_unit = [&](uint64_t id, uint64_t m, const MsgDesc& d, uint64_t after) {
         uint32_t ivw[3];
@@ -979,21 +1045,20 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid
         cache.key = 0xFFFFFFFFu;
         uint32_t e[4] = {0, 0, 0, 0};
         const gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, du, lane, 32u, te, gh, e);
-        p.seg_acc[id * 32 + lane] = make_uint4(y.w[0], y.w[1], y.w[2], y.w[3]);
+        __stcg(p.seg_acc + id * 32 + lane, make_uint4(y.w[0], y.w[1], y.w[2], y.w[3]));
         if (lane == 0) {
-            p.unit_desc[2 * id] = m + 1;
-            p.unit_desc[2 * id + 1] = after;
+            __stcg(p.unit_desc + 2 * id, m + 1);
+            __stcg(p.unit_desc + 2 * id + 1, after);
+            pend[n_pend] = (uint32_t)id;
         }
-        if (du.last && lane == 31) {   // the lane that met the length block also produced E_K(J0)
-            uint32_t* de = p.msg_ej0 + 4 * m;
-            de[0] = e[0]; de[1] = e[1]; de[2] = e[2]; de[3] = e[3];
-        }
-        __syncwarp();
+        if (du.last && lane == 31)   // the lane that met the length block also produced E_K(J0)
+            __stcg(reinterpret_cast<uint4*>(p.msg_ej0 + 4 * m), make_uint4(e[0], e[1], e[2], e[3]));
+        if (++n_pend == 16) combine();
     };
 
     if (p.quota) {
-        const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
-        const uint64_t wm = ag_msg_weight(p.aad ? p.aad_len : 0, p.len), total = wm * p.n_msgs;
+        const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+        const uint64_t total = wm * p.n_msgs;
         const uint64_t g0 = w * p.quota;
         uint64_t g1 = g0 + p.quota;
         if (g1 > total) g1 = total;
@@ -1001,79 +1066,27 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid
             const uint64_t lo = m * wm, r0 = (g0 > lo ? g0 : lo) - lo, r1 = (g1 < lo + wm ? g1 : lo + wm) - lo;
             uint64_t after = 0;
             const MsgDesc d = ag_batch_range(ag_batch_msg(p, m), r0, r1, &after);
-            if (!d.last && d.len == 0 && d.aad_len == 0) continue;   // a cut inside one block: nothing of it is mine
+            if (!d.last && d.len == 0 && d.aad_len == 0) {   // a cut inside one block: nothing of it is mine
+                if (lane == 0) arrive(m);
+                continue;
+            }
             run_unit(w + m, m, d, after);
         }
-        return;
-    }
-    const uint32_t S = p.split;
-    const uint64_t n_units = p.n_msgs * S;
-    for (;;) {
-        uint32_t tk = 0;
-        if (lane == 0) tk = atomicAdd(p.ticket, 1u);
-        const uint64_t u = __shfl_sync(0xffffffffu, tk, 0);
-        if (u >= n_units) break;
-        const uint64_t m = u / S;
-        uint64_t after = 0;
-        MsgDesc d = ag_batch_msg(p, m);
-        if (S > 1) d = ag_batch_segment(d, (uint32_t)(u - m * S), S, &after);
-        run_unit(u, m, d, after);
-    }
-}
-
-// One lane per unit id: R = sum_t Y_t H^(32-t) by a serial Horner over the dumped accumulators with
-// the H table, scaling by H^(blocks after the unit) (product of the H^(2^k) of the set bits), XOR
-// into the message's accumulator.
-__global__ void __launch_bounds__(128) k_batch_warp_reduce(const __grid_constant__ BatchParams p)
-{
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
-    fill_gh_tables(p.key->tab[0], nullptr);
-    __syncthreads();
-    GhSmem gh{ag_smem + SM_GH, (lane & 7) * 16};
-    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + tid;
-    if (id >= p.n_ids) return;
-    const uint64_t m1 = p.unit_desc[2 * id], after = p.unit_desc[2 * id + 1];
-    if (m1 == 0) return;
-    gf128 r = gf_zero();
-    const uint4* acc = p.seg_acc + id * 32;
-#pragma unroll 1
-    for (int t = 0; t < 32; ++t) {
-        const uint4 q = __ldcg(acc + t);
-        r.w[0] ^= q.x; r.w[1] ^= q.y; r.w[2] ^= q.z; r.w[3] ^= q.w;
-        r = gf_mul_table(r, gh);
-    }
-    if (after) {
-        gf128 f = gf_one();
-        bool first = true;
-#pragma unroll 1
-        for (int k = 0; k < 40; ++k)
-            if ((after >> k) & 1) {
-                f = first ? p.key->pow2[k] : gf_mul(f, p.key->pow2[k]);
-                first = false;
-            }
-        r = gf_mul(r, f);
-    }
-    uint32_t* dst = p.msg_acc + 4 * (m1 - 1);
-    atomicXor(dst + 0, r.w[0]); atomicXor(dst + 1, r.w[1]); atomicXor(dst + 2, r.w[2]); atomicXor(dst + 3, r.w[3]);
-}
-
-template <bool DEC>
-__global__ void k_batch_warp_finish(const __grid_constant__ BatchParams p)
-{
-    const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= p.n_msgs) return;
-    const uint4 r = *reinterpret_cast<const uint4*>(p.msg_acc + 4 * m);
-    const uint4 e = *reinterpret_cast<const uint4*>(p.msg_ej0 + 4 * m);
-    uint32_t tg[4] = {ag_bswap32(r.x) ^ e.x, ag_bswap32(r.y) ^ e.y, ag_bswap32(r.z) ^ e.z, ag_bswap32(r.w) ^ e.w};
-    uint8_t* tp = p.tag + 16 * m;
-    if (DEC) {
-        uint32_t x[4];
-        ag_load_block(tp, 16, x);
-        const uint32_t diff = (x[0] ^ tg[0]) | (x[1] ^ tg[1]) | (x[2] ^ tg[2]) | (x[3] ^ tg[3]);
-        p.ok[m] = diff ? 0 : 1;
     } else {
-        ag_store_block(tp, 16, tg);
+        const uint64_t n_units = p.n_msgs * S;
+        for (;;) {
+            uint32_t tk = 0;
+            if (lane == 0) tk = atomicAdd(p.ticket, 1u);
+            const uint64_t u = __shfl_sync(0xffffffffu, tk, 0);
+            if (u >= n_units) break;
+            const uint64_t m = u / S;
+            uint64_t after = 0;
+            MsgDesc d = ag_batch_msg(p, m);
+            if (S > 1) d = ag_batch_segment(d, (uint32_t)(u - m * S), S, &after);
+            run_unit(u, m, d, after);
+        }
     }
+    if (n_pend) combine();
 }
 
 // Tag finish of the split layout: one thread per message XORs its S scaled partials
@@ -1546,15 +1559,8 @@ template <int NR, bool DEC>
 static cudaError_t launch_batch_warp_t(const BatchParams& p, int ncta, cudaStream_t st)
 {
     cudaError_t e = cudaFuncSetAttribute(k_batch_warp<NR, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_batch_warp_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     k_batch_warp<NR, DEC><<<ncta, AG_STREAM_NT_MAX, kSmemBytes, st>>>(p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    k_batch_warp_reduce<<<(unsigned)((p.n_ids + 127) / 128), 128, kSmemBytes, st>>>(p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    k_batch_warp_finish<DEC><<<(unsigned)((p.n_msgs + 127) / 128), 128, 0, st>>>(p);
     return cudaGetLastError();
 }
 

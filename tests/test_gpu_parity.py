@@ -535,7 +535,7 @@ def test_batch_few_long_messages_auto_split(engine, oracle, torch_mod):
     before = engine.launch_count
     engine.batch_crypt_uniform_device(0, d_iv, d_aad, alen, alen, d_pt, d_ct, length, length, d_tags, n_msgs=n_msgs)
     torch.cuda.synchronize()
-    assert engine.launch_count - before == 3              # k_batch_warp (balanced units) + reduce + finish
+    assert engine.launch_count - before == 1              # k_batch_warp: balanced units, combine and tags in one launch
     for i in (0, 1, n_msgs // 2, n_msgs - 1):
         pt = d_pt[i * length:(i + 1) * length].cpu().numpy().tobytes()
         iv = d_iv[12 * i:12 * i + 12].cpu().numpy().tobytes()

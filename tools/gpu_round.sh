@@ -70,4 +70,16 @@ for s in $STEPS; do
         bench.py --gpus 2 --steps 30 --warmup 5 > $OUT/${TAG}_scale2.json 2> $OUT/${TAG}_scale2.err; echo "scale2 rc=$?"; cat $OUT/${TAG}_scale2.json; tail -5 $OUT/${TAG}_scale2.err ;;
   esac
 done
+# full ncu reports are 20-40 MB each and gpurun copies back at most 64 MiB: keep their raw pages and summaries
+for r in $OUT/${TAG}_prof*.ncu-rep; do
+  [ -f "$r" ] || continue
+  b=${r%.ncu-rep}
+  ncu -i $r --page raw --csv > $b.raw.csv 2>/dev/null
+  case $b in
+    *_prof) k=k_stream ;; *_prof_tile) k=k_batch_tile ;; *_prof_warp) k=k_batch_warp ;; *_prof_batch) k=k_batch ;; *_prof_perkey) k=k_batch_perkey ;; *) k=k_ ;;
+  esac
+  python tools/ncu_summary.py $r $k > $b.summary.md 2>/dev/null
+  [ "$k" = k_stream ] && python tools/ncu_json.py $r 1073741824 "gpurun_out/$(basename $b).raw.csv (ncu --set full --clock-control none, round 2)" > $b.json 2>/dev/null
+  [ -n "$KEEP_REP" ] || rm -f $r
+done
 echo "=== done ($(date +%T))"
