@@ -291,6 +291,7 @@ struct BatchParams {
     // uniform batches: static BALANCED partition -- warp w owns weight positions [w*quota, (w+1)*quota)
     // of the concatenated messages (ag_msg_weight each); 0 = units of `split` segments by ticket
     uint64_t quota;
+    uint32_t pt_weight;        // weight of a payload block on that axis (an AAD block weighs 1)
     uint64_t n_ids;            // unit ids in use: n_warps + n_msgs (balanced) or n_msgs * split (ticket)
 };
 
@@ -349,19 +350,20 @@ AG_HD void ag_batch_iv(const BatchParams& p, uint64_t m, uint32_t iv[3], uint32_
 // nothing; adjacent ranges share their boundary block index, so units tile a message exactly.
 constexpr uint64_t AG_FINISH_WEIGHT = 8;
 
-AG_HD uint64_t ag_msg_weight(uint64_t aad_len, uint64_t len)
+AG_HD uint64_t ag_msg_weight(uint64_t aad_len, uint64_t len, uint64_t ptw = 4)
 {
-    return ((aad_len + 15) >> 4) + 4 * ((len + 15) >> 4) + AG_FINISH_WEIGHT;
+    return ((aad_len + 15) >> 4) + ptw * ((len + 15) >> 4) + AG_FINISH_WEIGHT;
 }
 
-AG_HD MsgDesc ag_batch_range(const MsgDesc& w, uint64_t w0, uint64_t w1, uint64_t* after)
+// ptw = weight of a payload block (an AAD block weighs 1)
+AG_HD MsgDesc ag_batch_range(const MsgDesc& w, uint64_t w0, uint64_t w1, uint64_t* after, uint64_t ptw = 4)
 {
-    const uint64_t a = (w.aad_len + 15) >> 4, n = (w.len + 15) >> 4, tot = a + n, W = a + 4 * n;
+    const uint64_t a = (w.aad_len + 15) >> 4, n = (w.len + 15) >> 4, tot = a + n, W = a + ptw * n;
     const bool last = w1 >= W + AG_FINISH_WEIGHT;
     if (w0 > W) w0 = W;
     if (w1 > W) w1 = W;
-    uint64_t u0 = w0 <= a ? w0 : a + (w0 - a + 3) / 4;
-    uint64_t u1 = w1 <= a ? w1 : a + (w1 - a + 3) / 4;
+    uint64_t u0 = w0 <= a ? w0 : a + (w0 - a + ptw - 1) / ptw;
+    uint64_t u1 = w1 <= a ? w1 : a + (w1 - a + ptw - 1) / ptw;
     if (u0 > tot) u0 = tot;
     if (u1 > tot || last) u1 = tot;
     const uint64_t a0 = u0 < a ? u0 : a, a1 = u1 < a ? u1 : a;          // AAD blocks [a0, a1)
@@ -418,6 +420,42 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
     // that bulk AAD is not dragged through the AES-sized body of the general loop below.
     const uint32_t aad_rows = (uint32_t)(((uint64_t)a + pad) / G);
     uint32_t u = 0;
+#if defined(__CUDA_ARCH__)
+    // 16-byte aligned AAD: whole blocks move with one 128-bit load each, TWO rows ahead of the product
+    // that consumes them (a GHASH-only row is short: one row of prefetch does not cover a DRAM round trip)
+    if (aad_rows > 2 && ((uintptr_t)d.aad & 15) == 0) {
+        const uint32_t a_full = (uint32_t)(d.aad_len >> 4);   // blocks below this index are whole
+        auto ldq = [&](uint32_t bi) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (bi < a_full) {
+                v = *reinterpret_cast<const uint4*>(d.aad + 16 * (uint64_t)bi);
+            } else if (bi < a) {
+                uint32_t x[4];
+                ag_load_block(d.aad + 16 * (uint64_t)bi, atail, x);
+                v = make_uint4(x[0], x[1], x[2], x[3]);
+            }
+            return v;
+        };
+        uint4 q1 = ldq(i + G);   // row 1 (rows >= 1 never touch the front padding)
+        for (; u < aad_rows; ++u) {
+            const bool hv = have;
+            const uint32_t s0 = nxt[0], s1 = nxt[1], s2 = nxt[2], s3 = nxt[3];
+            nxt[0] = q1.x; nxt[1] = q1.y; nxt[2] = q1.z; nxt[3] = q1.w;
+            i += G;
+            have = true;
+            q1 = ldq(i + G);   // two rows ahead; past the AAD it returns zeros that are never used
+            if (u) y = gf_mul_table(y, gh_g);
+            if (hv) {
+                y.w[0] ^= ag_bswap32(s0);
+                y.w[1] ^= ag_bswap32(s1);
+                y.w[2] ^= ag_bswap32(s2);
+                y.w[3] ^= ag_bswap32(s3);
+            }
+        }
+        // hand over to the general loop with its one-row prefetch: nxt holds row aad_rows' AAD block (if it is one)
+        if (!(u < rows && i < a)) { nxt[0] = nxt[1] = nxt[2] = nxt[3] = 0; }
+    }
+#endif
     for (; u < aad_rows; ++u) {
         const bool hv = have;
         const uint32_t s0 = nxt[0], s1 = nxt[1], s2 = nxt[2], s3 = nxt[3];

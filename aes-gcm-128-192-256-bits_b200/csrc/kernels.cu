@@ -974,7 +974,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid
     uint32_t* pend = reinterpret_cast<uint32_t*>(ag_smem + SM_MISC + 1024) + warp * 16;
     uint32_t n_pend = 0;
     const uint32_t S = p.split;
-    const uint64_t wm = ag_msg_weight(p.aad ? p.aad_len : 0, p.len);
+    const uint64_t wm = ag_msg_weight(p.aad ? p.aad_len : 0, p.len, p.pt_weight);
 
     // One more unit of message m is done (combined, or a cut that owned no block); whoever completes
     // the count turns the accumulator into the tag.
@@ -1018,14 +1018,14 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid
                 r = gf_mul_table(r, gh_1);
             }
             if (after) {
+                // H^after left to right: a GF(2)-linear squaring (~130 integer ops) per bit and, for a set
+                // bit, one product with H through the shared table -- no generic products, no loads
                 gf128 f = gf_one();
-                bool first = true;
 #pragma unroll 1
-                for (int k = 0; k < 40; ++k)
-                    if ((after >> k) & 1) {
-                        f = first ? p.key->pow2[k] : gf_mul(f, p.key->pow2[k]);
-                        first = false;
-                    }
+                for (int k = 63 - __clzll((long long)after); k >= 0; --k) {
+                    f = gf_sqr(f);
+                    if ((after >> k) & 1) f = gf_mul_table(f, gh_1);
+                }
                 r = gf_mul(r, f);
             }
             uint32_t* dst = p.msg_acc + 4 * m;
@@ -1065,7 +1065,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid
         for (uint64_t m = g0 / wm; m * wm < g1; ++m) {   // uniform per warp
             const uint64_t lo = m * wm, r0 = (g0 > lo ? g0 : lo) - lo, r1 = (g1 < lo + wm ? g1 : lo + wm) - lo;
             uint64_t after = 0;
-            const MsgDesc d = ag_batch_range(ag_batch_msg(p, m), r0, r1, &after);
+            const MsgDesc d = ag_batch_range(ag_batch_msg(p, m), r0, r1, &after, p.pt_weight);
             if (!d.last && d.len == 0 && d.aad_len == 0) {   // a cut inside one block: nothing of it is mine
                 if (lane == 0) arrive(m);
                 continue;

@@ -751,6 +751,52 @@ def test_perkey_tile_tma_staged_records(engine, oracle, torch_mod, monkeypatch):
         assert (ok[bad] == 0).all() and int(ok.sum()) == n_msgs - bad.size
 
 
+def test_batch_bulk_aad_layouts(engine, oracle, torch_mod):
+    """Bulk AAD per message (the AAD-heavy end of BASELINE config 5) through every batch layout:
+    AAD-only rows run in their own loop with a two-row prefetch when the AAD is 16-byte aligned.
+    Ragged AAD tails, AAD that ends mid-row, payload shorter than a row, unaligned AAD pitch,
+    uniform (balanced warp units) and offset (ticketed segments) forms."""
+    torch = torch_mod
+    rng = np.random.default_rng(321)
+    for kb, n_msgs, length, alen, astride in ((16, 37, 1000, 16 * 700 + 5, 16 * 701), (32, 9, 16 * 64, 100000, 100000),
+                                              (24, 5, 0, 16 * 3000, 16 * 3000), (16, 12, 40, 16 * 96 + 1, 16 * 96 + 3),
+                                              (32, 3, 16 * 5000 + 3, 16 * 20000 + 9, 16 * 20001)):
+        key = _rb(rng, kb)
+        engine.set_key(key)
+        stride = (length + 15) & ~15
+        ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+        buf = rng.integers(0, 256, max(1, n_msgs * stride), dtype=np.uint8)
+        abuf = rng.integers(0, 256, n_msgs * astride, dtype=np.uint8)
+        packed = buf[:n_msgs * stride].reshape(n_msgs, max(stride, 1))[:, :length].reshape(-1).copy() if length else np.zeros(0, np.uint8)
+        apacked = abuf.reshape(n_msgs, astride)[:, :alen].reshape(-1).copy()
+        in_off = np.arange(n_msgs + 1, dtype=np.uint64) * length
+        aad_off = np.arange(n_msgs + 1, dtype=np.uint64) * alen
+        want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), kb, True, ivs, apacked, aad_off, packed, in_off,
+                                              threads=8)
+        d_in, d_aad, d_iv = _dev(torch, buf), _dev(torch, abuf), _dev(torch, ivs)
+        for lanes in (0, 4, 32, 1024, 1028, 4097, 4096 + 7):
+            d_out = torch.zeros_like(d_in)
+            d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+            engine.batch_crypt_uniform_device(0, d_iv, d_aad, alen, astride, d_in, d_out, length, stride, d_tags, n_msgs=n_msgs,
+                                              lanes=lanes)
+            torch.cuda.synchronize()
+            if length:
+                got = d_out.cpu().numpy()[:n_msgs * stride].reshape(n_msgs, stride)[:, :length].reshape(-1)
+                assert (got == want_ct[:n_msgs * length]).all(), (kb, alen, lanes)
+            assert (d_tags.cpu().numpy() == want_tags).all(), (kb, alen, lanes)
+        # offset form (packed buffers): ticketed segments
+        for lanes in (0, 4096 + 3):
+            d_out = torch.zeros(max(1, packed.size), dtype=torch.uint8, device="cuda")
+            d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+            engine.batch_crypt_device(0, d_iv, _dev(torch, apacked), torch.from_numpy(aad_off.astype(np.int64)).cuda(),
+                                      _dev(torch, packed) if length else d_out, torch.from_numpy(in_off.astype(np.int64)).cuda(),
+                                      d_out, d_tags, lanes=lanes, avg_len_hint=length + alen // 4)
+            torch.cuda.synchronize()
+            if length:
+                assert (d_out.cpu().numpy()[:packed.size] == want_ct[:packed.size]).all(), (kb, alen, lanes, "offsets")
+            assert (d_tags.cpu().numpy() == want_tags).all(), (kb, alen, lanes, "offsets")
+
+
 def test_batch_host_api_roundtrip(engine, oracle):
     rng = np.random.default_rng(9)
     key = _rb(rng, 32)

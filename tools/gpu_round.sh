@@ -29,6 +29,8 @@ for s in $STEPS; do
     perkey)
       timeout 600 python tools/bench_variants.py --only perkey > $OUT/${TAG}_perkey.log 2>&1; echo "perkey rc=$?"; cat $OUT/${TAG}_perkey.log
       AGCM_PERKEY_TILE=0 timeout 600 python tools/bench_variants.py --only perkey > $OUT/${TAG}_perkey_notile.log 2>&1; echo "perkey (no tile) rc=$?"; cat $OUT/${TAG}_perkey_notile.log ;;
+    probe)
+      for pad in 3 4 5 6 8; do echo "pt weight $pad"; AGCM_PT_WEIGHT=$pad timeout 300 python tools/probe_aad_heavy.py 0 2>&1 | tail -1; AGCM_PT_WEIGHT=$pad timeout 300 python tools/probe_aad_heavy.py 0 262144 4194304 2>&1 | tail -1; AGCM_PT_WEIGHT=$pad timeout 300 python tools/probe_aad_heavy.py 0 4194304 0 2>&1 | tail -1; done ;;
     sweep5)
       timeout 1500 python tools/sweep_config5.py --out $OUT/${TAG}_config5.json > $OUT/${TAG}_config5.log 2>&1; echo "sweep5 rc=$?"; tail -75 $OUT/${TAG}_config5.log ;;
     variants)
@@ -43,8 +45,10 @@ for s in $STEPS; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch_tile -s 2 -c 1 -f -o $OUT/${TAG}_prof_tile \
         python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_ncutile_run.log 2>&1; echo "ncutile rc=$?"; tail -3 $OUT/${TAG}_ncutile_run.log ;;
     ncuwarp)
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch_warp -s 1 -c 1 -f -o $OUT/${TAG}_prof_warp \
-        python tools/probe_aad_heavy.py > $OUT/${TAG}_ncuwarp_run.log 2>&1; echo "ncuwarp rc=$?"; tail -3 $OUT/${TAG}_ncuwarp_run.log ;;
+      timeout 900 ncu --set full --clock-control none -k regex:k_batch_warp -s 1 -c 1 -f -o $OUT/${TAG}_prof_warp \
+        python tools/probe_aad_heavy.py > $OUT/${TAG}_ncuwarp_run.log 2>&1; echo "ncuwarp rc=$?"; tail -3 $OUT/${TAG}_ncuwarp_run.log
+      timeout 900 ncu --set full --clock-control none -k regex:k_batch_warp -s 1 -c 1 -f -o $OUT/${TAG}_prof_warp2 \
+        python tools/probe_aad_heavy.py 0 262144 4194304 > $OUT/${TAG}_ncuwarp2_run.log 2>&1; echo "ncuwarp2 rc=$?"; tail -3 $OUT/${TAG}_ncuwarp2_run.log ;;
     ncubatch)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_batch -s 2 -c 1 -f -o $OUT/${TAG}_prof_batch \
         python tools/bench_variants.py --only packets --quick > $OUT/${TAG}_ncubatch_run.log 2>&1; echo "ncubatch rc=$?"; tail -3 $OUT/${TAG}_ncubatch_run.log ;;
@@ -76,7 +80,7 @@ for r in $OUT/${TAG}_prof*.ncu-rep; do
   b=${r%.ncu-rep}
   ncu -i $r --page raw --csv > $b.raw.csv 2>/dev/null
   case $b in
-    *_prof) k=k_stream ;; *_prof_tile) k=k_batch_tile ;; *_prof_warp) k=k_batch_warp ;; *_prof_batch) k=k_batch ;; *_prof_perkey) k=k_batch_perkey ;; *) k=k_ ;;
+    *_prof) k=k_stream ;; *_prof_tile) k=k_batch_tile ;; *_prof_warp|*_prof_warp2) k=k_batch_warp ;; *_prof_batch) k=k_batch ;; *_prof_perkey) k=k_batch_perkey ;; *) k=k_ ;;
   esac
   python tools/ncu_summary.py $r $k > $b.summary.md 2>/dev/null
   [ "$k" = k_stream ] && python tools/ncu_json.py $r 1073741824 "gpurun_out/$(basename $b).raw.csv (ncu --set full --clock-control none, round 2)" > $b.json 2>/dev/null
