@@ -1042,16 +1042,11 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
         int ncta_w = c->ncta;
         if (uniform) {
             const uint64_t warps = (uint64_t)ncta_w * per_cta;
-            // Weight of a payload block against an AAD block when warps doing either share an SM.  By pipe
-            // wavefronts it is 4 (AES-256: 269 vs 68 per row), but an AES row is a 14-round dependent chain
-            // and advances more slowly than its share: measured best 6 for AES-256 (tools/probe_aad_heavy.py
-            // with AGCM_PT_WEIGHT: 256 KiB + 4 MiB AAD messages 1395 -> 1582 GB/s), scaled with the round count.
-            p.pt_weight = (uint32_t)(c->nr / 2 - 1);
-            if (const char* e = getenv("AGCM_PT_WEIGHT")) p.pt_weight = (uint32_t)atol(e);   // tuning experiments
-            if (p.pt_weight < 1 || p.pt_weight > 64) p.pt_weight = 4;
-            const uint64_t total = ag_msg_weight(p.aad ? p.aad_len : 0, p.len, p.pt_weight) * (uint64_t)n_msgs;
-            p.quota = ((total + warps - 1) / warps + 32ull * p.pt_weight - 1) / (32ull * p.pt_weight) * (32ull * p.pt_weight);   // whole payload rows
-            p.n_ids = warps + n_msgs;
+            const uint64_t ax_a = p.aad ? (p.aad_len + 15) >> 4 : 0, ax_p = ((p.len + 15) >> 4) + AG_FINISH_WEIGHT;
+            p.quota_aad = ((ax_a * (uint64_t)n_msgs + warps - 1) / warps + 31) & ~31ull;   // whole rows
+            p.quota_pt = ((ax_p * (uint64_t)n_msgs + warps - 1) / warps + 31) & ~31ull;
+            if (!p.quota_aad) p.quota_aad = 32;
+            p.n_ids = 2 * (warps + n_msgs);
             p.split = 1;
         } else {
             p.split = (uint32_t)(g - 4096);

@@ -288,11 +288,12 @@ struct BatchParams {
     uint32_t* msg_acc;
     uint32_t* msg_cnt;         // units of message m combined so far (the last one writes the tag)
     uint32_t* msg_ej0;
-    // uniform batches: static BALANCED partition -- warp w owns weight positions [w*quota, (w+1)*quota)
-    // of the concatenated messages (ag_msg_weight each); 0 = units of `split` segments by ticket
-    uint64_t quota;
-    uint32_t pt_weight;        // weight of a payload block on that axis (an AAD block weighs 1)
-    uint64_t n_ids;            // unit ids in use: n_warps + n_msgs (balanced) or n_msgs * split (ticket)
+    // uniform batches: static BALANCED partition on two axes -- the AAD blocks of all messages laid end to
+    // end, and their payload blocks (+ AG_FINISH_WEIGHT positions per message for the length block and
+    // E_K(J0)); warp w owns positions [w*quota_aad, (w+1)*quota_aad) of the first and
+    // [w*quota_pt, (w+1)*quota_pt) of the second.  quota_pt == 0: units of `split` segments by ticket.
+    uint64_t quota_aad, quota_pt;
+    uint64_t n_ids;            // unit ids in use: 2 x (n_warps + n_msgs) (balanced) or n_msgs * split (ticket)
 };
 
 // One message, or one counter-range segment of it (ag_batch_segment).

@@ -944,11 +944,13 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_cta(const __grid_
 // Batched MID-SIZE and LONG messages under the shared key: one WARP per unit, where a unit is a
 // message or a counter-range part of it (ag_batch_range, the single-GPU form of the shards of
 // parallel.py).  Two ways of cutting:
-//   * uniform batches: a static BALANCED partition.  The messages are laid end to end on a weight
-//     axis (AAD block 1, payload block 4, finish 8) and warp w owns positions [w*quota, (w+1)*quota):
-//     every warp gets the same work to within a row, whatever the number and size of the messages,
-//     and there are at most n_warps + n_msgs units, so the per-unit overhead is paid once or twice
-//     per warp;
+//   * uniform batches: a static BALANCED partition.  The AAD blocks of all messages are laid end
+//     to end on one axis, their payload blocks (+ 8 positions per message for the length block and
+//     E_K(J0)) on a second one, and warp w owns the w-th equal share of EACH: every warp gets the
+//     same number of GHASH-only rows and the same number of AES rows to within one, whatever the
+//     number and size of the messages (a single weighted axis would hand some warps only AAD and
+//     others only payload, and those advance at different speeds next to each other: measured).
+//     At most 2 x (n_warps + n_msgs) units, so the per-unit overhead is paid a few times per warp;
 //   * offset (ragged) batches: `split` equal-work segments per message, handed out by ticket.
 // The per-unit epilogue is deferred: a warp DUMPS its 32 raw lane accumulators (512 B, coalesced).
 // The lane weights H^(32-t) -- one ~1100-instruction generic product per lane and unit when done in
@@ -974,13 +976,17 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid
     uint32_t* pend = reinterpret_cast<uint32_t*>(ag_smem + SM_MISC + 1024) + warp * 16;
     uint32_t n_pend = 0;
     const uint32_t S = p.split;
-    const uint64_t wm = ag_msg_weight(p.aad ? p.aad_len : 0, p.len, p.pt_weight);
+    const uint64_t ax_a = p.aad ? (p.aad_len + 15) >> 4 : 0;               // positions per message on the AAD axis
+    const uint64_t ax_p = ((p.len + 15) >> 4) + AG_FINISH_WEIGHT;            // ... and on the payload axis
 
     // One more unit of message m is done (combined, or a cut that owned no block); whoever completes
     // the count turns the accumulator into the tag.
     auto arrive = [&](uint64_t m) {
         uint32_t units = S;   // how many units the message was cut into
-        if (p.quota) units = (uint32_t)(((m + 1) * wm - 1) / p.quota - (m * wm) / p.quota + 1);
+        if (p.quota_pt) {
+            units = (uint32_t)(((m + 1) * ax_p - 1) / p.quota_pt - (m * ax_p) / p.quota_pt + 1);
+            if (ax_a) units += (uint32_t)(((m + 1) * ax_a - 1) / p.quota_aad - (m * ax_a) / p.quota_aad + 1);
+        }
         __threadfence();
         const uint32_t done = atomicAdd(p.msg_cnt + m, 1u) + 1;
         if (done != units) return;
@@ -1056,21 +1062,25 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_warp(const __grid
         if (++n_pend == 16) combine();
     };
 
-    if (p.quota) {
+    if (p.quota_pt) {
         const uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-        const uint64_t total = wm * p.n_msgs;
-        const uint64_t g0 = w * p.quota;
-        uint64_t g1 = g0 + p.quota;
-        if (g1 > total) g1 = total;
-        for (uint64_t m = g0 / wm; m * wm < g1; ++m) {   // uniform per warp
-            const uint64_t lo = m * wm, r0 = (g0 > lo ? g0 : lo) - lo, r1 = (g1 < lo + wm ? g1 : lo + wm) - lo;
-            uint64_t after = 0;
-            const MsgDesc d = ag_batch_range(ag_batch_msg(p, m), r0, r1, &after, p.pt_weight);
-            if (!d.last && d.len == 0 && d.aad_len == 0) {   // a cut inside one block: nothing of it is mine
-                if (lane == 0) arrive(m);
-                continue;
+        const uint64_t id_half = (uint64_t)gridDim.x * (blockDim.x >> 5) + p.n_msgs;
+        // axis 0: AAD blocks (positions 0 .. a of a message), axis 1: payload blocks + finish (positions a .. )
+        for (int axis = ax_a ? 0 : 1; axis < 2; ++axis) {
+            const uint64_t per = axis ? ax_p : ax_a, quota = axis ? p.quota_pt : p.quota_aad, total = per * p.n_msgs;
+            const uint64_t g0 = w * quota;
+            uint64_t g1 = g0 + quota;
+            if (g1 > total) g1 = total;
+            for (uint64_t m = g0 / per; m * per < g1; ++m) {   // uniform per warp
+                const uint64_t lo = m * per, r0 = (g0 > lo ? g0 : lo) - lo, r1 = (g1 < lo + per ? g1 : lo + per) - lo;
+                uint64_t after = 0;
+                const MsgDesc d = ag_batch_range(ag_batch_msg(p, m), axis ? ax_a + r0 : r0, axis ? ax_a + r1 : r1, &after, 1);
+                if (!d.last && d.len == 0 && d.aad_len == 0) {   // a cut inside the finish positions: no block of it is mine
+                    if (lane == 0) arrive(m);
+                    continue;
+                }
+                run_unit((axis ? id_half : 0) + w + m, m, d, after);
             }
-            run_unit(w + m, m, d, after);
         }
     } else {
         const uint64_t n_units = p.n_msgs * S;

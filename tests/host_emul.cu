@@ -204,7 +204,7 @@ void perkey_nk(const BatchParams& p)
 }  // namespace
 
 // k_batch_warp's BALANCED partition on a virtual grid of n_warps warps (uniform records): warp w
-// owns weight positions [w*quota, (w+1)*quota) of the concatenated messages; every unit's 32 lane
+// owns the w-th equal share of the AAD axis and of the payload axis of the concatenated messages; every unit's 32 lane
 // accumulators are combined as k_batch_warp_reduce does (serial Horner with H, times H^after) and
 // XORed into the message accumulator; k_batch_warp_finish's tag step at the end.
 template <int NR, bool DEC>
@@ -215,37 +215,49 @@ static void batch_balanced_nr(const BatchParams& p, uint32_t n_warps, const gf12
     build_table(H, tab_1);
     TeHost te{tables().te0};
     GhHost gh_g{tab_g.data()}, gh_1{tab_1.data()};
-    const uint64_t wm = ag_msg_weight(p.aad ? p.aad_len : 0, p.len), total = wm * p.n_msgs;
-    const uint64_t quota = ((total + n_warps - 1) / n_warps + 127) & ~127ull;
+    const uint64_t ax_a = p.aad ? (p.aad_len + 15) >> 4 : 0, ax_p = ((p.len + 15) >> 4) + AG_FINISH_WEIGHT;
+    uint64_t quota_aad = ((ax_a * p.n_msgs + n_warps - 1) / n_warps + 31) & ~31ull;
+    const uint64_t quota_pt = ((ax_p * p.n_msgs + n_warps - 1) / n_warps + 31) & ~31ull;
+    if (!quota_aad) quota_aad = 32;
     std::vector<gf128> acc(p.n_msgs, gf_zero());
     std::vector<uint32_t> ej0(4 * p.n_msgs, 0);
-    std::vector<int> closed(p.n_msgs, 0);
+    std::vector<int> closed(p.n_msgs, 0), arrived(p.n_msgs, 0);
     for (uint64_t w = 0; w < n_warps; ++w) {
-        const uint64_t g0 = w * quota;
-        uint64_t g1 = g0 + quota;
-        if (g1 > total) g1 = total;
-        for (uint64_t m = g0 / wm; m * wm < g1; ++m) {
-            const uint64_t lo = m * wm, r0 = (g0 > lo ? g0 : lo) - lo, r1 = (g1 < lo + wm ? g1 : lo + wm) - lo;
-            uint64_t after = 0;
-            MsgDesc d = ag_batch_range(ag_batch_msg(p, m), r0, r1, &after);
-            if (!d.last && d.len == 0 && d.aad_len == 0) continue;
-            const uint8_t* ivp = p.iv + 12 * m;
-            uint32_t iv[3] = {0, 0, 0};
-            for (int j = 0; j < 12; ++j) iv[j >> 2] |= (uint32_t)ivp[j] << (8 * (j & 3));
-            const AesCtrConst cc = aes_ctr_precompute(p.rk, iv[0], iv[1], iv[2], te);
-            gf128 r = gf_zero();
-            for (uint32_t t = 0; t < 32; ++t) {
-                AesCtrSeqCache cache;
-                cache.key = 0xFFFFFFFFu;
-                uint32_t el[4] = {0, 0, 0, 0};
-                gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, 32u, te, gh_g, el);
-                if (t == 31 && d.last) { memcpy(&ej0[4 * m], el, 16); closed[m]++; }
-                r = gf_xor(r, y);
-                r = gf_mul_table(r, gh_1);
+        for (int axis = ax_a ? 0 : 1; axis < 2; ++axis) {
+            const uint64_t per = axis ? ax_p : ax_a, quota = axis ? quota_pt : quota_aad, total = per * p.n_msgs;
+            const uint64_t g0 = w * quota;
+            uint64_t g1 = g0 + quota;
+            if (g1 > total) g1 = total;
+            for (uint64_t m = g0 / per; m * per < g1; ++m) {
+                const uint64_t lo = m * per, r0 = (g0 > lo ? g0 : lo) - lo, r1 = (g1 < lo + per ? g1 : lo + per) - lo;
+                uint64_t after = 0;
+                MsgDesc d = ag_batch_range(ag_batch_msg(p, m), axis ? ax_a + r0 : r0, axis ? ax_a + r1 : r1, &after, 1);
+                arrived[m]++;
+                if (!d.last && d.len == 0 && d.aad_len == 0) continue;
+                const uint8_t* ivp = p.iv + 12 * m;
+                uint32_t iv[3] = {0, 0, 0};
+                for (int j = 0; j < 12; ++j) iv[j >> 2] |= (uint32_t)ivp[j] << (8 * (j & 3));
+                const AesCtrConst cc = aes_ctr_precompute(p.rk, iv[0], iv[1], iv[2], te);
+                gf128 r = gf_zero();
+                for (uint32_t t = 0; t < 32; ++t) {
+                    AesCtrSeqCache cache;
+                    cache.key = 0xFFFFFFFFu;
+                    uint32_t el[4] = {0, 0, 0, 0};
+                    gf128 y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, 32u, te, gh_g, el);
+                    if (t == 31 && d.last) { memcpy(&ej0[4 * m], el, 16); closed[m]++; }
+                    r = gf_xor(r, y);
+                    r = gf_mul_table(r, gh_1);
+                }
+                if (after) r = gf_mul(r, gf_pow(H, after));
+                acc[m] = gf_xor(acc[m], r);
             }
-            if (after) r = gf_mul(r, gf_pow(H, after));
-            acc[m] = gf_xor(acc[m], r);
         }
+    }
+    // the kernel's count of units per message (arrive) must agree with the pairs actually visited
+    for (uint64_t m = 0; m < p.n_msgs; ++m) {
+        uint64_t units = ((m + 1) * ax_p - 1) / quota_pt - (m * ax_p) / quota_pt + 1;
+        if (ax_a) units += ((m + 1) * ax_a - 1) / quota_aad - (m * ax_a) / quota_aad + 1;
+        if (units != (uint64_t)arrived[m]) closed[m] = -1;
     }
     for (uint64_t m = 0; m < p.n_msgs; ++m) {
         const gf128 r = acc[m];
