@@ -363,7 +363,7 @@ int ensure_pipeline(agcm_ctx* c)
     return AGCM_OK;
 }
 
-int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, bool aligned16 = true)
+int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, bool aligned16 = true, uint64_t real_blocks = 0)
 {
     if (lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32) return lanes;
     if (lanes > 4096 && lanes <= 4096 + 65536) return lanes;  // one warp per 1/S of a message (k_batch_warp), S = lanes - 4096
@@ -382,7 +382,11 @@ int pick_lanes(const agcm_ctx* c, int lanes, uint64_t n_msgs, uint64_t avg_len, 
     // lane combine deferred to a second launch.  A unit is a message or one of S counter-range
     // segments of it; S keeps a unit near 64-256 rows of 32 blocks and gives every warp at least ~8
     // units to draw, so neither the per-unit overhead (a row or two) nor the tail matters.
-    if (blocks >= 2048 && !getenv("AGCM_NO_WARP_UNITS")) {
+    // (uniform batches say how many blocks a message really has, AAD included: bulk AAD counts in full here,
+    // although it only weighs a quarter in `avg_len`)
+    uint64_t warp_min = 2048;
+    if (const char* e = getenv("AGCM_WARP_MIN_BLOCKS")) warp_min = (uint64_t)atol(e);   // tuning experiments
+    if ((blocks >= warp_min || real_blocks >= warp_min) && !getenv("AGCM_NO_WARP_UNITS")) {
         // S only matters for offset batches (uniform ones are partitioned exactly): near 128 rows of
         // 32 blocks per unit, and at least ~16 units per warp to draw when the messages are few
         const uint64_t warps = total_lanes / 32;
@@ -1027,7 +1031,8 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
     if (!c->key_set) return AGCM_E_NO_KEY;
     if (n_msgs == 0) return AGCM_OK;
     if (!p.iv || !p.tag || (decrypt && !p.ok)) return AGCM_E_BAD_ARG;
-    const int g = pick_lanes(c, lanes, n_msgs, avg_len, aligned16);
+    const uint64_t real_blocks = (!p.in_off && !p.aad_off) ? ((p.len + 15) >> 4) + (p.aad ? (p.aad_len + 15) >> 4 : 0) : 0;
+    const int g = pick_lanes(c, lanes, n_msgs, avg_len, aligned16, real_blocks);
     if (g < 0) return AGCM_E_BAD_ARG;
     AG_CUDA(c, cudaSetDevice(c->device));
     memcpy(p.rk, c->h_rk, sizeof(p.rk));

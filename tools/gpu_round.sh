@@ -30,7 +30,10 @@ for s in $STEPS; do
       timeout 600 python tools/bench_variants.py --only perkey > $OUT/${TAG}_perkey.log 2>&1; echo "perkey rc=$?"; cat $OUT/${TAG}_perkey.log
       AGCM_PERKEY_TILE=0 timeout 600 python tools/bench_variants.py --only perkey > $OUT/${TAG}_perkey_notile.log 2>&1; echo "perkey (no tile) rc=$?"; cat $OUT/${TAG}_perkey_notile.log ;;
     probe)
-      for pad in 3 4 5 6 8; do echo "pt weight $pad"; AGCM_PT_WEIGHT=$pad timeout 300 python tools/probe_aad_heavy.py 0 2>&1 | tail -1; AGCM_PT_WEIGHT=$pad timeout 300 python tools/probe_aad_heavy.py 0 262144 4194304 2>&1 | tail -1; AGCM_PT_WEIGHT=$pad timeout 300 python tools/probe_aad_heavy.py 0 4194304 0 2>&1 | tail -1; done ;;
+      for v in 256 512 1024 2048; do echo "warp min blocks $v"; for sz in "1024 16384" "16384 0" "8192 0" "4096 0" "16384 16384" "4096 65536"; do AGCM_WARP_MIN_BLOCKS=$v timeout 300 python tools/probe_aad_heavy.py 0 $sz 2>&1 | tail -1; done; done ;;
+    hybrid)
+      nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I include -o /tmp/hybrid_probe tools/hybrid_probe.cu -L aes-gcm-128-192-256-bits_b200 -laesgcm_b200 -Xlinker -rpath=$PWD/aes-gcm-128-192-256-bits_b200 > $OUT/${TAG}_hybrid.log 2>&1
+      timeout 300 /tmp/hybrid_probe >> $OUT/${TAG}_hybrid.log 2>&1; echo "hybrid rc=$?"; cat $OUT/${TAG}_hybrid.log ;;
     sweep5)
       timeout 1500 python tools/sweep_config5.py --out $OUT/${TAG}_config5.json > $OUT/${TAG}_config5.log 2>&1; echo "sweep5 rc=$?"; tail -75 $OUT/${TAG}_config5.log ;;
     variants)

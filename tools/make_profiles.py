@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
 tag = sys.argv[1] if len(sys.argv) > 1 else "fin"
+RND = sys.argv[2] if len(sys.argv) > 2 else "r1"   # file-name prefix of the round
 
 
 def jl(path):
@@ -47,7 +48,7 @@ def lane_sweep():
             "used to combine their lanes with G-1 serial table products on the lookup pipe; they now apply one generic product per",
             "lane on the integer pipe and a butterfly XOR (64 KiB: 473 -> 497 GB/s; 1500 B with 32 lanes: 137 -> 315). `k_batch_cta`",
             "uses the stream kernel's counter-byte cache (its lanes step the counter by 512): 1 MiB messages 479 -> 498 GB/s."]
-    open(os.path.join(PROF, "r1_lane_sweep.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(PROF, RND + "_lane_sweep.md"), "w").write("\n".join(out) + "\n")
 
 
 def kernel_table():
@@ -70,18 +71,18 @@ def kernel_table():
                                                       r["aes"], r["ms"], r["Mkeys_per_s"] / 1000, r["GBps"]))
     sk = sum(r["set_key_us"] for r in keys) / max(1, len(keys))
     out += ["", "`agcm_set_key` (one launch: key schedule + H + 63 linear squarings `gf_sqr` + power tables + Shoup tables, one 272 B readback, synchronous): ~%.0f µs per key (was ~215 µs with two launches, three copies and bit-serial squarings)." % sk]
-    open(os.path.join(PROF, "r1_kernel_table.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(PROF, RND + "_kernel_table.md"), "w").write("\n".join(out) + "\n")
 
 
 def config5():
-    src = os.path.join(OUT, "config5.json")
-    shutil.copy(src, os.path.join(PROF, "r1_config5_sweep.json"))
+    src = os.path.join(OUT, tag + "_config5.json") if os.path.exists(os.path.join(OUT, tag + "_config5.json")) else os.path.join(OUT, "config5.json")
+    shutil.copy(src, os.path.join(PROF, RND + "_config5_sweep.json"))
     rows = json.load(open(src))
     ratios = ["0", "1/16", "1/4", "1", "4", "16"]
     out = ["# BASELINE config 5: message size x AAD/PT ratio (tools/sweep_config5.py, final build)", "",
            "(PT + AAD) GB/s, about 1 GiB per point, device-resident inputs, CUDA events; `s` marks points that ran as one stream",
            "call per message (up to four messages in all), every other point is ONE batch call. Raw rows with payload-only rates:",
-           "`profiles/r1_config5_sweep.json`.", ""]
+           "`profiles/%s_config5_sweep.json`." % RND, ""]
     for aes in (128, 256):
         out += ["## AES-%d" % aes, "", "| message \\ AAD:PT | " + " | ".join(ratios) + " |", "|---|" + "---|" * len(ratios)]
         sizes = sorted({r["msg_bytes"] for r in rows})
@@ -89,11 +90,11 @@ def config5():
             rs = sorted([r for r in rows if r["aes"] == aes and r["msg_bytes"] == sz], key=lambda r: r["aad_bytes"])
             out.append("| %d B | " % sz + " | ".join("%.0f%s" % (r["pt_plus_aad_GBps"], " s" if r["api"] == "stream" else "") for r in rs) + " |")
         out.append("")
-    open(os.path.join(PROF, "r1_config5_sweep.md"), "w").write("\n".join(out))
+    open(os.path.join(PROF, RND + "_config5_sweep.md"), "w").write("\n".join(out))
 
 
 if __name__ == "__main__":
     for fn, need in ((lane_sweep, "lane_sweep.jsonl"), (kernel_table, tag + "_variants.log"), (config5, "config5.json")):
-        if os.path.exists(os.path.join(OUT, need)):
+        if os.path.exists(os.path.join(OUT, need)) or (fn is config5 and os.path.exists(os.path.join(OUT, tag + "_config5.json"))):
             fn()
             print("wrote", fn.__name__)

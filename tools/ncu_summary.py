@@ -22,7 +22,7 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 
 rep, pat = sys.argv[1], sys.argv[2]
 title = sys.argv[3] if len(sys.argv) > 3 else pat
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out[out.index('"ID"'):])))
 hdr, units, data = rows[0], rows[1], rows[2:]
 ki = hdr.index('Kernel Name')
