@@ -72,6 +72,11 @@ for s in $STEPS; do
         bench.py --impl reference --gpus 8 --steps 2 --warmup 1 > $OUT/${TAG}_ref8.json 2> $OUT/${TAG}_ref8.err; echo "ref8 rc=$?"; cat $OUT/${TAG}_ref8.json; tail -3 $OUT/${TAG}_ref8.err ;;
     racecheck)
       timeout 900 compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -8 $OUT/${TAG}_racecheck.log ;;
+    pcie8|pcie4|pcie2)
+      N=${s#pcie}
+      nvidia-smi topo -m > $OUT/${TAG}_topo.txt 2>&1
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2956$N \
+        tools/bench_pcie_multi.py > $OUT/${TAG}_pcie$N.json 2> $OUT/${TAG}_pcie$N.err; echo "pcie$N rc=$?"; cat $OUT/${TAG}_pcie$N.json; tail -3 $OUT/${TAG}_pcie$N.err ;;
     scale2)
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
         bench.py --gpus 2 --steps 30 --warmup 5 > $OUT/${TAG}_scale2.json 2> $OUT/${TAG}_scale2.err; echo "scale2 rc=$?"; cat $OUT/${TAG}_scale2.json; tail -5 $OUT/${TAG}_scale2.err ;;
