@@ -1158,7 +1158,7 @@ static bool tile_eligible(const agcm_ctx* c, int lanes, const BatchParams& p, si
     if ((((uintptr_t)p.in | (uintptr_t)p.out) & 15) || (p.stride & 15) || p.stride >= (1ull << 40)) return false;
     if (lanes == 2048) return true;
     if (getenv("AGCM_NO_TILE")) return false;
-    return p.len + p.aad_len <= 16384 && n_msgs >= (size_t)c->ncta * (size_t)c->nt * 2;
+    return p.len + p.aad_len <= 16384 && n_msgs >= (size_t)c->ncta * (size_t)c->nt;   // at least a group of 32 per warp
 }
 
 static int batch_tile(agcm_ctx* c, int decrypt, BatchParams& p, size_t n_msgs, cudaStream_t st)
