@@ -326,10 +326,12 @@ def expected_aesgcm(key, iv, aad, pt):
         return ct, tag, "oracle/gcm_oracle.c"
 
 
-def batched_split(eng, torch, dist, dev, rank, world, iters=5):
-    """BASELINE configs 3 and 4 with the 2^20 messages split over the ranks (parallel.batch_split):
+def batched_split(eng, torch, dist, dev, rank, world, iters=5, weak=False):
+    """BASELINE configs 3 and 4 with the messages split over the ranks (parallel.batch_split):
     independent messages, NO collective on the data path.  Device-resident, CUDA events, max over
-    ranks.  Three messages per rank are checked against OpenSSL before timing."""
+    ranks.  Three messages per rank are checked against OpenSSL before timing.
+    weak=False: the 2^20 messages of the config over all ranks (strong scaling: 2^20 / N per GPU);
+    weak=True: 2^20 messages PER GPU (the batch grows with the machine)."""
     from aesgcm_b200.parallel import batch_split
 
     def timeit(fn):
@@ -357,7 +359,7 @@ def batched_split(eng, torch, dist, dev, rank, world, iters=5):
         return ct, tag
 
     res = []
-    n_total, length, stride = 1 << 20, 1500, 1504
+    n_total, length, stride = (1 << 20) * (world if weak else 1), 1500, 1504
     lo, hi = batch_split(n_total, world, rank)
     n_msgs = hi - lo
     rng = np.random.default_rng(2)
@@ -383,8 +385,10 @@ def batched_split(eng, torch, dist, dev, rank, world, iters=5):
         assert d_tags[16 * m:16 * m + 16].cpu().numpy().tobytes() == tag, "config 3: tag differs from OpenSSL"
         checked += 1
     ms = timeit(run3)
-    res.append({"workload": "config 3: AES-192 encrypt+tag, 2^20 x 1500 B at a 1504 B stride, per-message IV, shared "
-                            "pre-expanded key; messages split over %d rank(s), no collective" % world,
+    shape = "%d x 2^20" % world if weak else "2^20"
+    res.append({"workload": "config 3: AES-192 encrypt+tag, %s x 1500 B at a 1504 B stride, per-message IV, shared "
+                            "pre-expanded key; messages split over %d rank(s), no collective" % (shape, world),
+                "scaling": "weak" if weak else "strong",
                 "ms": round(ms, 4), "payload_GBps": round(n_total * length / ms / 1e6, 1),
                 "msgs_per_rank": n_msgs, "openssl_checked_msgs_per_rank": checked})
     del d_buf, d_out
@@ -414,8 +418,10 @@ def batched_split(eng, torch, dist, dev, rank, world, iters=5):
     want_ok[bad] = 0
     assert torch.equal(d_ok, want_ok), "config 4: ok flags do not match the corrupted tags"
     assert torch.equal(d_back.view(n_msgs, stride)[:, :length], d_pt.view(n_msgs, stride)[:, :length]), "config 4 round trip failed"
-    res.append({"workload": "config 4: AES-256 decrypt+verify, 2^20 x 1500 B at a 1504 B pitch, distinct key per message (schedule "
-                            "on device), 64 B AAD, 0.1 %% of the tags corrupted; messages split over %d rank(s), no collective" % world,
+    res.append({"workload": "config 4: AES-256 decrypt+verify, %s x 1500 B at a 1504 B pitch, distinct key per message (schedule "
+                            "on device), 64 B AAD, 0.1 %% of the tags corrupted; messages split over %d rank(s), no collective"
+                            % (shape, world),
+                "scaling": "weak" if weak else "strong",
                 "ms": round(ms, 4), "payload_GBps": round(n_total * length / ms / 1e6, 1),
                 "Mmsg_per_s": round(n_total / ms / 1e3, 1), "msgs_per_rank": n_msgs, "openssl_checked_msgs_per_rank": 3,
                 "bad_tags_per_rank": int(bad.numel())})
@@ -602,6 +608,8 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_extras:
         try:
             batched = batched_split(eng, torch, dist, dev, rank, world)
+            if world > 1:
+                batched += batched_split(eng, torch, dist, dev, rank, world, weak=True)
         except AssertionError:
             raise
         except Exception as ex:  # never lose the headline line over a secondary measurement
