@@ -88,7 +88,8 @@ struct agcm_ctx {
     uint8_t* d_chunk_partials = nullptr;
     uint8_t* d_aad_stage = nullptr;
     size_t aad_stage_cap = 0;
-    uint32_t* d_tile_ticket = nullptr;   // k_batch_tile: next group of 32 messages (zeroed before each launch)
+    uint32_t* d_tile_ticket = nullptr;   // k_batch_tile / _warp / _cta: next unit (zeroed before each launch)
+    bool no_ticket = false;              // set while the host batch pipeline runs chunks on several streams at once
     void* tmap_encode = nullptr;         // cuTensorMapEncodeTiled, resolved through the runtime (no link-time libcuda)
     uint8_t* d_verify = nullptr;     // whole ciphertext of a verify-then-release host decrypt, grown on demand
     size_t verify_cap = 0;
@@ -1104,7 +1105,7 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
             p.seg_parts = c->d_seg_parts;
         }
         const int ncta_m = (int)(n_units < (uint64_t)c->ncta ? n_units : (uint64_t)c->ncta);
-        if (n_units > (uint64_t)ncta_m && n_units < 0xFFFFFFFFull) {   // more units than CTAs: hand them out dynamically
+        if (n_units > (uint64_t)ncta_m && n_units < 0xFFFFFFFFull && !c->no_ticket) {   // more units than CTAs: hand them out dynamically
             if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
             AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
             p.ticket = c->d_tile_ticket;
@@ -1695,6 +1696,12 @@ int agcm_batch_crypt_uniform_host(agcm_ctx* c, int decrypt, int lanes, const uin
     // partials in one scratch buffer per context: whole-message layouts only on this path
     if (g > 4096) g = 32;     // (the warp-unit layout as well)
     if (g > 1024) g = 1024;
+    // (and no ticket-driven distribution: the context has ONE ticket word)
+    struct NoTicket {
+        agcm_ctx* c;
+        explicit NoTicket(agcm_ctx* ctx) : c(ctx) { c->no_ticket = true; }
+        ~NoTicket() { c->no_ticket = false; }
+    } no_ticket_scope(c);
     uint64_t k = 0;
     for (uint64_t m0 = 0; m0 < n_msgs; m0 += m_chunk, ++k) {
         const int s = (int)(k % kSlots);

@@ -820,6 +820,19 @@ def test_batch_host_api_roundtrip(engine, oracle):
     engine.crypt_batch_uniform_host(1, ivs, aad, alen, alen, out, back, length, stride, tags, ok)
     assert (back.reshape(n_msgs, stride)[:, :length] == data.reshape(n_msgs, stride)[:, :length]).all()
     assert ok.sum() == n_msgs - 1 and ok[5] == 0
+    # long records through the host pipeline: several chunks in flight on the library's streams at once, one CTA per
+    # message inside each (the chunks must not share a work ticket)
+    n_msgs, length = 700, 128 * 1024
+    ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+    data = rng.integers(0, 256, n_msgs * length, dtype=np.uint8)
+    out = np.zeros_like(data)
+    tags = np.zeros(16 * n_msgs, np.uint8)
+    engine.crypt_batch_uniform_host(0, ivs, None, 0, 0, data, out, length, length, tags, lanes=1024)
+    AESGCM = pytest.importorskip("cryptography.hazmat.primitives.ciphers.aead").AESGCM
+    a = AESGCM(key)
+    for i in list(range(0, n_msgs, 37)) + [n_msgs - 1]:
+        ref = a.encrypt(ivs[12 * i:12 * i + 12].tobytes(), data[i * length:(i + 1) * length].tobytes(), None)
+        assert ref[:-16] == out[i * length:(i + 1) * length].tobytes() and ref[-16:] == tags[16 * i:16 * i + 16].tobytes(), i
 
 
 def test_config4_perkey_decrypt_verify(engine, oracle, torch_mod):

@@ -70,6 +70,10 @@ for s in $STEPS; do
     refN8)
       timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29549 \
         bench.py --impl reference --gpus 8 --steps 2 --warmup 1 > $OUT/${TAG}_ref8.json 2> $OUT/${TAG}_ref8.err; echo "ref8 rc=$?"; cat $OUT/${TAG}_ref8.json; tail -3 $OUT/${TAG}_ref8.err ;;
+    sanitize2)
+      timeout 1700 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -q -x --timeout 1600 -k "tile or bulk_aad or peer_exchange_single or fails_closed or verified or long_iv_shard or few_long or split_over_ranks" > $OUT/${TAG}_sanitize2.log 2>&1; echo "sanitize2 rc=$?"; tail -12 $OUT/${TAG}_sanitize2.log ;;
+    racecheck2)
+      timeout 1700 compute-sanitizer --tool racecheck python -m pytest tests -m gpu -q -x --timeout 1600 -k "tile or bulk_aad or few_long" > $OUT/${TAG}_racecheck2.log 2>&1; echo "racecheck2 rc=$?"; tail -12 $OUT/${TAG}_racecheck2.log ;;
     racecheck)
       timeout 900 compute-sanitizer --tool racecheck python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -8 $OUT/${TAG}_racecheck.log ;;
     pcie8|pcie4|pcie2)
