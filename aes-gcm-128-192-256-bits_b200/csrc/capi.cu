@@ -1,6 +1,6 @@
 // C ABI of the engine (include/aesgcm_b200.h).  Host-side glue only: argument
 // checks, kernel parameter blocks, scratch buffers, and the chunked
-// host<->device pipeline.  All arithmetic happens in kernels.cu; there is no
+// host<->device pipeline.  All arithmetic happens in the kernels (kernels*.cu); there is no
 // CPU implementation of the datapath in this library.
 #include <cuda.h>
 #include <cuda_runtime.h>

@@ -1,6 +1,6 @@
 // Per-thread AES-GCM work items, written once as host+device code.
 //
-// The CUDA kernels in kernels.cu call these with shared-memory lookup functors;
+// The CUDA kernels (kernels*.cu) call these with shared-memory lookup functors;
 // tests/host_emul.cu calls the SAME functions on the CPU with plain-array
 // functors and loops over "threads" to check the index arithmetic (front
 // padding, strided Horner weights, partial last block) against the oracle

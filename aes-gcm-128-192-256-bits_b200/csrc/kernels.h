@@ -1,4 +1,4 @@
-// Internal launcher interface between kernels.cu and capi.cu (not installed).
+// Internal launcher interface between the kernel translation units (kernels*.cu) and capi.cu (not installed).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
