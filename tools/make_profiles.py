@@ -81,7 +81,7 @@ def config5():
     ratios = ["0", "1/16", "1/4", "1", "4", "16"]
     out = ["# BASELINE config 5: message size x AAD/PT ratio (tools/sweep_config5.py, final build)", "",
            "(PT + AAD) GB/s, about 1 GiB per point, device-resident inputs, CUDA events; `s` marks points that ran as one stream",
-           "call per message (up to four messages in all), every other point is ONE batch call. Raw rows with payload-only rates:",
+           "call (a single message), every other point is ONE batch call. Raw rows with payload-only rates:",
            "`profiles/%s_config5_sweep.json`." % RND, ""]
     for aes in (128, 256):
         out += ["## AES-%d" % aes, "", "| message \\ AAD:PT | " + " | ".join(ratios) + " |", "|---|" + "---|" * len(ratios)]
