@@ -42,7 +42,7 @@ def main():
                 d_aad = torch.randint(0, 256, (max(1, n_msgs * astride),), dtype=torch.uint8, device="cuda")
                 d_iv = torch.randint(0, 256, (n_msgs * 12,), dtype=torch.uint8, device="cuda")
                 d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
-                # up to four huge messages: one stream call each (the grid-wide kernel); everything else is ONE
+                # a single huge message: one stream call (the grid-wide kernel); everything else is ONE
                 # batch call -- the library cuts few long messages (bulk AAD included) into per-CTA segments
                 use_stream = n_msgs <= 1   # (round 1: <= 4; the balanced warp-unit layout now does better on 2-4 messages)
 
