@@ -94,7 +94,7 @@ _lib = None
 def build(verbose=False):
     """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     out = None if verbose else subprocess.DEVNULL
-    subprocess.check_call(["make", "-C", CSRC], stdout=out)
+    subprocess.check_call(["make", "-j", str(min(4, os.cpu_count() or 1)), "-C", CSRC], stdout=out)
     return SO_PATH
 
 

@@ -72,6 +72,8 @@ for s in $STEPS; do
         bench.py --impl reference --gpus 8 --steps 2 --warmup 1 > $OUT/${TAG}_ref8.json 2> $OUT/${TAG}_ref8.err; echo "ref8 rc=$?"; cat $OUT/${TAG}_ref8.json; tail -3 $OUT/${TAG}_ref8.err ;;
     sanitize2)
       timeout 1700 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -q -x --timeout 1600 -k "tile or bulk_aad or peer_exchange_single or fails_closed or verified or long_iv_shard or few_long or split_over_ranks" > $OUT/${TAG}_sanitize2.log 2>&1; echo "sanitize2 rc=$?"; tail -12 $OUT/${TAG}_sanitize2.log ;;
+    sanitizeall)
+      timeout 2400 compute-sanitizer --tool memcheck python -m pytest tests -m gpu -q --timeout 2300 -k "not (8GiB or maximum_length or full_size or two_gpus or plain_c_client)" > $OUT/${TAG}_sanitizeall.log 2>&1; echo "sanitizeall rc=$?"; tail -12 $OUT/${TAG}_sanitizeall.log ;;
     racecheck2)
       timeout 1700 compute-sanitizer --tool racecheck python -m pytest tests -m gpu -q -x --timeout 1600 -k "tile or bulk_aad or few_long" > $OUT/${TAG}_racecheck2.log 2>&1; echo "racecheck2 rc=$?"; tail -12 $OUT/${TAG}_racecheck2.log ;;
     racecheck)
