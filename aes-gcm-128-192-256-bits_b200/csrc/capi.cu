@@ -57,7 +57,7 @@ struct agcm_ctx {
     uint32_t* h_peer_status = nullptr;   // mapped pinned word raised by k_peer_finish on a timeout
     int peer_rank = 0, peer_world = 0;
     uint32_t peer_epoch = 0;             // exchanges issued so far
-    uint64_t peer_timeout_ns = 3000000000ull;
+    uint64_t peer_timeout_ns = 10000000000ull;   // 10 s (AGCM_PEER_TIMEOUT_MS)
     cudaStream_t peer_side = nullptr;    // the finishes wait for the world's flags here, off the caller's stream
     cudaEvent_t peer_bulk_ev[AG_PEER_RING] = {};
     cudaEvent_t peer_fin_ev[AG_PEER_RING] = {};

@@ -498,6 +498,7 @@ def run_ours(args, rank, world, local_rank):
     want_ct, want_tag, checker = expected_aesgcm(key, iv, aad, p_pt.tobytes())
     dp_in = torch.from_numpy(p_pt[p_shard.byte_offset:p_shard.byte_offset + p_shard.n_bytes].copy()).to(dev)
     dp_out = torch.zeros_like(dp_in)
+    barrier()   # the ranks made their inputs at different speeds: line up before the first exchange (its wait is bounded)
     make_step(p_total, p_shard, dp_in, dp_out)()
     join()
     torch.cuda.synchronize()
@@ -591,6 +592,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_gather_into_tensor(d_parts.view(-1), d_part)
         return eng.stream_finish_host(0, iv, d_parts.cpu().numpy(), aad, total)
 
+    barrier()   # (pinning 2 x 1 GiB takes a different time on every rank)
     e2e_step()
     barrier()
     t0 = time.perf_counter()

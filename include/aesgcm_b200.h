@@ -170,7 +170,7 @@ int agcm_stream_crypt_peer_j0(agcm_ctx* ctx, int decrypt, const uint8_t h_j0[16]
 /* ---- sharded message, partials exchanged over peer memory (NVLink) ---------------------------
  * agcm_peer_setup: h_peer_ptrs[w] = device address, valid in THIS process, of rank w's exchange
  * buffer (>= 2560 bytes, e.g. torch symmetric memory); zeroes this rank's buffer -- barrier before
- * the first exchange.  world <= 16.  AGCM_PEER_TIMEOUT_MS (environment, default 3000) bounds the wait.
+ * the first exchange.  world <= 16.  AGCM_PEER_TIMEOUT_MS (environment, default 10000) bounds the wait.
  * agcm_stream_crypt_peer: agcm_stream_part + the 16-byte all-to-all + agcm_stream_finish without a
  * collective library call.  The last CTA of the bulk kernel stores the scaled partial into every
  * peer's buffer (plain stores over NVLink) and raises an epoch flag; it does NOT wait.  A one-warp
