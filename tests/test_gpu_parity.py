@@ -1220,7 +1220,7 @@ def test_fuzz_all_paths(engine, engine_small, oracle, torch_mod):
         ivs = rng.integers(0, 256, 12 * nm, dtype=np.uint8)
         w_out, w_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), kb, True, ivs, aad, aad_off, msg, in_off,
                                          decrypt=False, threads=8)
-        lanes = int(rng.choice([0, 1, 2, 4, 8, 16, 32, 1024, 1026, 1032]))
+        lanes = int(rng.choice([0, 1, 2, 4, 8, 16, 32, 1024, 1026, 1032, 4097, 4098, 4096 + 5, 4096 + 64]))
         d_out = torch.zeros(max(1, msg.size), dtype=torch.uint8, device="cuda")
         d_tags = torch.zeros(16 * nm, dtype=torch.uint8, device="cuda")
         d_io, d_ao = torch.from_numpy(in_off.view(np.int64)).cuda(), torch.from_numpy(aad_off.view(np.int64)).cuda()
@@ -1245,6 +1245,51 @@ def test_fuzz_all_paths(engine, engine_small, oracle, torch_mod):
         exp = np.ones(nm, np.uint8)
         exp[bad] = 0
         assert (d_ok.cpu().numpy() == exp).all(), (it, "perkey ok")
+        # --- fixed-size records: every uniform layout (lane groups, TMA tiles, balanced warp units, CTA segments),
+        #     96-bit IVs or 1..40-byte IVs through the J0 form, shared key and key per message
+        if eng is engine:
+            nm = int(rng.integers(1, 150))
+            length = int(rng.choice([1, 15, 16, 17, 100, 1500, 4096, 16 * 700 + 3]))
+            alen = int(rng.choice([0, 0, 5, 16, 64, 16 * 300 + 9]))
+            stride = ((length + 15) & ~15) + 16 * int(rng.integers(0, 3))
+            astride = ((alen + 15) & ~15) if it % 2 else alen
+            ivl = 12 if it % 3 else int(rng.integers(1, 41))
+            ivs = rng.integers(0, 256, ivl * nm, dtype=np.uint8)
+            buf = rng.integers(0, 256, nm * stride, dtype=np.uint8)
+            abuf = rng.integers(0, 256, max(1, nm * astride), dtype=np.uint8)
+            want = [oracle.gcm_crypt_any_iv(key, ivs[ivl * i:ivl * (i + 1)].tobytes(), abuf[astride * i:astride * i + alen].tobytes(),
+                                            buf[stride * i:stride * i + length].tobytes()) for i in range(nm)]
+            d_iv = _dev(torch, ivs) if ivl == 12 else eng.batch_derive_j0_device(_dev(torch, ivs), None, ivl)
+            lanes = int(rng.choice([0, 2, 8, 2048, 4097, 1024, 1028]))
+            d_out = torch.full((nm * stride,), 0x77, dtype=torch.uint8, device="cuda")
+            d_tags = torch.zeros(16 * nm, dtype=torch.uint8, device="cuda")
+            eng.batch_crypt_uniform_device(0, d_iv, _dev(torch, abuf) if alen else None, alen, astride, _dev(torch, buf), d_out, length,
+                                           stride, d_tags, n_msgs=nm, lanes=lanes, j0=ivl != 12)
+            torch.cuda.synchronize()
+            got, tg = d_out.cpu().numpy().reshape(nm, stride), d_tags.cpu().numpy()
+            for i in range(nm):
+                assert got[i, :length].tobytes() == want[i][0], (it, "uniform ct", lanes, length, alen, ivl, i)
+                assert tg[16 * i:16 * i + 16].tobytes() == want[i][1], (it, "uniform tag", lanes, length, alen, ivl, i)
+            assert (got[:, length:] == 0x77).all(), (it, "uniform padding", lanes)
+            if ivl == 12:   # key per message, thread-per-message and TMA-tiled kernels
+                keys = rng.integers(0, 256, kb * nm, dtype=np.uint8)
+                wantk = [oracle.gcm_crypt(keys[kb * i:kb * (i + 1)].tobytes(), ivs[12 * i:12 * i + 12].tobytes(),
+                                          abuf[astride * i:astride * i + alen].tobytes(), buf[stride * i:stride * i + length].tobytes())
+                         for i in range(nm)]
+                for tile in ("0", "1"):
+                    os.environ["AGCM_PERKEY_TILE"] = tile
+                    try:
+                        d_out.fill_(0x77)
+                        eng.batch_crypt_perkey_uniform_device(kb * 8, 0, _dev(torch, keys), d_iv, _dev(torch, abuf) if alen else None, alen,
+                                                              astride, _dev(torch, buf), d_out, length, stride, d_tags, n_msgs=nm)
+                        torch.cuda.synchronize()
+                    finally:
+                        del os.environ["AGCM_PERKEY_TILE"]
+                    got, tg = d_out.cpu().numpy().reshape(nm, stride), d_tags.cpu().numpy()
+                    for i in range(nm):
+                        assert got[i, :length].tobytes() == wantk[i][0], (it, "perkey uniform ct", tile, length, alen, i)
+                        assert tg[16 * i:16 * i + 16].tobytes() == wantk[i][1], (it, "perkey uniform tag", tile, length, alen, i)
+                    assert (got[:, length:] == 0x77).all(), (it, "perkey uniform padding", tile)
 
 
 def test_plain_c_client(engine_lib, tmp_path):
