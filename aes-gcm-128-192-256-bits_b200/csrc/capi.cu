@@ -1359,9 +1359,10 @@ int agcm_batch_crypt_perkey_uniform(agcm_ctx* c, int mode, int decrypt, const ui
         const bool fits = len && len < (1ull << 31) && n_msgs < (1ull << 31) - 32 && !(((uintptr_t)d_in | (uintptr_t)d_out) & 15) &&
                           !(stride & 15) && stride < (1ull << 40);
         // Measured (tools/bench_variants.py --only perkey, AES-256, 64 B AAD): at a 4096 B pitch the tiled kernel wins
-        // (324 vs 294 GB/s: a lane per message at a large power-of-two pitch camps on few DRAM channels), at 1504 B
-        // the thread-per-message kernel does (353 vs 347: 16 warps instead of 14, and its aligned 128-bit accesses
-        // are only ~5 % of the pipe), at 64 B clearly (167 vs 157): tile from 2 KiB records.
+        // (341 vs 294 GB/s: a lane per message at a large power-of-two pitch camps on few DRAM channels), at 1504 B
+        // the thread-per-message kernel does (353 vs 335: its aligned 128-bit accesses are only ~5 % of the pipe, and
+        // the tiled kernel pays a PRMT more on three lookups in four for dropping Te1), at 64 B too (167 vs 164):
+        // tile from 2 KiB records.
         if (fits && !off && (force || (len >= 2048 && n_msgs >= (size_t)c->ncta * 448u * 2))) {
             const int nr = mode_to_nr(mode);
             if (!nr) return AGCM_E_BAD_MODE;

@@ -80,7 +80,34 @@ struct SubCacheT {
     }
 };
 using SubCacheSmem = SubCacheT<PK_NT>;
-using SubCacheTile = SubCacheT<448>;
+
+// Te0 alone (the even 128 B halves of the 256 B rows); Te1..Te3 by a byte rotate of the looked-up word
+struct TeSmem1 {
+    const uint8_t* base;
+    uint32_t lane4;
+    __device__ __forceinline__ uint32_t operator()(int tab, uint32_t w, int k) const
+    {
+        const uint32_t off = __byte_perm(w, lane4, 0x5504 | (k << 4));
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(base + off);
+        return tab == 0 ? v : __byte_perm(v, 0, tab == 1 ? 0x2103 : tab == 2 ? 0x1032 : 0x0321);   // rotl 8 / 16 / 24
+    }
+};
+
+// The SubWord columns in the ODD 128 B halves of the Te0 rows (where Te1 used to be): word j of thread
+// (warp, lane) in half-row j*16 + warp -- 12 x 16 = 192 of the 256 half-rows, a warp reads 128 consecutive bytes
+struct SubCacheRows {
+    uint32_t base;  // 32-bit shared address of (half-row `warp`, lane)
+    __device__ __forceinline__ void put(int j, uint32_t v) const
+    {
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + j * 4096), "r"(v) : "memory");
+    }
+    __device__ __forceinline__ uint32_t get(int j) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + j * 4096) : "memory");
+        return v;
+    }
+};
 
 __device__ __forceinline__ void load_words(const uint8_t* p, int n_words, uint32_t* w)
 {
@@ -144,13 +171,15 @@ __global__ void __launch_bounds__(PK_NT, 1) k_batch_perkey(const __grid_constant
 // box {32 bytes x 32 messages} per warp and tile, two tiles per warp, groups of 32 messages by
 // atomic ticket.  Removes the thread-per-message LDG.128 / STG.128 (32 lines per request: ~17 % of
 // the binding L1/shared data pipe and 1.29x DRAM over-fetch, profiles/r1_ncu_perkey.md).
-// 14 warps instead of 16: the tiles (28 KB) have to fit next to Te0|Te1 (64 KB), the private
-// 4-bit GHASH tables (256 B per thread) and the SubWord columns (48 B per thread).
+// To keep 16 warps next to 32 KB of tiles, Te1 goes: the AES region holds Te0 alone (Te1..Te3 by a byte
+// rotate of the looked-up word, one PRMT more on three lookups in four -- the ALU pipe has the room, the
+// lookup pipe is the binding one), and the SubWord columns move into the half-rows Te1 used to fill.
+// Shared memory: 64 KB Te0 + SubWord | 32 KB tiles | 128 KB private 4-bit GHASH tables.
 // ---------------------------------------------------------------------------
 namespace {
-constexpr uint32_t PKT_NT = 448;
-constexpr uint32_t PKT_TILES = 65536;                               // 14 warps x 2 x 1 KB
-constexpr uint32_t PKT_BARS = PKT_TILES + (PKT_NT / 32) * 2 * TILE_BYTES;   // 14 x 2 mbarriers
+constexpr uint32_t PKT_NT = 512;
+constexpr uint32_t PKT_TILES = 65536;                               // 16 warps x 2 x 1 KB
+constexpr uint32_t PKT_BARS = PKT_TILES + (PKT_NT / 32) * 2 * TILE_BYTES;   // 16 x 2 mbarriers
 constexpr uint32_t PKT_GH4 = PKT_BARS + 256;                        // + up to 2 KB alignment pad
 constexpr uint32_t PKT_SMEM = 232448;                               // all of it (227 KB); the layout is checked at run time
 }  // namespace
@@ -160,12 +189,9 @@ __global__ void __launch_bounds__(PKT_NT, 1) k_batch_perkey_tile(const __grid_co
 {
     const BatchParams& p = P.b;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (uint32_t idx = tid; idx < 256 * 32; idx += blockDim.x) {   // Te0 | Te1 only (Te2/Te3 by a 16-bit rotate)
+    for (uint32_t idx = tid; idx < 256 * 32; idx += blockDim.x) {   // Te0 only
         const uint32_t x = idx >> 5, l = idx & 31;
-        const uint32_t t = __ldg(p.te0 + x);
-        uint32_t* a = reinterpret_cast<uint32_t*>(ag_smem + SM_AES_A + x * 256 + l * 4);
-        a[0] = t;
-        a[32] = ag_rotl32(t, 8);
+        *reinterpret_cast<uint32_t*>(ag_smem + SM_AES_A + x * 256 + l * 4) = __ldg(p.te0 + x);
     }
     const uint32_t bar0 = ag_smem_addr(ag_smem + PKT_BARS + warp * 16), bar1 = bar0 + 8;
     if (lane == 0) {
@@ -176,13 +202,13 @@ __global__ void __launch_bounds__(PKT_NT, 1) k_batch_perkey_tile(const __grid_co
         ag_prefetch_tmap(&P.tm_out);
     }
     __syncthreads();
-    TeSmem2 te{ag_smem, lane * 4};
+    TeSmem1 te{ag_smem, lane * 4};
     SubWordSmem sb{ag_smem, lane * 4};
     const uint32_t s0 = ag_smem_addr(ag_smem) + PKT_GH4;
     const uint32_t s_al = (s0 + 2047u) & ~2047u;
     Rows4Smem rows{s_al + (tid >> 3) * 2048u + (tid & 7) * 16u};
-    SubCacheTile subc{s_al + PKT_NT * 256u + tid * 4u};
-    if (s_al + PKT_NT * 256u + 12u * PKT_NT * 4u > ag_smem_addr(ag_smem) + PKT_SMEM) __trap();   // layout does not fit
+    SubCacheRows subc{ag_smem_addr(ag_smem) + SM_AES_A + warp * 256u + 128u + lane * 4u};
+    if (s_al + PKT_NT * 256u > ag_smem_addr(ag_smem) + PKT_SMEM) __trap();   // layout does not fit
 
     uint8_t* tiles = ag_smem + PKT_TILES + warp * (2 * TILE_BYTES);
     const uint32_t tile_sa = ag_smem_addr(tiles);
