@@ -529,6 +529,7 @@ void agcm_ctx_destroy(agcm_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaDeviceSynchronize();   // a deferred peer finish or a pipeline chunk may still use the buffers freed below
     for (int s = 0; s < kSlots; ++s) {
         if (c->hs[s]) cudaStreamDestroy(c->hs[s]);
         cudaFree(c->d_stage[s]);
