@@ -55,6 +55,8 @@ SIGNATURES = {
     "agcm_stream_finish_j0": (c_int, [c_vp, c_int, c_u8p, c_u8p, c_int, c_u8p, c_u64, c_u64, c_u8p, c_u8p, c_vp]),
     "agcm_stream_crypt_peer_j0": (c_int, [c_vp, c_int, c_u8p, c_u64, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u64, c_u64,
                                           c_u8p, c_u8p, c_vp, c_int]),
+    "agcm_batch_crypt_slots": (c_int, [c_vp, c_int, c_int, c_u8p, c_u8p, c_u8p, c_u64, c_u64, c_u8p, c_u8p, c_u8p, c_u64, c_u64,
+                                       c_u8p, c_u8p, c_sz, c_vp]),
     "agcm_batch_derive_j0": (c_int, [c_vp, c_u8p, c_u8p, c_u64, c_sz, c_u8p, c_vp]),
     "agcm_batch_crypt_j0": (c_int, [c_vp, c_int, c_int, c_u64, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p, c_u8p,
                                     c_sz, c_vp]),

@@ -90,6 +90,8 @@ struct agcm_ctx {
     size_t aad_stage_cap = 0;
     uint32_t* d_tile_ticket = nullptr;   // k_batch_tile / _warp / _cta: next unit (zeroed before each launch)
     bool no_ticket = false;              // set while the host batch pipeline runs chunks on several streams at once
+    uint32_t* d_sort = nullptr;          // length sort of an offset batch: 4096 bucket counters, then perm[n_msgs]
+    size_t sort_cap = 0;
     void* tmap_encode = nullptr;         // cuTensorMapEncodeTiled, resolved through the runtime (no link-time libcuda)
     uint8_t* d_verify = nullptr;     // whole ciphertext of a verify-then-release host decrypt, grown on demand
     size_t verify_cap = 0;
@@ -548,6 +550,7 @@ void agcm_ctx_destroy(agcm_ctx* c)
     cudaFree(c->d_aad_stage);
     cudaFree(c->d_verify);
     cudaFree(c->d_tile_ticket);
+    cudaFree(c->d_sort);
     cudaFree(c->d_te0);
     cudaFree(c->d_key);
     cudaFree(c->d_parts);
@@ -1033,7 +1036,8 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
     if (!c->key_set) return AGCM_E_NO_KEY;
     if (n_msgs == 0) return AGCM_OK;
     if (!p.iv || !p.tag || (decrypt && !p.ok)) return AGCM_E_BAD_ARG;
-    const uint64_t real_blocks = (!p.in_off && !p.aad_off) ? ((p.len + 15) >> 4) + (p.aad ? (p.aad_len + 15) >> 4 : 0) : 0;
+    const bool ragged = p.in_off || p.aad_off || p.len_arr || p.aad_len_arr;   // messages of different lengths
+    const uint64_t real_blocks = !ragged ? ((p.len + 15) >> 4) + (p.aad ? (p.aad_len + 15) >> 4 : 0) : 0;
     const int g = pick_lanes(c, lanes, n_msgs, avg_len, aligned16, real_blocks);
     if (g < 0) return AGCM_E_BAD_ARG;
     AG_CUDA(c, cudaSetDevice(c->device));
@@ -1045,7 +1049,7 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
         // a warp per unit (k_batch_warp): balanced static partition for uniform batches, `split`
         // segments per message by ticket for offset batches
         const uint64_t per_cta = (uint64_t)AG_STREAM_NT_MAX / 32;
-        const bool uniform = !p.in_off && !p.aad_off;
+        const bool uniform = !ragged;
         int ncta_w = c->ncta;
         if (uniform) {
             const uint64_t warps = (uint64_t)ncta_w * per_cta;
@@ -1119,6 +1123,28 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
     const uint64_t groups_per_cta = (uint64_t)c->nt / g;
     uint64_t need = (n_msgs + groups_per_cta - 1) / groups_per_cta;
     int ncta = (int)(need < (uint64_t)c->ncta ? need : (uint64_t)c->ncta);
+    if (ragged && n_msgs >= 1024 && n_msgs < 0xFFFFFF00ull && !c->no_ticket && !getenv("AGCM_NO_LEN_SORT")) {
+        // messages of different lengths: take them longest first, so that the 32/G messages a warp works on in
+        // lock step are equally long (3 small launches; the kernels then follow perm[])
+        const size_t need_b = sizeof(uint32_t) * (4096 + (size_t)n_msgs);
+        if (need_b > c->sort_cap) {
+            AG_CUDA(c, cudaFree(c->d_sort));
+            c->d_sort = nullptr;
+            c->sort_cap = 0;
+            AG_CUDA(c, cudaMalloc(&c->d_sort, need_b));
+            c->sort_cap = need_b;
+        }
+        p.n_msgs = n_msgs;
+        AG_CUDA(c, ag_launch_len_sort(p, c->d_sort, c->d_sort + 4096, (cudaStream_t)stream));
+        c->launches += 3;
+        p.perm = c->d_sort + 4096;
+    }
+    if (ragged && need > (uint64_t)ncta && n_msgs < 0xFFFFFF00ull && !c->no_ticket && !getenv("AGCM_NO_BATCH_TICKET")) {
+        // messages of different lengths and more than one pass of the grid: hand them out warp by warp
+        if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
+        AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
+        p.ticket = c->d_tile_ticket;
+    }
     AG_CUDA(c, ag_launch_batch(p, c->nr, decrypt, g, ncta, c->nt, (cudaStream_t)stream));
     c->launches++;
     return AGCM_OK;
@@ -1279,6 +1305,36 @@ int agcm_batch_crypt_uniform_j0(agcm_ctx* c, int decrypt, int lanes, const uint8
 {
     return batch_uniform(c, decrypt, lanes, d_j0, 1, d_aad, aad_len, aad_stride, d_in, d_out, len, stride, d_tag, d_ok, n_msgs,
                          stream);
+}
+
+int agcm_batch_crypt_slots(agcm_ctx* c, int decrypt, int lanes, const uint8_t* d_iv12, const uint8_t* d_aad,
+                           const uint32_t* d_aad_len, uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out,
+                           const uint32_t* d_len, uint64_t stride, uint64_t avg_len_hint, uint8_t* d_tag, uint8_t* d_ok,
+                           size_t n_msgs, void* stream)
+{
+    if (!c || !d_len) return AGCM_E_BAD_ARG;
+    if (n_msgs && stride && (!d_in || !d_out)) return AGCM_E_BAD_ARG;
+    const bool has_aad = d_aad && (d_aad_len || aad_len);
+    if (has_aad && (aad_stride < aad_len || aad_stride == 0)) return AGCM_E_BAD_LEN;
+    if (((stride + 15) >> 4) > kMaxBlocks || ((aad_stride + 15) >> 4) + ((stride + 15) >> 4) + 1 > 0xFFFFFFFFull)
+        return AGCM_E_COUNTER_OVERFLOW;   // no slot can hold a message beyond the limits
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.iv = d_iv12;
+    p.aad = has_aad ? d_aad : nullptr;
+    p.in = d_in;
+    p.out = d_out;
+    p.tag = d_tag;
+    p.ok = d_ok;
+    p.len = stride;
+    p.stride = stride;
+    p.len_arr = d_len;
+    p.aad_len = has_aad ? aad_len : 0;
+    p.aad_stride = has_aad ? aad_stride : 0;
+    p.aad_len_arr = has_aad ? d_aad_len : nullptr;
+    const bool aligned16 = ((((uintptr_t)d_in | (uintptr_t)d_out) | stride) & 15) == 0;
+    if (lanes == 2048) return AGCM_E_BAD_ARG;   // the TMA-staged kernel takes records of ONE length
+    return batch_common(c, decrypt, lanes, avg_len_hint ? avg_len_hint : stride / 2, p, n_msgs, stream, aligned16);
 }
 
 int agcm_batch_derive_j0(agcm_ctx* c, const uint8_t* d_iv, const uint64_t* d_iv_off, uint64_t iv_len, size_t n_msgs,

@@ -273,6 +273,10 @@ struct BatchParams {
     uint8_t* ok;               // n_msgs, dec only: 1 = authentic
     uint64_t n_msgs;
     uint64_t len, stride, aad_len, aad_stride;  // uniform layout
+    // fixed-pitch SLOTS holding messages of different lengths (agcm_batch_crypt_slots): message m is
+    // len_arr[m] bytes at m * stride (clamped to the pitch); null => `len` for all.  AAD likewise.
+    const uint32_t* len_arr;
+    const uint32_t* aad_len_arr;
     // k_batch_cta only: every message is cut into `split` counter-range segments, one CTA each
     // (1 = whole messages); seg_parts holds n_msgs x split scaled partials then n_msgs x E_K(J0)
     uint32_t split;
@@ -280,6 +284,9 @@ struct BatchParams {
     // k_batch_cta: units (messages or segments) are handed out by this counter (zero at launch);
     // null = static round-robin over the CTAs
     uint32_t* ticket;
+    // k_batch, offset batches: the order in which the lane groups take the messages -- sorted by length
+    // (longest first) so that the messages a warp works on side by side are equally long; null = 0, 1, 2, ...
+    const uint32_t* perm;
     // k_batch_warp (a warp per unit): raw lane accumulators (32 x 16 B per unit id, BE words), unit
     // descriptors {message + 1 (0 = unused id), blocks after the unit}, per-message XOR accumulators
     // and E_K(J0) (n_msgs x 16 B each)
@@ -312,11 +319,13 @@ AG_HD MsgDesc ag_batch_msg(const BatchParams& p, uint64_t m)
 {
     MsgDesc d;
     uint64_t o, l;
-    if (p.in_off) { o = p.in_off[m]; l = p.in_off[m + 1] - o; } else { o = m * p.stride; l = p.len; }
+    if (p.in_off) { o = p.in_off[m]; l = p.in_off[m + 1] - o; }
+    else { o = m * p.stride; l = p.len_arr ? (p.len_arr[m] < p.stride ? p.len_arr[m] : p.stride) : p.len; }
     d.in = p.in + o;
     d.out = p.out + o;
     d.len = l;
-    if (p.aad_off) { o = p.aad_off[m]; l = p.aad_off[m + 1] - o; } else { o = m * p.aad_stride; l = p.aad_len; }
+    if (p.aad_off) { o = p.aad_off[m]; l = p.aad_off[m + 1] - o; }
+    else { o = m * p.aad_stride; l = p.aad_len_arr ? (p.aad_len_arr[m] < p.aad_stride ? p.aad_len_arr[m] : p.aad_stride) : p.aad_len; }
     d.aad = p.aad ? p.aad + o : nullptr;
     d.aad_len = p.aad ? l : 0;
     d.total_len = d.len;

@@ -69,10 +69,20 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
     const uint64_t groups_per_cta = nt / G;
     const uint64_t n_groups = (uint64_t)gridDim.x * groups_per_cta;
     const uint64_t gid = (uint64_t)blockIdx.x * groups_per_cta + tid / G;
-    // every warp runs the same trip count; lanes past the end are predicated off
+    // every warp runs the same trip count; lanes past the end are predicated off.  With a ticket (zero at
+    // launch) each warp draws its next 32/G messages when it is done with the last: messages of different
+    // lengths (an offset batch) then no longer pin the grid to the warps that drew the long ones.
     const uint64_t warp_first = (uint64_t)blockIdx.x * groups_per_cta + (tid & ~31u) / G;
-    for (uint64_t w0 = warp_first, m = gid; w0 < p.n_msgs; w0 += n_groups, m += n_groups) {
+    for (uint64_t w0 = warp_first, m = gid;; w0 += n_groups, m += n_groups) {
+        if (p.ticket) {
+            uint32_t tk = 0;
+            if (lane == 0) tk = atomicAdd(p.ticket, 32u / G);
+            w0 = __shfl_sync(0xffffffffu, tk, 0);
+            m = w0 + lane / G;
+        }
+        if (w0 >= p.n_msgs) break;
         const bool valid = m < p.n_msgs;
+        if (valid && p.perm) m = p.perm[m];
         gf128 y = gf_zero();
         AesCtrConst cc;
         AesCtrSeqCache cache;
@@ -618,6 +628,72 @@ __global__ void k_batch_split_finish(const __grid_constant__ BatchParams p)
     } else {
         ag_store_block(tp, 16, tg);
     }
+}
+
+// ===========================================================================
+// Length sort of an offset batch (counting sort, longest first).  A warp works on 32/G messages side by
+// side in lock step, so a row costs the warp as much as its LONGEST message needs: with mixed lengths in
+// arrival order (an IMIX of 64 / 576 / 1500 B packets) three quarters of the lane-rows are idle.  Keys are
+// the work of a message in blocks (payload + a quarter of the AAD), clipped to AG_SORT_BUCKETS - 1.
+// ===========================================================================
+namespace {
+constexpr uint32_t AG_SORT_BUCKETS = 4096;
+__device__ __forceinline__ uint32_t ag_sort_bucket(const BatchParams& p, uint64_t m)
+{
+    const MsgDesc d = ag_batch_msg(p, m);
+    const uint64_t n = (d.len + 15) >> 4, a = (d.aad_len + 15) >> 4;
+    const uint64_t w = n + (a + 3) / 4;
+    return AG_SORT_BUCKETS - 1 - (uint32_t)(w < AG_SORT_BUCKETS - 1 ? w : AG_SORT_BUCKETS - 1);   // bucket 0 = longest
+}
+}  // namespace
+
+__global__ void __launch_bounds__(256) k_len_hist(const __grid_constant__ BatchParams p, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t h[AG_SORT_BUCKETS];
+    for (uint32_t i = threadIdx.x; i < AG_SORT_BUCKETS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < p.n_msgs; m += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&h[ag_sort_bucket(p, m)], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < AG_SORT_BUCKETS; i += blockDim.x)
+        if (h[i]) atomicAdd(hist + i, h[i]);
+}
+
+// exclusive scan of the 4096 bucket counts, in place (one CTA of 1024 threads, 4 buckets each)
+__global__ void __launch_bounds__(1024) k_len_scan(uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t part[1024];
+    const uint32_t t = threadIdx.x;
+    uint32_t v[4], s = 0;
+    for (int k = 0; k < 4; ++k) { v[k] = hist[4 * t + k]; s += v[k]; }
+    part[t] = s;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        const uint32_t x = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += x;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - s;
+    for (int k = 0; k < 4; ++k) { hist[4 * t + k] = run; run += v[k]; }
+}
+
+__global__ void __launch_bounds__(256) k_len_scatter(const __grid_constant__ BatchParams p, uint32_t* __restrict__ cursor,
+                                                     uint32_t* __restrict__ perm)
+{
+    for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < p.n_msgs; m += (uint64_t)gridDim.x * blockDim.x)
+        perm[atomicAdd(cursor + ag_sort_bucket(p, m), 1u)] = (uint32_t)m;
+}
+
+cudaError_t ag_launch_len_sort(const BatchParams& p, uint32_t* hist4096, uint32_t* perm, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(hist4096, 0, sizeof(uint32_t) * AG_SORT_BUCKETS, st);
+    if (e != cudaSuccess) return e;
+    const unsigned nb = (unsigned)((p.n_msgs + 255) / 256 < 1184 ? (p.n_msgs + 255) / 256 : 1184);
+    k_len_hist<<<nb, 256, 0, st>>>(p, hist4096);
+    k_len_scan<<<1, 1024, 0, st>>>(hist4096);
+    k_len_scatter<<<nb, 256, 0, st>>>(p, hist4096, perm);
+    return cudaGetLastError();
 }
 
 // ===========================================================================

@@ -367,6 +367,15 @@ class GcmEngine:
         self._ck(fn(self._ctx, int(decrypt), int(lanes), _dptr(ivs), _dptr(aad), int(aad_len), int(aad_stride), _dptr(data_in),
                     _dptr(data_out), int(length), int(stride), _dptr(tags), _dptr(ok), n, _stream(stream)))
 
+    def batch_crypt_slots_device(self, decrypt, ivs, aad, aad_lens, aad_len, aad_stride, data_in, data_out, lens, stride, tags,
+                                 ok=None, n_msgs=None, lanes=0, avg_len_hint=0, stream=None):
+        """Fixed-pitch slots, per-message lengths: `lens` / `aad_lens` are CUDA int32/uint32 tensors [n] (aad_lens may be
+        None: `aad_len` for all; aad None: no AAD)."""
+        n = lens.numel() if n_msgs is None else int(n_msgs)
+        self._ck(self._L.agcm_batch_crypt_slots(self._ctx, int(decrypt), int(lanes), _dptr(ivs), _dptr(aad), _dptr(aad_lens),
+                                                int(aad_len), int(aad_stride), _dptr(data_in), _dptr(data_out), _dptr(lens),
+                                                int(stride), int(avg_len_hint), _dptr(tags), _dptr(ok), n, _stream(stream)))
+
     def batch_crypt_perkey_device(self, mode, decrypt, keys, ivs, aad, aad_off, data_in, in_off, data_out, tags, ok=None,
                                   stream=None):
         """One distinct raw key per message (keys: CUDA uint8 [n, mode/8]); BASELINE config 4."""

@@ -226,6 +226,18 @@ int agcm_batch_crypt_uniform(agcm_ctx* ctx, int decrypt, int lanes, const uint8_
                              uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in, uint8_t* d_out, uint64_t len,
                              uint64_t stride, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);
 
+/* Fixed-pitch SLOTS holding messages of different lengths (a packet ring): message i is d_len[i] bytes at
+ * d_in + i*stride (a length beyond the pitch is clamped to it), its AAD d_aad_len[i] bytes at d_aad + i*aad_stride
+ * (d_aad_len NULL: aad_len bytes for every message; d_aad NULL: none).  With 16-byte aligned buffers and pitch every
+ * access is a 128-bit one, whatever the lengths.  From 1024 messages on, this call and agcm_batch_crypt take the
+ * messages in LENGTH order (a counting sort on the device, longest first, handed out by ticket): a warp works on
+ * several messages in lock step, and side by side they should be equally long (an IMIX of 64 / 576 / 1500 B
+ * packets: 2-4x).  avg_len_hint as in agcm_batch_crypt (0: half the pitch). */
+int agcm_batch_crypt_slots(agcm_ctx* ctx, int decrypt, int lanes, const uint8_t* d_iv12, const uint8_t* d_aad,
+                           const uint32_t* d_aad_len, uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in,
+                           uint8_t* d_out, const uint32_t* d_len, uint64_t stride, uint64_t avg_len_hint, uint8_t* d_tag,
+                           uint8_t* d_ok, size_t n_msgs, void* stream);
+
 /* Batches whose IVs are not all 96 bits: agcm_batch_derive_j0 turns n IVs (d_iv_off: n+1 byte
  * offsets into d_iv, or NULL = fixed iv_len bytes each) into n 16-byte J0 blocks, one thread per IV;
  * the *_j0 batch forms take d_j0 (n x 16) where the plain forms take d_iv12 (n x 12). */

@@ -797,6 +797,98 @@ def test_batch_bulk_aad_layouts(engine, oracle, torch_mod):
             assert (d_tags.cpu().numpy() == want_tags).all(), (kb, alen, lanes, "offsets")
 
 
+def test_batch_ragged_length_sorted(engine, oracle, torch_mod):
+    """Offset batches of >= 1024 messages are taken in length order (counting sort on the device, longest
+    first) and handed out by ticket: an IMIX-like mix with a few jumbo messages, empty messages and AAD, every
+    lane-group width, encrypt and decrypt with corrupted tags -- same bytes as the oracle, message by message."""
+    torch = torch_mod
+    rng = np.random.default_rng(4242)
+    key = _rb(rng, 32)
+    engine.set_key(key)
+    n_msgs = 3001
+    lens = rng.choice([0, 1, 64, 576, 1500, 9000], n_msgs, p=[0.02, 0.03, 0.5, 0.3, 0.13, 0.02])
+    lens[7], lens[2999] = 70000, 16 * 4200 + 5          # beyond the last sort bucket
+    alens = rng.choice([0, 13, 16, 200], n_msgs)
+    in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.uint64)
+    data = rng.integers(0, 256, int(in_off[-1]), dtype=np.uint8)
+    aad = rng.integers(0, 256, int(aad_off[-1]), dtype=np.uint8)
+    ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+    want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), 32, True, ivs, aad, aad_off, data, in_off, threads=8)
+    d_io, d_ao = torch.from_numpy(in_off.view(np.int64)).cuda(), torch.from_numpy(aad_off.view(np.int64)).cuda()
+    d_data, d_aad, d_iv = _dev(torch, data), _dev(torch, aad), _dev(torch, ivs)
+    for lanes in (0, 1, 2, 8, 32):
+        d_out = torch.zeros_like(d_data)
+        d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_device(0, d_iv, d_aad, d_ao, d_data, d_io, d_out, d_tags, lanes=lanes, avg_len_hint=int(lens.mean()))
+        torch.cuda.synchronize()
+        assert (d_out.cpu().numpy() == want_ct).all(), lanes
+        assert (d_tags.cpu().numpy() == want_tags).all(), lanes
+        tags_in = want_tags.copy()
+        bad = np.arange(3, n_msgs, 97)
+        tags_in[16 * bad + 1] ^= 0x04
+        d_back = torch.zeros_like(d_data)
+        d_ok = torch.full((n_msgs,), 5, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_device(1, d_iv, d_aad, d_ao, d_out, d_io, d_back, _dev(torch, tags_in), d_ok, lanes=lanes,
+                                  avg_len_hint=int(lens.mean()))
+        torch.cuda.synchronize()
+        assert (d_back.cpu().numpy() == data).all(), lanes
+        ok = d_ok.cpu().numpy()
+        assert (ok[bad] == 0).all() and int(ok.sum()) == n_msgs - bad.size, lanes
+
+
+def test_batch_slots_per_message_lengths(engine, oracle, torch_mod):
+    """agcm_batch_crypt_slots: messages of different lengths in fixed-pitch slots (a packet ring), AAD in slots of its
+    own with per-message lengths or one common length; small batches (arrival order) and large ones (length-sorted);
+    a length beyond the pitch is clamped; the rest of every slot is left untouched; decrypt with corrupted tags."""
+    torch = torch_mod
+    rng = np.random.default_rng(777)
+    for kb, n_msgs, stride, astride, per_msg_aad in ((16, 300, 1504, 64, True), (32, 5000, 2048, 32, False), (24, 2000, 256, 0, False)):
+        key = _rb(rng, kb)
+        engine.set_key(key)
+        lens = rng.choice([0, 1, 64, 100, 576, 1500, stride], n_msgs).astype(np.uint32)
+        lens = np.minimum(lens, stride).astype(np.uint32)
+        alens = (rng.integers(0, astride + 1, n_msgs) if per_msg_aad else np.full(n_msgs, astride // 2)).astype(np.uint32)
+        ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
+        buf = rng.integers(0, 256, n_msgs * stride, dtype=np.uint8)
+        abuf = rng.integers(0, 256, max(1, n_msgs * astride), dtype=np.uint8)
+        in_off = np.concatenate([[0], np.cumsum(lens.astype(np.int64))]).astype(np.uint64)
+        aad_off = np.concatenate([[0], np.cumsum(alens.astype(np.int64))]).astype(np.uint64)
+        packed = np.concatenate([buf[i * stride:i * stride + lens[i]] for i in range(n_msgs)] + [np.zeros(0, np.uint8)])
+        apacked = np.concatenate([abuf[i * astride:i * astride + alens[i]] for i in range(n_msgs)] + [np.zeros(0, np.uint8)])
+        want_ct, want_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), kb, True, ivs, apacked if astride else None,
+                                              aad_off if astride else None, packed, in_off, threads=8)
+        d_len = torch.from_numpy(lens.astype(np.int32)).cuda()
+        d_len_over = d_len.clone()
+        d_len_over[lens == stride] = stride + 999            # clamped to the pitch by the kernel
+        d_alen = torch.from_numpy(alens.astype(np.int32)).cuda() if per_msg_aad else None
+        d_in, d_aad = _dev(torch, buf), (_dev(torch, abuf) if astride else None)
+        for lanes in (0, 1, 4, 32):
+            d_out = torch.full((n_msgs * stride,), 0x3C, dtype=torch.uint8, device="cuda")
+            d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
+            engine.batch_crypt_slots_device(0, _dev(torch, ivs), d_aad, d_alen, astride // 2, astride, d_in, d_out, d_len_over, stride,
+                                            d_tags, lanes=lanes, avg_len_hint=int(lens.mean()))
+            torch.cuda.synchronize()
+            got = d_out.cpu().numpy().reshape(n_msgs, stride)
+            for i in range(n_msgs):
+                assert got[i, :lens[i]].tobytes() == want_ct[int(in_off[i]):int(in_off[i + 1])].tobytes(), (kb, lanes, i)
+                assert (got[i, lens[i]:] == 0x3C).all(), (kb, lanes, i, "slot padding written")
+            assert (d_tags.cpu().numpy() == want_tags).all(), (kb, lanes)
+        tags_in = want_tags.copy()
+        bad = np.arange(1, n_msgs, 53)
+        tags_in[16 * bad + 15] ^= 0x80
+        d_back = torch.zeros(n_msgs * stride, dtype=torch.uint8, device="cuda")
+        d_ok = torch.full((n_msgs,), 3, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_slots_device(1, _dev(torch, ivs), d_aad, d_alen, astride // 2, astride, d_out, d_back, d_len, stride,
+                                        _dev(torch, tags_in), d_ok, avg_len_hint=int(lens.mean()))
+        torch.cuda.synchronize()
+        back = d_back.cpu().numpy().reshape(n_msgs, stride)
+        for i in range(0, n_msgs, 7):
+            assert back[i, :lens[i]].tobytes() == buf[i * stride:i * stride + lens[i]].tobytes(), i
+        ok = d_ok.cpu().numpy()
+        assert (ok[bad] == 0).all() and int(ok.sum()) == n_msgs - bad.size
+
+
 def test_batch_host_api_roundtrip(engine, oracle):
     rng = np.random.default_rng(9)
     key = _rb(rng, 32)
