@@ -678,11 +678,37 @@ __global__ void __launch_bounds__(1024) k_len_scan(uint32_t* __restrict__ hist)
     for (int k = 0; k < 4; ++k) { hist[4 * t + k] = run; run += v[k]; }
 }
 
+// Scatter, chunk by chunk of 2048 messages per CTA: a shared-memory histogram of the chunk, ONE global atomic per
+// (chunk, non-empty bucket) to reserve that bucket's range, then ranks inside the chunk from shared-memory
+// atomics.  (A global atomic per message serialises on the handful of buckets a real packet mix uses: an IMIX of
+// three lengths spent more time here than in the cipher.)
 __global__ void __launch_bounds__(256) k_len_scatter(const __grid_constant__ BatchParams p, uint32_t* __restrict__ cursor,
                                                      uint32_t* __restrict__ perm)
 {
-    for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < p.n_msgs; m += (uint64_t)gridDim.x * blockDim.x)
-        perm[atomicAdd(cursor + ag_sort_bucket(p, m), 1u)] = (uint32_t)m;
+    constexpr uint32_t CH = 2048;
+    __shared__ uint32_t cnt[AG_SORT_BUCKETS];    // count, then the chunk's base in the bucket's global range
+    __shared__ uint32_t rank[AG_SORT_BUCKETS];
+    const uint64_t n_chunks = (p.n_msgs + CH - 1) / CH;
+    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < AG_SORT_BUCKETS; i += blockDim.x) { cnt[i] = 0; rank[i] = 0; }
+        __syncthreads();
+        const uint64_t m0 = c * CH, m1 = (m0 + CH < p.n_msgs) ? m0 + CH : p.n_msgs;
+        uint32_t bk[CH / 256];
+#pragma unroll
+        for (uint32_t k = 0; k < CH / 256; ++k) {
+            const uint64_t m = m0 + k * 256 + threadIdx.x;
+            bk[k] = m < m1 ? ag_sort_bucket(p, m) : 0xFFFFFFFFu;
+            if (m < m1) atomicAdd(&cnt[bk[k]], 1u);
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < AG_SORT_BUCKETS; i += blockDim.x)
+            if (cnt[i]) cnt[i] = atomicAdd(cursor + i, cnt[i]);
+        __syncthreads();
+#pragma unroll
+        for (uint32_t k = 0; k < CH / 256; ++k)
+            if (bk[k] != 0xFFFFFFFFu) perm[cnt[bk[k]] + atomicAdd(&rank[bk[k]], 1u)] = (uint32_t)(m0 + k * 256 + threadIdx.x);
+        __syncthreads();
+    }
 }
 
 cudaError_t ag_launch_len_sort(const BatchParams& p, uint32_t* hist4096, uint32_t* perm, cudaStream_t st)
