@@ -1087,7 +1087,7 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
         p.seg_acc = reinterpret_cast<uint4*>(base + zero_bytes + desc_bytes + ej0_bytes);
         AG_CUDA(c, cudaMemsetAsync(base, 0, zero_bytes, (cudaStream_t)stream));
         if (!uniform) {
-            if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
+            if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, 4 * sizeof(uint32_t)));
             AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
             p.ticket = c->d_tile_ticket;
         }
@@ -1111,7 +1111,7 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
         }
         const int ncta_m = (int)(n_units < (uint64_t)c->ncta ? n_units : (uint64_t)c->ncta);
         if (n_units > (uint64_t)ncta_m && n_units < 0xFFFFFFFFull && !c->no_ticket) {   // more units than CTAs: hand them out dynamically
-            if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
+            if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, 4 * sizeof(uint32_t)));
             AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
             p.ticket = c->d_tile_ticket;
         }
@@ -1124,9 +1124,13 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
     uint64_t need = (n_msgs + groups_per_cta - 1) / groups_per_cta;
     int ncta = (int)(need < (uint64_t)c->ncta ? need : (uint64_t)c->ncta);
     if (ragged && n_msgs >= 1024 && n_msgs < 0xFFFFFF00ull && !c->no_ticket && !getenv("AGCM_NO_LEN_SORT")) {
-        // messages of different lengths: take them longest first, so that the 32/G messages a warp works on in
-        // lock step are equally long (3 small launches; the kernels then follow perm[])
-        const size_t need_b = sizeof(uint32_t) * (4096 + (size_t)n_msgs);
+        // Messages of different lengths: take them longest first, so that the 32/G messages a warp works on in
+        // lock step are equally long (3 small launches; the kernels then follow perm[]), warp by warp by ticket.
+        // With lanes = 0 the order is cut into three length classes, one launch each: 32 lanes per message from
+        // 16 KiB of work, 4 from 4 KiB, 1 below -- a heavy tail of long messages must not crawl through one lane.
+        // The class sizes stay on the device (no host round trip): an empty class costs one idle launch.
+        cudaStream_t st = (cudaStream_t)stream;
+        const size_t need_b = sizeof(uint32_t) * (4096 + 8 + (size_t)n_msgs);
         if (need_b > c->sort_cap) {
             AG_CUDA(c, cudaFree(c->d_sort));
             c->d_sort = nullptr;
@@ -1134,16 +1138,25 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
             AG_CUDA(c, cudaMalloc(&c->d_sort, need_b));
             c->sort_cap = need_b;
         }
-        p.n_msgs = n_msgs;
-        AG_CUDA(c, ag_launch_len_sort(p, c->d_sort, c->d_sort + 4096, (cudaStream_t)stream));
+        if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, 4 * sizeof(uint32_t)));
+        AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, 4 * sizeof(uint32_t), st));
+        uint32_t* ranges = c->d_sort + 4096;
+        AG_CUDA(c, ag_launch_len_sort(p, c->d_sort, ranges, c->d_sort + 4096 + 8, st));
         c->launches += 3;
-        p.perm = c->d_sort + 4096;
-    }
-    if (ragged && need > (uint64_t)ncta && n_msgs < 0xFFFFFF00ull && !c->no_ticket && !getenv("AGCM_NO_BATCH_TICKET")) {
-        // messages of different lengths and more than one pass of the grid: hand them out warp by warp
-        if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
-        AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
-        p.ticket = c->d_tile_ticket;
+        p.perm = c->d_sort + 4096 + 8;
+        if (lanes == 0 && !getenv("AGCM_NO_LEN_CLASSES")) {
+            // short class: one lane per message with realigned wide accesses when records sit at odd addresses,
+            // two lanes (32 contiguous bytes per request) when they are 16-byte aligned
+            const int gs[3] = {32, 4, (aligned16 && !p.in_off) ? 2 : 1};   // packed by offsets: alignment unknown
+            for (int k = 0; k < 3; ++k) {
+                p.range = ranges + 2 * k;
+                p.ticket = c->d_tile_ticket + 1 + k;
+                AG_CUDA(c, ag_launch_batch(p, c->nr, decrypt, gs[k], c->ncta, c->nt, st));
+                c->launches++;
+            }
+            return AGCM_OK;
+        }
+        p.ticket = c->d_tile_ticket + 1;
     }
     AG_CUDA(c, ag_launch_batch(p, c->nr, decrypt, g, ncta, c->nt, (cudaStream_t)stream));
     c->launches++;
@@ -1194,7 +1207,7 @@ static int batch_tile(agcm_ctx* c, int decrypt, BatchParams& p, size_t n_msgs, c
     if (!c->key_set) return AGCM_E_NO_KEY;
     if (!p.iv || !p.tag || (decrypt && !p.ok)) return AGCM_E_BAD_ARG;
     AG_CUDA(c, cudaSetDevice(c->device));
-    if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
+    if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, 4 * sizeof(uint32_t)));
     TileParams t;
     memset(&t, 0, sizeof(t));
     memcpy(p.rk, c->h_rk, sizeof(p.rk));
@@ -1425,7 +1438,7 @@ int agcm_batch_crypt_perkey_uniform(agcm_ctx* c, int mode, int decrypt, const ui
             if (!nr) return AGCM_E_BAD_MODE;
             if (!p.keys || !p.iv || !p.tag || (decrypt && !p.ok)) return AGCM_E_BAD_ARG;
             AG_CUDA(c, cudaSetDevice(c->device));
-            if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, sizeof(uint32_t)));
+            if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, 4 * sizeof(uint32_t)));
             TileParams t;
             memset(&t, 0, sizeof(t));
             p.te0 = c->d_te0;

@@ -125,6 +125,80 @@ AG_HD void ag_mask_block(uint32_t x[4], uint32_t nvalid)
     }
 }
 
+// ---- 16-byte blocks at addresses that are NOT 16-byte aligned (device only) -----------------
+// Byte-wise access costs 16 load and 16 store instructions per block, each of them scattered over the
+// warp; these helpers use whole aligned 16-byte granules instead.
+#if defined(__CUDA_ARCH__)
+// bytes r .. r+15 of the 32-byte string a | b (1 <= r <= 15): a three-stage barrel shifter
+__device__ __forceinline__ uint4 ag_realign(const uint4& a, const uint4& b, uint32_t r)
+{
+    uint32_t c0 = a.x, c1 = a.y, c2 = a.z, c3 = a.w, c4 = b.x, c5 = b.y, c6 = b.z;
+    if (r & 8) { c0 = c2; c1 = c3; c2 = c4; c3 = c5; c4 = c6; c5 = b.w; }
+    if (r & 4) { c0 = c1; c1 = c2; c2 = c3; c3 = c4; c4 = c5; }
+    const uint32_t sh = (r & 3) * 8;
+    return make_uint4(__funnelshift_r(c0, c1, sh), __funnelshift_r(c1, c2, sh), __funnelshift_r(c2, c3, sh),
+                      __funnelshift_r(c3, c4, sh));
+}
+#endif
+
+// Load like ag_load_block; a whole block at an unaligned address comes from the two aligned granules that
+// hold it when both lie inside [lo, hi) -- the unit's own bytes, so nothing outside the caller's data is read.
+AG_HD void ag_load_block_in(const uint8_t* p, uint32_t nvalid, uint32_t x[4], const uint8_t* lo, const uint8_t* hi)
+{
+#if defined(__CUDA_ARCH__)
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t r = (uint32_t)(a & 15);
+    if (nvalid == 16 && r != 0) {
+        const uint8_t* base = p - r;
+        if (base >= lo && base + 32 <= hi) {
+            const uint4 w0 = *reinterpret_cast<const uint4*>(base), w1 = *reinterpret_cast<const uint4*>(base + 16);
+            const uint4 v = ag_realign(w0, w1, r);
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+            return;
+        }
+    }
+#else
+    (void)lo; (void)hi;
+#endif
+    ag_load_block(p, nvalid, x);
+}
+
+#if defined(__CUDA_ARCH__)
+// Stores of CONSECUTIVE whole blocks at unaligned addresses by one thread: the granule that holds the tail of
+// the previous block and the head of this one leaves with one 128-bit store; only the head of the first block
+// and the tail of the last one go out byte by byte (flush).  Writes exactly the bytes of the blocks it is given.
+struct AgStoreCarry {
+    uint4 prev;
+    uint8_t* prev_addr;
+    bool have;
+    __device__ __forceinline__ void init() { have = false; prev_addr = nullptr; prev = make_uint4(0, 0, 0, 0); }
+    __device__ __forceinline__ void flush()
+    {
+        if (!have) return;
+        const uint32_t ro = (uint32_t)((uintptr_t)prev_addr & 15);
+        const uint32_t w[4] = {prev.x, prev.y, prev.z, prev.w};
+        uint8_t* q = prev_addr + 16 - ro;   // aligned: the last ro bytes of the block
+        for (uint32_t j = 16 - ro; j < 16; ++j) q[j - (16 - ro)] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+        have = false;
+    }
+    // q: unaligned address of this whole block
+    __device__ __forceinline__ void put(uint8_t* q, const uint32_t o[4])
+    {
+        const uint32_t ro = (uint32_t)((uintptr_t)q & 15);
+        const uint4 cur = make_uint4(o[0], o[1], o[2], o[3]);
+        if (have && prev_addr + 16 == q) {
+            *reinterpret_cast<uint4*>(q - ro) = ag_realign(prev, cur, 16 - ro);
+        } else {
+            flush();
+            for (uint32_t j = 0; j < 16 - ro; ++j) q[j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
+        }
+        prev = cur;
+        prev_addr = q;
+        have = true;
+    }
+};
+#endif
+
 // ---- single stream: one lane of the grid-wide strided Horner ----------------
 struct StreamParams {
     uint32_t rk[60];
@@ -205,7 +279,7 @@ AG_HD gf128 ag_stream_lane(const StreamParams& p, uint32_t g, uint32_t Gt, TE&& 
             ag_load_block(src, 16, x);
 #endif
         } else {
-            ag_load_block(src, bi < n_full ? 16u : tail, x);
+            ag_load_block_in(src, bi < n_full ? 16u : tail, x, p.in, p.in + p.n_bytes);
         }
     };
 
@@ -287,6 +361,9 @@ struct BatchParams {
     // k_batch, offset batches: the order in which the lane groups take the messages -- sorted by length
     // (longest first) so that the messages a warp works on side by side are equally long; null = 0, 1, 2, ...
     const uint32_t* perm;
+    // ... and the slice [range[0], range[1]) of that order this launch works on (device words written by the sort:
+    // one launch per length class, each with its own lane-group width); null = all n_msgs
+    const uint32_t* range;
     // k_batch_warp (a warp per unit): raw lane accumulators (32 x 16 B per unit id, BE words), unit
     // descriptors {message + 1 (0 = unused id), blocks after the unit}, per-message XOR accumulators
     // and E_K(J0) (n_msgs x 16 B each)
@@ -410,7 +487,8 @@ AG_HD MsgDesc ag_batch_segment(const MsgDesc& w, uint32_t seg, uint32_t S, uint6
 // An AAD row has no AES pass to hide its load behind, so the AAD block of row u+1 is fetched
 // before row u is processed (one row of software prefetch); a payload block is loaded at the top
 // of its own row and consumed after the AES rounds.
-template <int NR, bool DEC, class CACHE, class TE, class GH>
+// SEQ: the lane walks CONSECUTIVE payload blocks (G == 1), so unaligned output can leave granule by granule.
+template <int NR, bool DEC, bool SEQ = false, class CACHE, class TE, class GH>
 AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cache, const MsgDesc& d, uint32_t t,
                           uint32_t G, TE&& te, GH&& gh_g, uint32_t ej0[4])
 {
@@ -424,7 +502,14 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
     uint32_t i = t - pad;                 // wraps while inside the front padding (row 0 only)
     bool have = t >= pad;
     uint32_t nxt[4] = {0, 0, 0, 0};
-    if (rows && have && i < a) ag_load_block(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt);
+    const uint8_t* const aad_hi = d.aad + d.aad_len;
+    const uint8_t* const in_hi = d.in + d.len;
+#if defined(__CUDA_ARCH__)
+    AgStoreCarry carry;
+    carry.init();
+    const bool wide_st = SEQ && (((uintptr_t)d.out & 15) != 0);
+#endif
+    if (rows && have && i < a) ag_load_block_in(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt, d.aad, aad_hi);
     // Rows 0 .. aad_rows-1 hold AAD blocks only (row u spans blocks uG-pad .. uG+G-1-pad): they run in
     // a loop of their own -- prefetch, one table product, one XOR, like k_stream<GHASH_ONLY> -- so
     // that bulk AAD is not dragged through the AES-sized body of the general loop below.
@@ -471,7 +556,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
         const uint32_t s0 = nxt[0], s1 = nxt[1], s2 = nxt[2], s3 = nxt[3];
         i += G;
         have = true;
-        if (u + 1 < rows && i < a) ag_load_block(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt);
+        if (u + 1 < rows && i < a) ag_load_block_in(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt, d.aad, aad_hi);
         if (u) y = gf_mul_table(y, gh_g);
         if (hv) {
             y.w[0] ^= ag_bswap32(s0);
@@ -486,7 +571,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
         uint32_t s[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
         i += G;
         have = true;
-        if (u + 1 < rows && i < a) ag_load_block(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt);
+        if (u + 1 < rows && i < a) ag_load_block_in(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt, d.aad, aad_hi);
         if (u) y = gf_mul_table(y, gh_g);
         if (!hv) continue;
         if (ic >= a) {
@@ -497,7 +582,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
             const uint32_t j = ic - a;
             const uint32_t nv = (j == n - 1 && tail) ? tail : 16u;
             uint32_t x[4] = {0, 0, 0, 0};
-            if (!is_len) ag_load_block(d.in + 16 * (uint64_t)j, nv, x);   // in flight during the AES rounds
+            if (!is_len) ag_load_block_in(d.in + 16 * (uint64_t)j, nv, x, d.in, in_hi);   // in flight during the AES rounds
             uint32_t ks[4];
             aes_ctr_block_auto<NR>(rk, cc, cache, is_len ? d.j0ctr : d.j0ctr + 1u + d.ctr_off + j, te, ks);   // inc32: wraps mod 2^32
             if (is_len) {
@@ -511,7 +596,16 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
                 continue;
             }
             uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
+#if defined(__CUDA_ARCH__)
+            if (wide_st && nv == 16) {
+                carry.put(d.out + 16 * (uint64_t)j, o);
+            } else {
+                if (SEQ) carry.flush();
+                ag_store_block(d.out + 16 * (uint64_t)j, nv, o);
+            }
+#else
             ag_store_block(d.out + 16 * (uint64_t)j, nv, o);
+#endif
             if (DEC) {
                 s[0] = x[0]; s[1] = x[1]; s[2] = x[2]; s[3] = x[3];
             } else {
@@ -524,5 +618,8 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
         y.w[2] ^= ag_bswap32(s[2]);
         y.w[3] ^= ag_bswap32(s[3]);
     }
+#if defined(__CUDA_ARCH__)
+    if (SEQ) carry.flush();
+#endif
     return y;
 }

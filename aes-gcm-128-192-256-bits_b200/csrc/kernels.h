@@ -49,8 +49,9 @@ cudaError_t ag_launch_batch_tile(const TileParams& p, int nr, int decrypt, int n
 cudaError_t ag_launch_batch_perkey_tile(const TileParams& p, int nr, int decrypt, int max_cta, cudaStream_t st);
 // k_batch_warp + k_batch_warp_reduce + k_batch_split_finish (p.split, p.seg_parts, p.seg_acc, p.ticket set)
 cudaError_t ag_launch_batch_warp(const BatchParams& p, int nr, int decrypt, int ncta, cudaStream_t st);
-// counting sort of an offset batch by message length (longest first): perm[n_msgs], scratch hist[4096]
-cudaError_t ag_launch_len_sort(const BatchParams& p, uint32_t* hist4096, uint32_t* perm, cudaStream_t st);
+// counting sort of a ragged batch by message length (longest first): perm[n_msgs], scratch hist[4096], and the
+// [start, end) slices of the order that hold the long / medium / short messages (ranges6)
+cudaError_t ag_launch_len_sort(const BatchParams& p, uint32_t* hist4096, uint32_t* ranges6, uint32_t* perm, cudaStream_t st);
 cudaError_t ag_launch_batch_cta(const BatchParams& p, int nr, int decrypt, int ncta, int nt, cudaStream_t st);
 cudaError_t ag_launch_batch_perkey(const BatchParams& p, int nr, int decrypt, int max_cta, cudaStream_t st);
 cudaError_t ag_launch_key_expand(const uint8_t* keys, uint64_t n_keys, int key_bytes, const uint32_t* te0,

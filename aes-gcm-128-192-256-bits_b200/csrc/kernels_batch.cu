@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
     constexpr int LG = (G == 1) ? 0 : (G == 2) ? 1 : (G == 4) ? 2 : (G == 8) ? 3 : (G == 16) ? 4 : 5;
+    if (p.range && p.range[0] >= p.range[1]) return;   // an empty length class: not even the tables
     stage_te0(p.te0);
     fill_gh_tables(p.key->tab[LG], p.key->tab[0]);
     __syncthreads();
@@ -73,15 +74,16 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
     // launch) each warp draws its next 32/G messages when it is done with the last: messages of different
     // lengths (an offset batch) then no longer pin the grid to the warps that drew the long ones.
     const uint64_t warp_first = (uint64_t)blockIdx.x * groups_per_cta + (tid & ~31u) / G;
-    for (uint64_t w0 = warp_first, m = gid;; w0 += n_groups, m += n_groups) {
+    const uint64_t r0 = p.range ? p.range[0] : 0, r1 = p.range ? p.range[1] : p.n_msgs;   // this launch's slice of the order
+    for (uint64_t w0 = r0 + warp_first, m = r0 + gid;; w0 += n_groups, m += n_groups) {
         if (p.ticket) {
             uint32_t tk = 0;
             if (lane == 0) tk = atomicAdd(p.ticket, 32u / G);
-            w0 = __shfl_sync(0xffffffffu, tk, 0);
+            w0 = r0 + __shfl_sync(0xffffffffu, tk, 0);
             m = w0 + lane / G;
         }
-        if (w0 >= p.n_msgs) break;
-        const bool valid = m < p.n_msgs;
+        if (w0 >= r1) break;
+        const bool valid = m < r1;
         if (valid && p.perm) m = p.perm[m];
         gf128 y = gf_zero();
         AesCtrConst cc;
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
                 iv0 = ivw[0]; iv1 = ivw[1]; iv2 = ivw[2];
             }
             cc = aes_ctr_precompute(p.rk, iv0, iv1, iv2, te);
-            y = ag_batch_lane<NR, DEC>(p.rk, cc, cache, d, t, (uint32_t)G, te, gh_g, e);
+            y = ag_batch_lane<NR, DEC, G == 1>(p.rk, cc, cache, d, t, (uint32_t)G, te, gh_g, e);
         }
         __syncwarp();
         // R = sum_t Y_t H^(G-t)
@@ -638,6 +640,7 @@ __global__ void k_batch_split_finish(const __grid_constant__ BatchParams p)
 // ===========================================================================
 namespace {
 constexpr uint32_t AG_SORT_BUCKETS = 4096;
+constexpr uint32_t AG_SORT_LONG = 1024, AG_SORT_MID = 256;   // class limits in blocks of work: long >= 1024 > medium >= 256 > short
 __device__ __forceinline__ uint32_t ag_sort_bucket(const BatchParams& p, uint64_t m)
 {
     const MsgDesc d = ag_batch_msg(p, m);
@@ -660,7 +663,7 @@ __global__ void __launch_bounds__(256) k_len_hist(const __grid_constant__ BatchP
 }
 
 // exclusive scan of the 4096 bucket counts, in place (one CTA of 1024 threads, 4 buckets each)
-__global__ void __launch_bounds__(1024) k_len_scan(uint32_t* __restrict__ hist)
+__global__ void __launch_bounds__(1024) k_len_scan(uint32_t* __restrict__ hist, uint32_t* __restrict__ ranges)
 {
     __shared__ uint32_t part[1024];
     const uint32_t t = threadIdx.x;
@@ -676,6 +679,15 @@ __global__ void __launch_bounds__(1024) k_len_scan(uint32_t* __restrict__ hist)
     }
     uint32_t run = part[t] - s;
     for (int k = 0; k < 4; ++k) { hist[4 * t + k] = run; run += v[k]; }
+    __syncthreads();
+    // three length classes of the sorted order, one k_batch launch each (long: 32 lanes per message, medium: 4,
+    // short: 1): ranges[2c], ranges[2c+1].  Bucket b holds work 4095 - b blocks; the order is longest first.
+    if (t == 0) {
+        const uint32_t end_long = hist[AG_SORT_BUCKETS - AG_SORT_LONG], end_mid = hist[AG_SORT_BUCKETS - AG_SORT_MID];
+        ranges[0] = 0;        ranges[1] = end_long;
+        ranges[2] = end_long; ranges[3] = end_mid;
+        ranges[4] = end_mid;  ranges[5] = part[1023];
+    }
 }
 
 // Scatter, chunk by chunk of 2048 messages per CTA: a shared-memory histogram of the chunk, ONE global atomic per
@@ -711,13 +723,13 @@ __global__ void __launch_bounds__(256) k_len_scatter(const __grid_constant__ Bat
     }
 }
 
-cudaError_t ag_launch_len_sort(const BatchParams& p, uint32_t* hist4096, uint32_t* perm, cudaStream_t st)
+cudaError_t ag_launch_len_sort(const BatchParams& p, uint32_t* hist4096, uint32_t* ranges6, uint32_t* perm, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(hist4096, 0, sizeof(uint32_t) * AG_SORT_BUCKETS, st);
     if (e != cudaSuccess) return e;
     const unsigned nb = (unsigned)((p.n_msgs + 255) / 256 < 1184 ? (p.n_msgs + 255) / 256 : 1184);
     k_len_hist<<<nb, 256, 0, st>>>(p, hist4096);
-    k_len_scan<<<1, 1024, 0, st>>>(hist4096);
+    k_len_scan<<<1, 1024, 0, st>>>(hist4096, ranges6);
     k_len_scatter<<<nb, 256, 0, st>>>(p, hist4096, perm);
     return cudaGetLastError();
 }

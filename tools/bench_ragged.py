@@ -18,7 +18,8 @@ for kb in (16, 32):
         d_in = torch.randint(0, 256, (total,), dtype=torch.uint8, device="cuda"); d_out = torch.empty_like(d_in)
         d_off = torch.from_numpy(off).cuda()
         d_iv = torch.randint(0, 256, (12 * n,), dtype=torch.uint8, device="cuda"); d_tags = torch.zeros(16 * n, dtype=torch.uint8, device="cuda")
-        fn = lambda: eng.batch_crypt_device(0, d_iv, None, None, d_in, d_off, d_out, d_tags, avg_len_hint=int(lens.mean()))
+        fn = lambda: eng.batch_crypt_device(0, d_iv, None, None, d_in, d_off, d_out, d_tags, avg_len_hint=int(lens.mean()),
+                                            lanes=int(os.environ.get("AGCM_RAGGED_LANES", "0")))
         for _ in range(2): fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
