@@ -36,12 +36,14 @@
  *     1024 shard partials; agcm_peer_setup up to 16 ranks; the host-buffer stream call up to
  *     1024 x 64 MiB per call.  AAD of any length (bytes 4097.. run through the grid-wide GHASH).
  *   - Device buffers may have any byte alignment; 16-byte alignment selects the 128-bit
- *     load/store path (4-byte alignment a 32-bit path, anything else bytes).  Fixed-size records at a
- *     16-byte-aligned pitch additionally take the TMA-staged batch kernels.
+ *     load/store path (4-byte alignment a 32-bit path, anything else bytes; batched messages that a single
+ *     lane walks are read and written as realigned 16-byte granules whatever their address).  Fixed-size
+ *     records at a 16-byte-aligned pitch additionally take the TMA-staged batch kernels.
  *   - Environment (read by the library, all optional; none changes a result): AGCM_CHUNK_MB (granule of
  *     the host-buffer pipeline, 1..64, default 32), AGCM_PEER_TIMEOUT_MS (default 10000), and the A/B
  *     switches of the layout choice AGCM_NO_TILE, AGCM_PERKEY_TILE=0|1, AGCM_NO_WARP_UNITS,
- *     AGCM_WARP_MIN_BLOCKS.
+ *     AGCM_WARP_MIN_BLOCKS, AGCM_NO_LEN_SORT (ragged batches in arrival order), AGCM_NO_LEN_CLASSES
+ *     (sorted, but one lane count for the whole batch).
  */
 #ifndef AESGCM_B200_H
 #define AESGCM_B200_H

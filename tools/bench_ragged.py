@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Offset (ragged) batches: an IMIX-like mix of packet sizes and a heavy-tailed mix, 2^20 messages, AES-128 and AES-256,
-through agcm_batch_crypt (lanes = 0).  AGCM_NO_BATCH_TICKET=1 in the environment gives the static assignment for comparison."""
+through agcm_batch_crypt (lanes = 0) and agcm_batch_crypt_slots.  AGCM_NO_LEN_SORT=1 in the environment gives the arrival-order
+assignment for comparison, AGCM_NO_LEN_CLASSES=1 the sorted order under one lane count, AGCM_RAGGED_LANES=G a fixed lane count."""
 import os, sys, json
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch, aesgcm_b200
