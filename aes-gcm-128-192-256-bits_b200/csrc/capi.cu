@@ -13,6 +13,7 @@
 
 #include "../../include/aesgcm_b200.h"
 #include "kernels.h"
+#include "host_sched.h"
 
 namespace {
 
@@ -97,6 +98,7 @@ struct agcm_ctx {
     size_t verify_cap = 0;
     bool pipeline_ready = false;
     size_t chunk_bytes = 32u << 20;
+    size_t ramp_base = 1u << 20;         // first and last granule of the host pipeline (host_sched.h)
 };
 
 namespace {
@@ -354,6 +356,10 @@ int ensure_pipeline(agcm_ctx* c)
     if (const char* e = getenv("AGCM_CHUNK_MB")) {
         const long mb = atol(e);
         if (mb >= 1 && (size_t)mb <= (kChunkBytesMax >> 20)) c->chunk_bytes = (size_t)mb << 20;
+    }
+    if (const char* e = getenv("AGCM_RAMP_KB")) {   // first / last granule of a host-buffer call; 0 = equal granules
+        const long kb = atol(e);
+        if (kb >= 0 && (size_t)kb <= (kChunkBytesMax >> 10)) c->ramp_base = (size_t)kb << 10;
     }
     for (int s = 0; s < kSlots; ++s) {
         AG_CUDA(c, cudaStreamCreateWithFlags(&c->hs[s], cudaStreamNonBlocking));
@@ -1492,21 +1498,25 @@ static int host_pipeline(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], uin
 {
     const uint64_t nblocks = (n_bytes + 15) >> 4;
     const uint64_t kChunkBytes = pick_chunk(c, n_bytes);
-    const uint64_t n_chunks = (n_bytes + kChunkBytes - 1) / kChunkBytes;
-    if (n_chunks > kMaxChunks || n_chunks > SC_PARTS_MAX) return AGCM_E_BAD_LEN;
+    // ramped granule sizes (host_sched.h): the first kernel starts after `ramp_base` bytes, not after a whole granule
+    uint64_t sizes[SC_PARTS_MAX];
+    const uint64_t n_chunks = ag_chunk_schedule(n_bytes, kChunkBytes, c->ramp_base < kChunkBytes ? c->ramp_base : 0, sizes,
+                                                (uint32_t)SC_PARTS_MAX);
+    if (n_bytes && !n_chunks) return AGCM_E_BAD_LEN;
     const int mode = decrypt ? AG_MODE_DEC : AG_MODE_ENC;
+    uint64_t off = 0;
     for (uint64_t k = 0; k < n_chunks; ++k) {
         const int s = (int)(k % kSlots);
         cudaStream_t st = c->hs[s];
-        const uint64_t off = k * kChunkBytes;
-        const uint64_t nb = (n_bytes - off) < kChunkBytes ? (n_bytes - off) : kChunkBytes;
+        const uint64_t nb = sizes[k];
         const uint64_t fb = off >> 4;
         const uint64_t after = nblocks - fb - ((nb + 15) >> 4) + blocks_after0;
         AG_CUDA(c, cudaMemcpyAsync(c->d_stage[s], h_in + off, nb, cudaMemcpyHostToDevice, st));
-        int rc = run_stream(c, mode, h_iv12, first_block0 + fb, c->d_stage[s], c->d_stage[s], nb, after,
-                            c->d_stage_parts[s], c->d_chunk_partials + 16 * k, st, c->d_counters + 1 + s);
+        int rc = run_stream(c, mode, h_iv12, first_block0 + fb, c->d_stage[s], c->d_stage[s], nb,
+                            after, c->d_stage_parts[s], c->d_chunk_partials + 16 * k, st, c->d_counters + 1 + s);
         if (rc) return rc;
         AG_CUDA(c, cudaMemcpyAsync(h_out + off, c->d_stage[s], nb, cudaMemcpyDeviceToHost, st));
+        off += nb;
     }
     *n_chunks_out = n_chunks;
     return AGCM_OK;
@@ -1631,8 +1641,10 @@ int agcm_stream_crypt_host(agcm_ctx* c, int decrypt, const uint8_t h_iv12[12], c
     if (aad_len) AG_CUDA(c, cudaMemcpyAsync(c->d_aad_stage, h_aad, aad_len, cudaMemcpyHostToDevice, c->hs[0]));
     uint8_t* d_tag = c->d_scratch + SC_TAG;
     uint8_t* d_ok = c->d_scratch + SC_OK;
-    if (n_bytes && n_bytes <= c->chunk_bytes && aad_len <= kAadInlineMax) {
-        // one granule: copy in, ONE launch (the kernel's last CTA finishes the tag), copy out, one wait
+    const uint64_t one_shot = (c->ramp_base && 2 * c->ramp_base < c->chunk_bytes) ? 2 * c->ramp_base : c->chunk_bytes;
+    if (n_bytes && n_bytes <= one_shot && aad_len <= kAadInlineMax) {
+        // short message: copy in, ONE launch (the kernel's last CTA finishes the tag), copy out, one wait;
+        // anything longer overlaps its copies with the kernel granule by granule
         cudaStream_t st = c->hs[0];
         AG_CUDA(c, cudaMemcpyAsync(c->d_stage[0], h_in, n_bytes, cudaMemcpyHostToDevice, st));
         if (decrypt) AG_CUDA(c, cudaMemcpyAsync(d_tag, h_tag, 16, cudaMemcpyHostToDevice, st));

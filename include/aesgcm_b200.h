@@ -40,7 +40,8 @@
  *     lane walks are read and written as realigned 16-byte granules whatever their address).  Fixed-size
  *     records at a 16-byte-aligned pitch additionally take the TMA-staged batch kernels.
  *   - Environment (read by the library, all optional; none changes a result): AGCM_CHUNK_MB (granule of
- *     the host-buffer pipeline, 1..64, default 32), AGCM_PEER_TIMEOUT_MS (default 10000), and the A/B
+ *     the host-buffer pipeline, 1..64, default 32), AGCM_RAMP_KB (its first and last granule, default 1024;
+ *     0 = equal granules), AGCM_PEER_TIMEOUT_MS (default 10000), and the A/B
  *     switches of the layout choice AGCM_NO_TILE, AGCM_PERKEY_TILE=0|1, AGCM_NO_WARP_UNITS,
  *     AGCM_WARP_MIN_BLOCKS, AGCM_NO_LEN_SORT (ragged batches in arrival order), AGCM_NO_LEN_CLASSES
  *     (sorted, but one lane count for the whole batch).

@@ -14,6 +14,7 @@
 
 #include "../aes-gcm-128-192-256-bits_b200/csrc/gcm_core.cuh"
 #include "../aes-gcm-128-192-256-bits_b200/csrc/perkey_core.cuh"
+#include "../aes-gcm-128-192-256-bits_b200/csrc/host_sched.h"
 
 namespace {
 
@@ -428,5 +429,11 @@ void emul_gf_mul_table(const uint8_t x[16], const uint8_t c[16], uint8_t out[16]
 void emul_gf_sqr(const uint8_t a[16], uint8_t out[16]) { gf_to_bytes(gf_sqr(gf_from_bytes(a)), out); }
 
 void emul_sbox(uint8_t out[256]) { memcpy(out, tables().sbox, 256); }
+
+// granule schedule of the host-buffer pipeline (csrc/host_sched.h)
+uint32_t emul_chunk_schedule(uint64_t n, uint64_t peak, uint64_t base, uint64_t* sz, uint32_t cap)
+{
+    return ag_chunk_schedule(n, peak, base, sz, cap);
+}
 
 }  // extern "C"

@@ -1824,3 +1824,39 @@ def test_config3_full_size_roundtrip(engine, oracle, torch_mod):
     assert int(d_ok.sum().item()) == n_msgs
     v = d_back.view(n_msgs, stride)[:, :length]
     assert torch.equal(v, d_pt.view(n_msgs, stride)[:, :length])
+
+
+@pytest.mark.gpu
+def test_host_pipeline_ramped_granules(engine, torch_mod):
+    """Host-buffer calls long enough for the ramped granule schedule (csrc/host_sched.h: 1, 2, 4 ... MiB up, the odd
+    rest, the steady granules, and back down): every byte and the tag against OpenSSL, encrypt and decrypt, pageable and
+    pinned buffers, lengths around the one-shot limit (2 MiB) and off every granule boundary; then the same message
+    as two counter-range shards through agcm_stream_part_host / agcm_stream_finish_host."""
+    AESGCM = pytest.importorskip("cryptography.hazmat.primitives.ciphers.aead").AESGCM
+    torch = torch_mod
+    rng = np.random.default_rng(123)
+    key, iv, aad = _rb(rng, 32), _rb(rng, 12), _rb(rng, 21)
+    engine.set_key(key)
+    ossl = AESGCM(key)
+    MiB = 1 << 20
+    for n in (2 * MiB, 2 * MiB + 1, 3 * MiB + 16, 8 * MiB, 37 * MiB + 4097, 95 * MiB - 5):
+        pt = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        pt.random_(0, 256)
+        want = ossl.encrypt(iv, pt.numpy().tobytes(), aad)
+        out = torch.zeros(n, dtype=torch.uint8, pin_memory=True)
+        _, tag = engine.encrypt(iv, aad, pt, out=out)
+        assert tag == want[-16:], n
+        assert out.numpy().tobytes() == want[:-16], n
+        back = np.zeros(n, dtype=np.uint8)                       # pageable output
+        engine.decrypt(iv, aad, out, tag, out=back)
+        assert back.tobytes() == pt.numpy().tobytes(), n
+        with pytest.raises(ValueError):
+            engine.decrypt(iv, aad, out, bytes([tag[0] ^ 1]) + tag[1:], out=back)
+    # two shards of the last message, cut off a granule boundary
+    cut = (41 * MiB + 4096) & ~15
+    o2 = np.zeros(n, dtype=np.uint8)
+    src = pt.numpy()
+    p0 = engine.stream_part_host(0, iv, 0, src[:cut], o2[:cut], ((n - cut) + 15) // 16)
+    p1 = engine.stream_part_host(0, iv, cut // 16, src[cut:], o2[cut:], 0)
+    assert o2.tobytes() == want[:-16]
+    assert engine.stream_finish_host(0, iv, p0 + p1, aad, n) == want[-16:]

@@ -212,3 +212,47 @@ def test_perkey_messages(emul, oracle, kb):
             assert list(ok) == [1, 1, 1, 1, 0] + [1] * 7
         else:
             assert (tag == et).all(), kb
+
+
+def test_host_pipeline_granule_schedule(emul):
+    """csrc/host_sched.h: the ramped granule list of the host-buffer pipeline covers the range exactly, keeps every
+    granule but the last a whole number of counter blocks, never exceeds the stage buffer, starts and ends small, and
+    falls back to equal granules when the list would not fit."""
+    emul.emul_chunk_schedule.restype = ctypes.c_uint32
+    MiB = 1 << 20
+    cap = 1024
+    sz = np.zeros(cap, np.uint64)
+
+    def plan(n, peak, base, cap_=cap):
+        k = emul.emul_chunk_schedule(ctypes.c_uint64(n), ctypes.c_uint64(peak), ctypes.c_uint64(base), u64p(sz), cap_)
+        return [int(x) for x in sz[:k]]
+
+    assert plan(0, 32 * MiB, 2 * MiB) == []
+    rng = np.random.default_rng(5)
+    sizes = [1, 15, 16, 17, MiB, 4 * MiB, 4 * MiB + 1, 8 * MiB, 8 * MiB + 5, 32 * MiB, 32 * MiB + 4097, 92 * MiB - 1, 92 * MiB,
+             92 * MiB + 16, 1 << 30, (1 << 30) + 7, 3 << 30] + [int(x) for x in rng.integers(1, 1 << 31, 200)]
+    for peak, base in ((32 * MiB, 2 * MiB), (32 * MiB, MiB), (24 * MiB, 2 * MiB), (64 * MiB, 4 * MiB), (32 * MiB, 0), (2 * MiB, 2 * MiB)):
+        for n in sizes:
+            p = plan(n, peak, base)
+            if (n + peak - 1) // peak > cap:      # the caller grows the granule first (pick_chunk)
+                assert p == []
+                continue
+            assert sum(p) == n and all(x > 0 for x in p), (n, peak, base)
+            assert all(x % 16 == 0 for x in p[:-1])
+            assert max(p) <= peak + 15
+            if base and base < peak and n >= 3 * peak:
+                assert p[0] == base and base <= p[-1] < base + 16          # ramps at both ends
+                lmax = (peak // base).bit_length() - 1
+                assert p[:lmax] == [base << i for i in range(lmax)]
+                assert [x & ~15 for x in p[-lmax:]] == [base << i for i in reversed(range(lmax))]
+                assert len(p) <= n // peak + 2 * 8 + 2
+            if not base or base >= peak:
+                assert p == [peak] * (n // peak) + ([n % peak] if n % peak else [])
+    # one GiB at the defaults: 2, 4, 8, 16 MiB, the odd rest, 30 x 32 MiB ... and back down
+    p = plan(1 << 30, 32 * MiB, 2 * MiB)
+    assert p[:4] == [2 * MiB, 4 * MiB, 8 * MiB, 16 * MiB] and p[-4:] == [16 * MiB, 8 * MiB, 4 * MiB, 2 * MiB]
+    # a short range shortens the ramp instead of dropping it
+    assert plan(8 * MiB, 32 * MiB, 2 * MiB) == [2 * MiB, 4 * MiB, 2 * MiB]
+    # does not fit the list: equal granules; cannot fit at all: 0
+    assert plan(64 * MiB, 32 * MiB, 2 * MiB, 3) == [32 * MiB, 32 * MiB]
+    assert plan(64 * MiB + 1, 32 * MiB, 2 * MiB, 2) == []
