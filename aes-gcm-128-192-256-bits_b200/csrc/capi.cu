@@ -1174,7 +1174,9 @@ typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int tile_tensor_map(agcm_ctx* c, CUtensorMap* tm, const uint8_t* base, uint64_t len, uint64_t stride, uint64_t n_msgs)
+// box_rows: AG_TILE_BOX_MSGS for the one-box loads, 1 for the row-gathering form (tile::gather4 / scatter4)
+static int tile_tensor_map(agcm_ctx* c, CUtensorMap* tm, const uint8_t* base, uint64_t len, uint64_t stride, uint64_t n_msgs,
+                           uint32_t box_rows = AG_TILE_BOX_MSGS)
 {
     if (!c->tmap_encode) {
         void* fn = nullptr;
@@ -1187,7 +1189,7 @@ static int tile_tensor_map(agcm_ctx* c, CUtensorMap* tm, const uint8_t* base, ui
     // the batch as a 2-D byte tensor: dim 0 = the bytes of a record (extent len), dim 1 = the messages (pitch = stride)
     const cuuint64_t dims[2] = {len, n_msgs};
     const cuuint64_t strides[1] = {stride};
-    const cuuint32_t box[2] = {AG_TILE_BOX_BYTES, AG_TILE_BOX_MSGS};
+    const cuuint32_t box[2] = {AG_TILE_BOX_BYTES, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = reinterpret_cast<tmap_encode_fn>(c->tmap_encode)(
         tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1238,7 +1240,71 @@ static int batch_tile(agcm_ctx* c, int decrypt, BatchParams& p, size_t n_msgs, c
     const uint64_t groups = (n_msgs + 31) / 32, per_cta = (uint64_t)AG_STREAM_NT_MAX / 32;
     const uint64_t need = (groups + per_cta - 1) / per_cta;
     const int ncta = (int)(need < (uint64_t)c->ncta ? need : (uint64_t)c->ncta);
-    AG_CUDA(c, ag_launch_batch_tile(t, c->nr, decrypt, ncta, st));
+    AG_CUDA(c, ag_launch_batch_tile(t, c->nr, decrypt, 0, ncta, st));
+    c->launches++;
+    return AGCM_OK;
+}
+
+// Slots (fixed 16-byte aligned pitch, a length per message) through the row-gathering form of the tiled kernel:
+// every message fits a lane's share (pitch <= 16 KiB) and there are enough of them to fill the grid.
+static bool tile_slots_eligible(const agcm_ctx* c, int lanes, const BatchParams& p, size_t n_msgs)
+{
+    if (lanes != 0 && lanes != 2048) return false;
+    if (!p.len_arr || p.stride == 0 || p.stride >= (1ull << 31) || n_msgs >= (1ull << 30) || c->no_ticket) return false;
+    if ((((uintptr_t)p.in | (uintptr_t)p.out) & 15) || (p.stride & 15)) return false;
+    if (lanes == 2048) return true;   // asked for by name
+    // Not a default: measured against the lane-group classes on 2^20 messages (profiles/r2_ragged.md) it is within
+    // +-3 % -- with 16-byte aligned slots two lanes per message already fetch whole sectors, and the per-message work
+    // that dominates short packets (IV, J0, tag) is the same in both.  AGCM_GATHER=1 makes it the choice for A/B runs.
+    if (!getenv("AGCM_GATHER") || getenv("AGCM_NO_TILE")) return false;
+    if (p.stride > 16384) return false;                                              // a message per lane: short messages
+    if (p.aad && (p.aad_len_arr ? p.aad_stride : p.aad_len) > 4096) return false;   // long AAD: the lane-group layouts
+    return n_msgs >= (size_t)c->ncta * (size_t)c->nt;
+}
+
+static int batch_tile_slots(agcm_ctx* c, int decrypt, BatchParams& p, size_t n_msgs, cudaStream_t st)
+{
+    if (!c->key_set) return AGCM_E_NO_KEY;
+    if (!p.iv || !p.tag || (decrypt && !p.ok)) return AGCM_E_BAD_ARG;
+    AG_CUDA(c, cudaSetDevice(c->device));
+    if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, 4 * sizeof(uint32_t)));
+    memcpy(p.rk, c->h_rk, sizeof(p.rk));
+    p.key = c->d_key;
+    p.te0 = c->d_te0;
+    p.n_msgs = n_msgs;
+    // length order (longest first): the 32 messages a warp takes side by side are equally long
+    if (n_msgs >= 64 && !getenv("AGCM_NO_LEN_SORT")) {
+        const size_t need_b = sizeof(uint32_t) * (4096 + 8 + (size_t)n_msgs);
+        if (need_b > c->sort_cap) {
+            AG_CUDA(c, cudaFree(c->d_sort));
+            c->d_sort = nullptr;
+            c->sort_cap = 0;
+            AG_CUDA(c, cudaMalloc(&c->d_sort, need_b));
+            c->sort_cap = need_b;
+        }
+        AG_CUDA(c, ag_launch_len_sort(p, c->d_sort, c->d_sort + 4096, c->d_sort + 4096 + 8, st));
+        c->launches += 3;
+        p.perm = c->d_sort + 4096 + 8;
+    }
+    TileParams t;
+    memset(&t, 0, sizeof(t));
+    t.b = p;
+    // whole slots as rows: a lane masks what lies past its message, and rows are stored only where whole blocks are
+    int rc = tile_tensor_map(c, &t.tm_in, p.in, p.stride, p.stride, n_msgs, 1);
+    if (rc) return rc;
+    rc = tile_tensor_map(c, &t.tm_out, p.out, p.stride, p.stride, n_msgs, 1);
+    if (rc) return rc;
+    if (p.aad && p.aad_len && !p.aad_len_arr && !((uintptr_t)p.aad & 15) && !(p.aad_stride & 15)) {   // AAD of one length: tiled too
+        rc = tile_tensor_map(c, &t.tm_aad, p.aad, (p.aad_len + 15) & ~15ull, p.aad_stride, n_msgs, 1);
+        if (rc) return rc;
+        t.aad_tiled = 1;
+    }
+    t.ticket = c->d_tile_ticket;
+    AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), st));
+    const uint64_t groups = (n_msgs + 31) / 32, per_cta = (uint64_t)AG_STREAM_NT_MAX / 32;
+    const uint64_t need = (groups + per_cta - 1) / per_cta;
+    const int ncta = (int)(need < (uint64_t)c->ncta ? need : (uint64_t)c->ncta);
+    AG_CUDA(c, ag_launch_batch_tile(t, c->nr, decrypt, 1, ncta, st));
     c->launches++;
     return AGCM_OK;
 }
@@ -1352,7 +1418,8 @@ int agcm_batch_crypt_slots(agcm_ctx* c, int decrypt, int lanes, const uint8_t* d
     p.aad_stride = has_aad ? aad_stride : 0;
     p.aad_len_arr = has_aad ? d_aad_len : nullptr;
     const bool aligned16 = ((((uintptr_t)d_in | (uintptr_t)d_out) | stride) & 15) == 0;
-    if (lanes == 2048) return AGCM_E_BAD_ARG;   // the TMA-staged kernel takes records of ONE length
+    if (lanes == 2048 && !tile_slots_eligible(c, lanes, p, n_msgs)) return AGCM_E_BAD_ARG;   // needs 16-byte aligned slots
+    if (n_msgs && tile_slots_eligible(c, lanes, p, n_msgs)) return batch_tile_slots(c, decrypt, p, n_msgs, (cudaStream_t)stream);
     return batch_common(c, decrypt, lanes, avg_len_hint ? avg_len_hint : stride / 2, p, n_msgs, stream, aligned16);
 }
 

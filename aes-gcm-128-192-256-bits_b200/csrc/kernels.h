@@ -45,7 +45,9 @@ struct TileParams {
     uint32_t* ticket;            // zero at launch: next group of 32 messages
 };
 constexpr uint32_t AG_TILE_BOX_BYTES = 32, AG_TILE_BOX_MSGS = 32;
-cudaError_t ag_launch_batch_tile(const TileParams& p, int nr, int decrypt, int ncta, cudaStream_t st);
+// gather = 1: rows named one by one (tile::gather4 / scatter4; tensor maps with box {32 bytes, 1 message}), messages
+// of different lengths in fixed-pitch slots, taken in the order b.perm
+cudaError_t ag_launch_batch_tile(const TileParams& p, int nr, int decrypt, int gather, int ncta, cudaStream_t st);
 cudaError_t ag_launch_batch_perkey_tile(const TileParams& p, int nr, int decrypt, int max_cta, cudaStream_t st);
 // k_batch_warp + k_batch_warp_reduce + k_batch_split_finish (p.split, p.seg_parts, p.seg_acc, p.ticket set)
 cudaError_t ag_launch_batch_warp(const BatchParams& p, int nr, int decrypt, int ncta, cudaStream_t st);

@@ -168,6 +168,15 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch(const __grid_cons
 // arrive as zeros and are clipped on the way out.
 // Two tiles per warp (load of tile t+1 in flight while tile t is processed); groups of 32
 // messages are handed out by an atomic ticket, so no warp idles while another still has a queue.
+//
+// GATHER = true: messages of DIFFERENT lengths in fixed-pitch slots (agcm_batch_crypt_slots), taken in
+// the length-sorted order perm[].  A warp's 32 messages are then 32 arbitrary rows of the tensor, which
+// the Blackwell TMA addresses directly: tile::gather4 loads four named rows x 32 bytes (box {32, 1}),
+// tile::scatter4 stores them; eight lanes issue one each per tile, all completing on the warp's
+// mbarrier.  A row index past the tensor reads zeros and writes nothing (tools/gather4_probe.cu), which
+// is how lanes without a message, and rows whose 32 bytes are not both whole blocks of their message,
+// are kept out of the store: those last one or two blocks leave by the lane's own stores, so no byte
+// past a message's length is written.  The tile loop runs to the longest of the 32 messages.
 // ===========================================================================
 namespace {
 constexpr uint32_t SM_TILE_BAR = SM_MISC + 1024;          // 16 warps x 2 mbarriers
@@ -175,7 +184,7 @@ constexpr uint32_t SM_TILE = SM_MISC + 2048;              // 16 warps x 2 tiles 
 constexpr size_t kTileSmemBytes = SM_TILE + (AG_STREAM_NT_MAX / 32) * 2 * TILE_BYTES;
 }  // namespace
 
-template <int NR, bool DEC>
+template <int NR, bool DEC, bool GATHER>
 __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid_constant__ TileParams P)
 {
     const BatchParams& p = P.b;
@@ -204,29 +213,50 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
     const uint32_t coff0 = lane * 32 + ((0 ^ sw) << 4), coff1 = lane * 32 + ((1 ^ sw) << 4);
     uint32_t par0 = 0, par1 = 0;
 
-    const uint32_t n_blocks = (uint32_t)((p.len + 15) >> 4), tail = (uint32_t)(p.len & 15), n_full = (uint32_t)(p.len >> 4);
-    const uint32_t n_tiles = (n_blocks + 1) >> 1;
-    const uint32_t a_blocks = (uint32_t)((p.aad_len + 15) >> 4), atail = (uint32_t)(p.aad_len & 15);
+    // uniform records: the same for every lane; GATHER: this lane's message, set per group
+    uint64_t len = p.len, aad_len = p.aad_len;
+    uint32_t n_blocks = (uint32_t)((len + 15) >> 4), tail = (uint32_t)(len & 15), n_full = (uint32_t)(len >> 4);
+    uint32_t a_blocks = (uint32_t)((aad_len + 15) >> 4), atail = (uint32_t)(aad_len & 15);
     // the unified sequence AAD | CT (gcm_ghash.vhd:259-272) as ONE stream of tiles through the two buffers
+    // (tiled AAD has one length for all messages, also with GATHER)
     const uint32_t a_tiles = P.aad_tiled ? (a_blocks + 1) >> 1 : 0;
-    const uint32_t tot_tiles = a_tiles + n_tiles;
+    uint32_t tot_tiles = a_tiles + ((n_blocks + 1) >> 1);
     const uint32_t n_groups = (uint32_t)((p.n_msgs + 31) >> 5);
+    const bool issuer = GATHER ? (lane & 3) == 0 : lane == 0;   // lanes that talk to the TMA unit
+    const int32_t row_none = (int32_t)p.n_msgs;                 // the first row past the tensors
     for (;;) {
         uint32_t g = 0;
         if (lane == 0) g = atomicAdd(P.ticket, 1u);
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= n_groups) break;
         const int32_t row0 = (int32_t)(g * 32);
-        auto issue = [&](uint32_t T, uint32_t buf) {   // lane 0 only
-            const uint32_t bar = buf ? bar1 : bar0;
-            ag_mbar_expect_tx(bar, TILE_BYTES);
-            if (T < a_tiles) ag_tma_load_2d(tile_sa + buf * TILE_BYTES, &P.tm_aad, (int32_t)(T * 32), row0, bar);
-            else ag_tma_load_2d(tile_sa + buf * TILE_BYTES, &P.tm_in, (int32_t)((T - a_tiles) * 32), row0, bar);
-        };
-        if (lane == 0 && tot_tiles) issue(0, 0);
         const uint64_t m_raw = (uint64_t)g * 32 + lane;
         const bool valid = m_raw < p.n_msgs;
-        const uint64_t m = valid ? m_raw : p.n_msgs - 1;   // idle lanes of the last group shadow a real message
+        uint64_t m = valid ? m_raw : p.n_msgs - 1;   // idle lanes of the last group shadow a real message
+        int32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;     // GATHER: the rows of this lane's quad
+        if constexpr (GATHER) {
+            if (p.perm) m = p.perm[m];
+            const MsgDesc d = ag_batch_msg(p, m);
+            len = d.len;
+            aad_len = d.aad_len;
+            n_blocks = (uint32_t)((len + 15) >> 4); tail = (uint32_t)(len & 15); n_full = (uint32_t)(len >> 4);
+            a_blocks = (uint32_t)((aad_len + 15) >> 4); atail = (uint32_t)(aad_len & 15);
+            tot_tiles = a_tiles + __reduce_max_sync(0xffffffffu, (n_blocks + 1) >> 1);
+            const int32_t row = valid ? (int32_t)m : row_none;
+            r0 = __shfl_sync(0xffffffffu, row, (lane & ~3u) + 0);
+            r1 = __shfl_sync(0xffffffffu, row, (lane & ~3u) + 1);
+            r2 = __shfl_sync(0xffffffffu, row, (lane & ~3u) + 2);
+            r3 = __shfl_sync(0xffffffffu, row, (lane & ~3u) + 3);
+        }
+        auto issue = [&](uint32_t T, uint32_t buf) {   // issuer lanes only
+            const uint32_t bar = buf ? bar1 : bar0;
+            if (lane == 0) ag_mbar_expect_tx(bar, TILE_BYTES);
+            const CUtensorMap* tm = T < a_tiles ? &P.tm_aad : &P.tm_in;
+            const int32_t col = (int32_t)((T < a_tiles ? T : T - a_tiles) * 32);
+            if constexpr (GATHER) ag_tma_gather4(tile_sa + buf * TILE_BYTES + lane * 32, tm, col, r0, r1, r2, r3, bar);
+            else ag_tma_load_2d(tile_sa + buf * TILE_BYTES, tm, col, row0, bar);
+        };
+        if (issuer && tot_tiles) issue(0, 0);
         uint32_t ivw[3], j0ctr;
         ag_batch_iv(p, m, ivw, &j0ctr);
         const AesCtrConst cc = aes_ctr_precompute(p.rk, ivw[0], ivw[1], ivw[2], te);
@@ -244,7 +274,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
         }
         for (uint32_t T = 0; T < tot_tiles; ++T) {
             const uint32_t b = T & 1;
-            if (lane == 0 && T + 1 < tot_tiles) {
+            if (issuer && T + 1 < tot_tiles) {
                 ag_bulk_wait_read0();   // the store of tile T-1 has read the buffer tile T+1 lands in
                 issue(T + 1, b ^ 1);
             }
@@ -266,25 +296,28 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
                 continue;
             }
             const uint32_t t = T - a_tiles;
+            // GATHER: this row leaves through the TMA only if both of its blocks in the tile are whole
+            const bool row_by_tma = !GATHER || 2 * t + 2 <= n_full;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const uint32_t j = 2 * t + k;
-                if (j < n_blocks) {   // uniform
+                if (j < n_blocks) {   // uniform unless GATHER
                     uint4* cp = reinterpret_cast<uint4*>(tb + (k ? coff1 : coff0));
                     const uint4 xv = *cp;
                     uint32_t x[4] = {xv.x, xv.y, xv.z, xv.w};
-                    const bool ragged = (j == n_full);   // the record's short last block (uniform)
+                    const bool ragged = (j == n_full);   // the record's short last block
                     if (ragged) ag_mask_block(x, tail);  // the load box reaches into the caller's padding
                     uint32_t ks[4];
                     aes_ctr_block_seq<NR>(p.rk, cc, cache, j0ctr + 1u + j, te, ks);
                     uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
-                    if (!ragged) {
+                    if (!ragged && row_by_tma) {
                         *cp = make_uint4(o[0], o[1], o[2], o[3]);
                     } else {
-                        // the store tensor ends at the last WHOLE block: the tail goes out byte-wise, once
-                        // per message, so that the padding between records is never written
-                        if (valid) ag_store_block(p.out + m * p.stride + 16 * (uint64_t)j, tail, o);
-                        ag_mask_block(o, tail);
+                        // the store tensor ends at the last WHOLE block (GATHER: the row is left out of the
+                        // scatter): these bytes go out by the lane's own stores, once per message, so that
+                        // the padding between records is never written
+                        if (valid) ag_store_block(p.out + m * p.stride + 16 * (uint64_t)j, ragged ? tail : 16u, o);
+                        if (ragged) ag_mask_block(o, tail);
                     }
                     if (DEC) {
                         y.w[0] ^= ag_bswap32(x[0]); y.w[1] ^= ag_bswap32(x[1]); y.w[2] ^= ag_bswap32(x[2]); y.w[3] ^= ag_bswap32(x[3]);
@@ -294,7 +327,17 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
                     y = gf_mul_table(y, gh);
                 }
             }
-            if (2 * t < n_full) {   // uniform: the tile holds at least one whole block
+            if constexpr (GATHER) {
+                const int32_t row = (valid && row_by_tma) ? (int32_t)m : row_none;
+                const int32_t s0 = __shfl_sync(0xffffffffu, row, (lane & ~3u) + 0), s1 = __shfl_sync(0xffffffffu, row, (lane & ~3u) + 1);
+                const int32_t s2 = __shfl_sync(0xffffffffu, row, (lane & ~3u) + 2), s3 = __shfl_sync(0xffffffffu, row, (lane & ~3u) + 3);
+                ag_fence_async_smem();
+                __syncwarp();
+                if (issuer && (s0 != row_none || s1 != row_none || s2 != row_none || s3 != row_none)) {
+                    ag_tma_scatter4(&P.tm_out, (int32_t)(t * 32), s0, s1, s2, s3, tile_sa + b * TILE_BYTES + lane * 32);
+                    ag_bulk_commit();
+                }
+            } else if (2 * t < n_full) {   // uniform: the tile holds at least one whole block
                 ag_fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -307,7 +350,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
         }
         // length block (gcm_ghash.vhd:257), last multiply, E_K(J0) (gcm_ghash.vhd:293)
         {
-            const uint64_t ab = p.aad_len * 8, cb = p.len * 8;
+            const uint64_t ab = aad_len * 8, cb = len * 8;
             y.w[0] ^= (uint32_t)(ab >> 32); y.w[1] ^= (uint32_t)ab; y.w[2] ^= (uint32_t)(cb >> 32); y.w[3] ^= (uint32_t)cb;
             y = gf_mul_table(y, gh);
             uint32_t e[4];
@@ -326,10 +369,10 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_batch_tile(const __grid
                 }
             }
         }
-        if (lane == 0) ag_bulk_wait_read0();   // both tiles are free again for the next group
+        if (issuer) ag_bulk_wait_read0();   // both tiles are free again for the next group
         __syncwarp();
     }
-    if (lane == 0) ag_bulk_wait0();
+    if (issuer) ag_bulk_wait0();
 }
 
 // ===========================================================================
@@ -772,23 +815,29 @@ static cudaError_t launch_batch_cta_t(const BatchParams& p, int ncta, int nt, cu
     return cudaGetLastError();
 }
 
-template <int NR, bool DEC>
+template <int NR, bool DEC, bool GATHER>
 static cudaError_t launch_batch_tile_t(const TileParams& p, int ncta, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_batch_tile<NR, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(k_batch_tile<NR, DEC, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemBytes);
     if (e != cudaSuccess) return e;
-    k_batch_tile<NR, DEC><<<ncta, AG_STREAM_NT_MAX, kTileSmemBytes, st>>>(p);
+    k_batch_tile<NR, DEC, GATHER><<<ncta, AG_STREAM_NT_MAX, kTileSmemBytes, st>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t ag_launch_batch_tile(const TileParams& p, int nr, int decrypt, int ncta, cudaStream_t st)
+template <bool GATHER>
+static cudaError_t launch_batch_tile_g(const TileParams& p, int nr, int decrypt, int ncta, cudaStream_t st)
 {
     switch (nr) {
-        case 10: return decrypt ? launch_batch_tile_t<10, true>(p, ncta, st) : launch_batch_tile_t<10, false>(p, ncta, st);
-        case 12: return decrypt ? launch_batch_tile_t<12, true>(p, ncta, st) : launch_batch_tile_t<12, false>(p, ncta, st);
-        case 14: return decrypt ? launch_batch_tile_t<14, true>(p, ncta, st) : launch_batch_tile_t<14, false>(p, ncta, st);
+        case 10: return decrypt ? launch_batch_tile_t<10, true, GATHER>(p, ncta, st) : launch_batch_tile_t<10, false, GATHER>(p, ncta, st);
+        case 12: return decrypt ? launch_batch_tile_t<12, true, GATHER>(p, ncta, st) : launch_batch_tile_t<12, false, GATHER>(p, ncta, st);
+        case 14: return decrypt ? launch_batch_tile_t<14, true, GATHER>(p, ncta, st) : launch_batch_tile_t<14, false, GATHER>(p, ncta, st);
     }
     return cudaErrorInvalidValue;
+}
+
+cudaError_t ag_launch_batch_tile(const TileParams& p, int nr, int decrypt, int gather, int ncta, cudaStream_t st)
+{
+    return gather ? launch_batch_tile_g<true>(p, nr, decrypt, ncta, st) : launch_batch_tile_g<false>(p, nr, decrypt, ncta, st);
 }
 
 template <int NR, bool DEC>

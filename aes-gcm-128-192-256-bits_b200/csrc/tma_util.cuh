@@ -55,6 +55,25 @@ __device__ __forceinline__ void ag_tma_store_2d(const CUtensorMap* tm, int32_t c
                  : "memory");
 }
 
+// Blackwell row gather / scatter: four rows y0..y3 of the tensor, box {box0 bytes, 1 row} each, to / from 4 x box0
+// contiguous (swizzled) bytes.  A row index outside the tensor loads zeros (still counted in the transaction) and
+// stores nothing; columns outside the extent likewise (tools/gather4_probe.cu).
+__device__ __forceinline__ void ag_tma_gather4(uint32_t dst, const CUtensorMap* tm, int32_t c0, int32_t y0, int32_t y1, int32_t y2,
+                                               int32_t y3, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+                 "l"(tm), "r"(c0), "r"(y0), "r"(y1), "r"(y2), "r"(y3), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void ag_tma_scatter4(const CUtensorMap* tm, int32_t c0, int32_t y0, int32_t y1, int32_t y2, int32_t y3,
+                                                uint32_t src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile::scatter4.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(tm), "r"(c0),
+                 "r"(y0), "r"(y1), "r"(y2), "r"(y3), "r"(src)
+                 : "memory");
+}
+
 __device__ __forceinline__ void ag_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed stores have READ their shared-memory source (the tile may be overwritten)
 __device__ __forceinline__ void ag_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -44,7 +44,7 @@
  *     0 = equal granules), AGCM_PEER_TIMEOUT_MS (default 10000), and the A/B
  *     switches of the layout choice AGCM_NO_TILE, AGCM_PERKEY_TILE=0|1, AGCM_NO_WARP_UNITS,
  *     AGCM_WARP_MIN_BLOCKS, AGCM_NO_LEN_SORT (ragged batches in arrival order), AGCM_NO_LEN_CLASSES
- *     (sorted, but one lane count for the whole batch).
+ *     (sorted, but one lane count for the whole batch), AGCM_GATHER (slots: the row-gathering kernel by default).
  */
 #ifndef AESGCM_B200_H
 #define AESGCM_B200_H
@@ -235,7 +235,9 @@ int agcm_batch_crypt_uniform(agcm_ctx* ctx, int decrypt, int lanes, const uint8_
  * access is a 128-bit one, whatever the lengths.  From 1024 messages on, this call and agcm_batch_crypt take the
  * messages in LENGTH order (a counting sort on the device, longest first, handed out by ticket): a warp works on
  * several messages in lock step, and side by side they should be equally long (an IMIX of 64 / 576 / 1500 B
- * packets: 2-4x).  avg_len_hint as in agcm_batch_crypt (0: half the pitch). */
+ * packets: 2-4x).  avg_len_hint as in agcm_batch_crypt (0: half the pitch).  lanes = 2048 here names the
+ * row-gathering form of the TMA-staged kernel (tile::gather4 / scatter4 over the sorted rows; 16-byte aligned buffers
+ * and pitch, else AGCM_E_BAD_ARG): same bytes, within a few percent of the default either way. */
 int agcm_batch_crypt_slots(agcm_ctx* ctx, int decrypt, int lanes, const uint8_t* d_iv12, const uint8_t* d_aad,
                            const uint32_t* d_aad_len, uint64_t aad_len, uint64_t aad_stride, const uint8_t* d_in,
                            uint8_t* d_out, const uint32_t* d_len, uint64_t stride, uint64_t avg_len_hint, uint8_t* d_tag,

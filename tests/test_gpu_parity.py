@@ -840,13 +840,16 @@ def test_batch_ragged_length_sorted(engine, oracle, torch_mod):
 def test_batch_slots_per_message_lengths(engine, oracle, torch_mod):
     """agcm_batch_crypt_slots: messages of different lengths in fixed-pitch slots (a packet ring), AAD in slots of its
     own with per-message lengths or one common length; small batches (arrival order) and large ones (length-sorted);
-    a length beyond the pitch is clamped; the rest of every slot is left untouched; decrypt with corrupted tags."""
+    a length beyond the pitch is clamped; the rest of every slot is left untouched; decrypt with corrupted tags.
+    lanes = 2048 names the row-gathering TMA kernel (k_batch_tile<GATHER>: tile::gather4 / scatter4 over the sorted
+    order), AGCM_GATHER=1 makes it the default choice for large batches (the last case)."""
     torch = torch_mod
     rng = np.random.default_rng(777)
-    for kb, n_msgs, stride, astride, per_msg_aad in ((16, 300, 1504, 64, True), (32, 5000, 2048, 32, False), (24, 2000, 256, 0, False)):
+    for kb, n_msgs, stride, astride, per_msg_aad in ((16, 300, 1504, 64, True), (32, 5000, 2048, 32, False), (24, 2000, 256, 0, False),
+                                                     (32, 33, 48, 16, False), (16, 90000, 208, 32, True)):
         key = _rb(rng, kb)
         engine.set_key(key)
-        lens = rng.choice([0, 1, 64, 100, 576, 1500, stride], n_msgs).astype(np.uint32)
+        lens = rng.choice([0, 1, 15, 16, 17, 31, 32, 33, 64, 100, 576, 1500, stride - 1, stride], n_msgs).astype(np.uint32)
         lens = np.minimum(lens, stride).astype(np.uint32)
         alens = (rng.integers(0, astride + 1, n_msgs) if per_msg_aad else np.full(n_msgs, astride // 2)).astype(np.uint32)
         ivs = rng.integers(0, 256, 12 * n_msgs, dtype=np.uint8)
@@ -863,16 +866,28 @@ def test_batch_slots_per_message_lengths(engine, oracle, torch_mod):
         d_len_over[lens == stride] = stride + 999            # clamped to the pitch by the kernel
         d_alen = torch.from_numpy(alens.astype(np.int32)).cuda() if per_msg_aad else None
         d_in, d_aad = _dev(torch, buf), (_dev(torch, abuf) if astride else None)
-        for lanes in (0, 1, 4, 32):
+        col = np.arange(stride)[None, :]
+        inside = col < lens[:, None].astype(np.int64)
+        want = np.full((n_msgs, stride), 0x3C, dtype=np.uint8)
+        want[inside] = want_ct
+        for lanes in (0, 1, 4, 32, 2048, "gather"):
             d_out = torch.full((n_msgs * stride,), 0x3C, dtype=torch.uint8, device="cuda")
             d_tags = torch.zeros(16 * n_msgs, dtype=torch.uint8, device="cuda")
-            engine.batch_crypt_slots_device(0, _dev(torch, ivs), d_aad, d_alen, astride // 2, astride, d_in, d_out, d_len_over, stride,
-                                            d_tags, lanes=lanes, avg_len_hint=int(lens.mean()))
+            if lanes == "gather":
+                os.environ["AGCM_GATHER"] = "1"      # the A/B switch: large aligned batches take the gathering kernel by default
+            try:
+                n0 = engine.launch_count
+                engine.batch_crypt_slots_device(0, _dev(torch, ivs), d_aad, d_alen, astride // 2, astride, d_in, d_out, d_len_over, stride,
+                                                d_tags, lanes=0 if lanes == "gather" else lanes, avg_len_hint=int(lens.mean()))
+                n_launch = engine.launch_count - n0
+            finally:
+                os.environ.pop("AGCM_GATHER", None)
             torch.cuda.synchronize()
+            if lanes == 2048 or (lanes == "gather" and n_msgs >= 148 * 512):
+                assert n_launch == (4 if n_msgs >= 64 else 1), (lanes, n_launch)     # length sort (3) + one k_batch_tile<GATHER>
             got = d_out.cpu().numpy().reshape(n_msgs, stride)
-            for i in range(n_msgs):
-                assert got[i, :lens[i]].tobytes() == want_ct[int(in_off[i]):int(in_off[i + 1])].tobytes(), (kb, lanes, i)
-                assert (got[i, lens[i]:] == 0x3C).all(), (kb, lanes, i, "slot padding written")
+            bad_rows = np.nonzero((got != want).any(axis=1))[0]
+            assert bad_rows.size == 0, (kb, lanes, bad_rows[:5], lens[bad_rows[:5]])   # ciphertext, and the slot padding untouched
             assert (d_tags.cpu().numpy() == want_tags).all(), (kb, lanes)
         tags_in = want_tags.copy()
         bad = np.arange(1, n_msgs, 53)
