@@ -1352,6 +1352,37 @@ def test_fuzz_all_paths(engine, engine_small, oracle, torch_mod):
         exp = np.ones(nm, np.uint8)
         exp[bad] = 0
         assert (d_ok.cpu().numpy() == exp).all(), (it, "perkey ok")
+        # --- slots: a pitch (16-byte aligned or not), a length per message, AAD of one length or one per message; lane
+        #     groups, the length-sorted classes (from 1024 messages) and the row-gathering TMA kernel
+        nm = int(rng.choice([1, 3, 33, 200, 1100]))
+        aligned = bool(it % 3)
+        stride = int(rng.choice([16, 48, 208, 1504])) if aligned else int(rng.choice([1, 7, 100, 1500]))
+        astride = int(rng.choice([0, 16, 48])) if aligned else int(rng.choice([0, 5, 20]))
+        per_msg_aad = bool(astride and it % 2)
+        lens = rng.integers(0, stride + 1, nm).astype(np.uint32)
+        alens = (rng.integers(0, astride + 1, nm) if per_msg_aad else np.full(nm, astride // 2)).astype(np.uint32)
+        ivs = rng.integers(0, 256, 12 * nm, dtype=np.uint8)
+        buf = rng.integers(0, 256, nm * stride, dtype=np.uint8)
+        abuf = rng.integers(0, 256, max(1, nm * astride), dtype=np.uint8)
+        in_off = np.concatenate([[0], np.cumsum(lens.astype(np.int64))]).astype(np.uint64)
+        aad_off = np.concatenate([[0], np.cumsum(alens.astype(np.int64))]).astype(np.uint64)
+        inside = np.arange(stride)[None, :] < lens[:, None].astype(np.int64)
+        ainside = np.arange(max(astride, 1))[None, :] < alens[:, None].astype(np.int64)
+        packed = buf.reshape(nm, stride)[inside]
+        apacked = abuf[:nm * astride].reshape(nm, astride)[ainside[:, :astride]] if astride else None
+        s_ct, s_tags = oracle.gcm_batch(np.frombuffer(key, dtype=np.uint8), kb, True, ivs, apacked, aad_off if astride else None,
+                                        packed, in_off, threads=8)
+        want_slots = np.full((nm, stride), 0x5D, dtype=np.uint8)
+        want_slots[inside] = s_ct
+        lanes = int(rng.choice([0, 1, 2, 8, 2048] if aligned else [0, 1, 2, 8]))
+        d_out = torch.full((nm * stride,), 0x5D, dtype=torch.uint8, device="cuda")
+        d_tags = torch.zeros(16 * nm, dtype=torch.uint8, device="cuda")
+        eng.batch_crypt_slots_device(0, _dev(torch, ivs), _dev(torch, abuf) if astride else None,
+                                     torch.from_numpy(alens.astype(np.int32)).cuda() if per_msg_aad else None, astride // 2, astride,
+                                     _dev(torch, buf), d_out, torch.from_numpy(lens.astype(np.int32)).cuda(), stride, d_tags, lanes=lanes)
+        torch.cuda.synchronize()
+        assert (d_out.cpu().numpy().reshape(nm, stride) == want_slots).all(), (it, "slots ct / padding", lanes, stride, astride, nm)
+        assert (d_tags.cpu().numpy() == s_tags).all(), (it, "slots tag", lanes, stride, astride, nm)
         # --- fixed-size records: every uniform layout (lane groups, TMA tiles, balanced warp units, CTA segments),
         #     96-bit IVs or 1..40-byte IVs through the J0 form, shared key and key per message
         if eng is engine:
