@@ -143,15 +143,14 @@ __device__ __forceinline__ uint4 ag_realign(const uint4& a, const uint4& b, uint
 
 // Load like ag_load_block; a whole block at an unaligned address comes from the two aligned granules that
 // hold it when both lie inside [lo, hi) -- the unit's own bytes, so nothing outside the caller's data is read.
-// `words_too`: also when the address is word-aligned.  Measured on 1500 B records at a 1500 B pitch (AES-192): lanes that
-// share a message (G >= 2) do better with four 32-bit loads there (487 vs 442 GB/s), a lane that walks a message alone
-// (G = 1) with the two granules (430 vs 404).
-AG_HD void ag_load_block_in(const uint8_t* p, uint32_t nvalid, uint32_t x[4], const uint8_t* lo, const uint8_t* hi, bool words_too = false)
+// Only for addresses that are not even word-aligned (k_stream's strided lanes: a word-aligned block is cheaper as four
+// 32-bit loads).
+AG_HD void ag_load_block_in(const uint8_t* p, uint32_t nvalid, uint32_t x[4], const uint8_t* lo, const uint8_t* hi)
 {
 #if defined(__CUDA_ARCH__)
     const uintptr_t a = (uintptr_t)p;
     const uint32_t r = (uint32_t)(a & 15);
-    if (nvalid == 16 && (words_too ? r != 0 : (r & 3) != 0)) {
+    if (nvalid == 16 && (r & 3) != 0) {
         const uint8_t* base = p - r;
         if (base >= lo && base + 32 <= hi) {
             const uint4 w0 = *reinterpret_cast<const uint4*>(base), w1 = *reinterpret_cast<const uint4*>(base + 16);
@@ -164,6 +163,44 @@ AG_HD void ag_load_block_in(const uint8_t* p, uint32_t nvalid, uint32_t x[4], co
     (void)lo; (void)hi;
 #endif
     ag_load_block(p, nvalid, x);
+}
+
+// The same decision hoisted out of a message's block loop, for a lane that walks its message alone (k_batch<G = 1>):
+// blocks 1 .. n_wide of a buffer whose base sits r != 0 bytes past a 16-byte boundary are read as two aligned granules
+// inside the buffer; the loop pays one unsigned compare per block.  Here the two granules also beat four 32-bit loads
+// of a word-aligned block (1500 B records at a 1500 B pitch, AES-192: 450 vs 404 GB/s).
+struct AgWideWindow {
+    uint32_t r;        // base & 15
+    uint32_t n_wide;   // blocks 1 .. n_wide qualify (0: none)
+    AG_HD static AgWideWindow make(const uint8_t* base, uint64_t len)
+    {
+        AgWideWindow w;
+        w.r = (uint32_t)((uintptr_t)base & 15);
+        // block j (j >= 1) spans granules [16j - r, 16j - r + 32) of the buffer: inside it while 16j - r + 32 <= len
+        w.n_wide = 0;
+        if (w.r != 0 && len + w.r >= 48) {
+            const uint64_t q = (len + w.r - 32) >> 4;
+            w.n_wide = q > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)q;
+        }
+        return w;
+    }
+};
+
+template <bool WIDE>
+AG_HD void ag_load_block_win(const uint8_t* base, uint32_t j, uint32_t nvalid, uint32_t x[4], const AgWideWindow& w)
+{
+#if defined(__CUDA_ARCH__)
+    if (WIDE && j - 1u < w.n_wide) {   // 1 <= j <= n_wide: a whole block (the last, possibly short, block is index >= n_wide + 1)
+        const uint8_t* g = base + 16 * (uint64_t)j - w.r;
+        const uint4 w0 = *reinterpret_cast<const uint4*>(g), w1 = *reinterpret_cast<const uint4*>(g + 16);
+        const uint4 v = ag_realign(w0, w1, w.r);
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        return;
+    }
+#else
+    (void)w;
+#endif
+    ag_load_block(base + 16 * (uint64_t)j, nvalid, x);
 }
 
 #if defined(__CUDA_ARCH__)
@@ -505,14 +542,17 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
     uint32_t i = t - pad;                 // wraps while inside the front padding (row 0 only)
     bool have = t >= pad;
     uint32_t nxt[4] = {0, 0, 0, 0};
-    const uint8_t* const aad_hi = d.aad + d.aad_len;
-    const uint8_t* const in_hi = d.in + d.len;
+    // Realigned wide loads only where a lane walks its message alone (SEQ).  For lane groups they were measured too:
+    // +3 % on a heavy-tailed packed mix (long messages at odd addresses), but the extra path in the block loop cost
+    // every ALIGNED lane-group batch about 1 % (1500 B records, G = 2: 536 vs 529 GB/s) -- not kept.
+    const AgWideWindow win_aad = SEQ ? AgWideWindow::make(d.aad, d.aad ? d.aad_len : 0) : AgWideWindow{0, 0};
+    const AgWideWindow win_in = SEQ ? AgWideWindow::make(d.in, d.len) : AgWideWindow{0, 0};
 #if defined(__CUDA_ARCH__)
     AgStoreCarry carry;
     carry.init();
     const bool wide_st = SEQ && (((uintptr_t)d.out & 15) != 0);
 #endif
-    if (rows && have && i < a) ag_load_block_in(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt, d.aad, aad_hi, SEQ);
+    if (rows && have && i < a) ag_load_block_win<SEQ>(d.aad, i, (i == a - 1 && atail) ? atail : 16u, nxt, win_aad);
     // Rows 0 .. aad_rows-1 hold AAD blocks only (row u spans blocks uG-pad .. uG+G-1-pad): they run in
     // a loop of their own -- prefetch, one table product, one XOR, like k_stream<GHASH_ONLY> -- so
     // that bulk AAD is not dragged through the AES-sized body of the general loop below.
@@ -559,7 +599,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
         const uint32_t s0 = nxt[0], s1 = nxt[1], s2 = nxt[2], s3 = nxt[3];
         i += G;
         have = true;
-        if (u + 1 < rows && i < a) ag_load_block_in(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt, d.aad, aad_hi, SEQ);
+        if (u + 1 < rows && i < a) ag_load_block_win<SEQ>(d.aad, i, (i == a - 1 && atail) ? atail : 16u, nxt, win_aad);
         if (u) y = gf_mul_table(y, gh_g);
         if (hv) {
             y.w[0] ^= ag_bswap32(s0);
@@ -574,7 +614,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
         uint32_t s[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
         i += G;
         have = true;
-        if (u + 1 < rows && i < a) ag_load_block_in(d.aad + 16 * (uint64_t)i, (i == a - 1 && atail) ? atail : 16u, nxt, d.aad, aad_hi, SEQ);
+        if (u + 1 < rows && i < a) ag_load_block_win<SEQ>(d.aad, i, (i == a - 1 && atail) ? atail : 16u, nxt, win_aad);
         if (u) y = gf_mul_table(y, gh_g);
         if (!hv) continue;
         if (ic >= a) {
@@ -585,7 +625,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
             const uint32_t j = ic - a;
             const uint32_t nv = (j == n - 1 && tail) ? tail : 16u;
             uint32_t x[4] = {0, 0, 0, 0};
-            if (!is_len) ag_load_block_in(d.in + 16 * (uint64_t)j, nv, x, d.in, in_hi, SEQ);   // in flight during the AES rounds
+            if (!is_len) ag_load_block_win<SEQ>(d.in, j, nv, x, win_in);   // in flight during the AES rounds
             uint32_t ks[4];
             aes_ctr_block_auto<NR>(rk, cc, cache, is_len ? d.j0ctr : d.j0ctr + 1u + d.ctr_off + j, te, ks);   // inc32: wraps mod 2^32
             if (is_len) {
