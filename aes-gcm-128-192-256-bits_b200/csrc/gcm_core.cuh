@@ -186,19 +186,28 @@ struct AgWideWindow {
     }
 };
 
+// The upper granule of block j is the lower granule of block j + 1: a lane that reads consecutive blocks keeps it.
+struct AgLoadCarry {
+    uint4 g;
+    uint32_t j;   // g is the lower granule of block j (0xFFFFFFFF: nothing kept)
+};
+
 template <bool WIDE>
-AG_HD void ag_load_block_win(const uint8_t* base, uint32_t j, uint32_t nvalid, uint32_t x[4], const AgWideWindow& w)
+AG_HD void ag_load_block_win(const uint8_t* base, uint32_t j, uint32_t nvalid, uint32_t x[4], const AgWideWindow& w, AgLoadCarry& c)
 {
 #if defined(__CUDA_ARCH__)
     if (WIDE && j - 1u < w.n_wide) {   // 1 <= j <= n_wide: a whole block (the last, possibly short, block is index >= n_wide + 1)
         const uint8_t* g = base + 16 * (uint64_t)j - w.r;
-        const uint4 w0 = *reinterpret_cast<const uint4*>(g), w1 = *reinterpret_cast<const uint4*>(g + 16);
+        const uint4 w1 = *reinterpret_cast<const uint4*>(g + 16);
+        const uint4 w0 = (c.j == j) ? c.g : *reinterpret_cast<const uint4*>(g);
         const uint4 v = ag_realign(w0, w1, w.r);
         x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        c.g = w1;
+        c.j = j + 1;
         return;
     }
 #else
-    (void)w;
+    (void)w; (void)c;
 #endif
     ag_load_block(base + 16 * (uint64_t)j, nvalid, x);
 }
@@ -547,12 +556,15 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
     // every ALIGNED lane-group batch about 1 % (1500 B records, G = 2: 536 vs 529 GB/s) -- not kept.
     const AgWideWindow win_aad = SEQ ? AgWideWindow::make(d.aad, d.aad ? d.aad_len : 0) : AgWideWindow{0, 0};
     const AgWideWindow win_in = SEQ ? AgWideWindow::make(d.in, d.len) : AgWideWindow{0, 0};
+    AgLoadCarry lc_aad, lc_in;
+    lc_aad.j = lc_in.j = 0xFFFFFFFFu;
+    lc_aad.g = lc_in.g = make_uint4(0, 0, 0, 0);
 #if defined(__CUDA_ARCH__)
     AgStoreCarry carry;
     carry.init();
     const bool wide_st = SEQ && (((uintptr_t)d.out & 15) != 0);
 #endif
-    if (rows && have && i < a) ag_load_block_win<SEQ>(d.aad, i, (i == a - 1 && atail) ? atail : 16u, nxt, win_aad);
+    if (rows && have && i < a) ag_load_block_win<SEQ>(d.aad, i, (i == a - 1 && atail) ? atail : 16u, nxt, win_aad, lc_aad);
     // Rows 0 .. aad_rows-1 hold AAD blocks only (row u spans blocks uG-pad .. uG+G-1-pad): they run in
     // a loop of their own -- prefetch, one table product, one XOR, like k_stream<GHASH_ONLY> -- so
     // that bulk AAD is not dragged through the AES-sized body of the general loop below.
@@ -599,7 +611,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
         const uint32_t s0 = nxt[0], s1 = nxt[1], s2 = nxt[2], s3 = nxt[3];
         i += G;
         have = true;
-        if (u + 1 < rows && i < a) ag_load_block_win<SEQ>(d.aad, i, (i == a - 1 && atail) ? atail : 16u, nxt, win_aad);
+        if (u + 1 < rows && i < a) ag_load_block_win<SEQ>(d.aad, i, (i == a - 1 && atail) ? atail : 16u, nxt, win_aad, lc_aad);
         if (u) y = gf_mul_table(y, gh_g);
         if (hv) {
             y.w[0] ^= ag_bswap32(s0);
@@ -614,7 +626,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
         uint32_t s[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
         i += G;
         have = true;
-        if (u + 1 < rows && i < a) ag_load_block_win<SEQ>(d.aad, i, (i == a - 1 && atail) ? atail : 16u, nxt, win_aad);
+        if (u + 1 < rows && i < a) ag_load_block_win<SEQ>(d.aad, i, (i == a - 1 && atail) ? atail : 16u, nxt, win_aad, lc_aad);
         if (u) y = gf_mul_table(y, gh_g);
         if (!hv) continue;
         if (ic >= a) {
@@ -625,7 +637,7 @@ AG_HD gf128 ag_batch_lane(const uint32_t* rk, const AesCtrConst& cc, CACHE& cach
             const uint32_t j = ic - a;
             const uint32_t nv = (j == n - 1 && tail) ? tail : 16u;
             uint32_t x[4] = {0, 0, 0, 0};
-            if (!is_len) ag_load_block_win<SEQ>(d.in, j, nv, x, win_in);   // in flight during the AES rounds
+            if (!is_len) ag_load_block_win<SEQ>(d.in, j, nv, x, win_in, lc_in);   // in flight during the AES rounds
             uint32_t ks[4];
             aes_ctr_block_auto<NR>(rk, cc, cache, is_len ? d.j0ctr : d.j0ctr + 1u + d.ctr_off + j, te, ks);   // inc32: wraps mod 2^32
             if (is_len) {
