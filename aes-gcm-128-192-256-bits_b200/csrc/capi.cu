@@ -1036,6 +1036,24 @@ int agcm_ghash(agcm_ctx* c, const uint8_t* d_in, uint64_t n_bytes, uint8_t* d_y1
                       c->d_counters);
 }
 
+// Length order of a batch of different-length messages (device counting sort, longest first): fills the per-context
+// scratch [4096-bucket histogram | 8 words of class bounds | perm[n_msgs]] and points p.perm at the order.
+static int len_sort(agcm_ctx* c, BatchParams& p, size_t n_msgs, cudaStream_t st)
+{
+    const size_t need_b = sizeof(uint32_t) * (4096 + 8 + n_msgs);
+    if (need_b > c->sort_cap) {
+        AG_CUDA(c, cudaFree(c->d_sort));
+        c->d_sort = nullptr;
+        c->sort_cap = 0;
+        AG_CUDA(c, cudaMalloc(&c->d_sort, need_b));
+        c->sort_cap = need_b;
+    }
+    AG_CUDA(c, ag_launch_len_sort(p, c->d_sort, c->d_sort + 4096, c->d_sort + 4096 + 8, st));
+    c->launches += 3;
+    p.perm = c->d_sort + 4096 + 8;
+    return AGCM_OK;
+}
+
 static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, BatchParams& p, size_t n_msgs, void* stream,
                         bool aligned16 = true)
 {
@@ -1136,20 +1154,11 @@ static int batch_common(agcm_ctx* c, int decrypt, int lanes, uint64_t avg_len, B
         // 16 KiB of work, 4 from 4 KiB, 1 below -- a heavy tail of long messages must not crawl through one lane.
         // The class sizes stay on the device (no host round trip): an empty class costs one idle launch.
         cudaStream_t st = (cudaStream_t)stream;
-        const size_t need_b = sizeof(uint32_t) * (4096 + 8 + (size_t)n_msgs);
-        if (need_b > c->sort_cap) {
-            AG_CUDA(c, cudaFree(c->d_sort));
-            c->d_sort = nullptr;
-            c->sort_cap = 0;
-            AG_CUDA(c, cudaMalloc(&c->d_sort, need_b));
-            c->sort_cap = need_b;
-        }
         if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, 4 * sizeof(uint32_t)));
         AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, 4 * sizeof(uint32_t), st));
+        int rc_sort = len_sort(c, p, n_msgs, st);
+        if (rc_sort) return rc_sort;
         uint32_t* ranges = c->d_sort + 4096;
-        AG_CUDA(c, ag_launch_len_sort(p, c->d_sort, ranges, c->d_sort + 4096 + 8, st));
-        c->launches += 3;
-        p.perm = c->d_sort + 4096 + 8;
         if (lanes == 0 && !getenv("AGCM_NO_LEN_CLASSES")) {
             // short class: one lane per message with realigned wide accesses when records sit at odd addresses,
             // two lanes (32 contiguous bytes per request) when they are 16-byte aligned
@@ -1274,17 +1283,8 @@ static int batch_tile_slots(agcm_ctx* c, int decrypt, BatchParams& p, size_t n_m
     p.n_msgs = n_msgs;
     // length order (longest first): the 32 messages a warp takes side by side are equally long
     if (n_msgs >= 64 && !getenv("AGCM_NO_LEN_SORT")) {
-        const size_t need_b = sizeof(uint32_t) * (4096 + 8 + (size_t)n_msgs);
-        if (need_b > c->sort_cap) {
-            AG_CUDA(c, cudaFree(c->d_sort));
-            c->d_sort = nullptr;
-            c->sort_cap = 0;
-            AG_CUDA(c, cudaMalloc(&c->d_sort, need_b));
-            c->sort_cap = need_b;
-        }
-        AG_CUDA(c, ag_launch_len_sort(p, c->d_sort, c->d_sort + 4096, c->d_sort + 4096 + 8, st));
-        c->launches += 3;
-        p.perm = c->d_sort + 4096 + 8;
+        int rc_sort = len_sort(c, p, n_msgs, st);
+        if (rc_sort) return rc_sort;
     }
     TileParams t;
     memset(&t, 0, sizeof(t));
@@ -1445,6 +1445,12 @@ static int perkey_common(agcm_ctx* c, int mode, int decrypt, BatchParams& p, siz
     p.key = nullptr;
     p.te0 = c->d_te0;
     p.n_msgs = n_msgs;
+    if ((p.in_off || p.aad_off) && n_msgs >= 1024 && n_msgs < 0xFFFFFF00ull && !c->no_ticket && !getenv("AGCM_NO_LEN_SORT")) {
+        // messages of different lengths, a message per lane: take them in length order (as batch_common does), so that
+        // the 32 messages of a warp are equally long; thread g then works on perm[g], perm[g + grid], ...
+        int rc = len_sort(c, p, n_msgs, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
     AG_CUDA(c, ag_launch_batch_perkey(p, nr, decrypt, c->ncta, (cudaStream_t)stream));
     c->launches++;
     return AGCM_OK;

@@ -127,7 +127,7 @@ __device__ __forceinline__ void load_words(const uint8_t* p, int n_words, uint32
 
 }  // namespace
 
-template <int NK, bool DEC>
+template <int NK, bool DEC, bool WIDE>
 __global__ void __launch_bounds__(PK_NT, 1) k_batch_perkey(const __grid_constant__ BatchParams p)
 {
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -147,13 +147,14 @@ __global__ void __launch_bounds__(PK_NT, 1) k_batch_perkey(const __grid_constant
     Rows4Smem rows{s_al + (tid >> 3) * 2048u + (tid & 7) * 16u};
     SubCacheSmem subc{s_al + PK_NT * 256u + tid * 4u};
 
-    for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + tid; m < p.n_msgs; m += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + tid; g < p.n_msgs; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t m = p.perm ? p.perm[g] : g;   // length order for offset batches: a warp's 32 messages are equally long
         const MsgDesc d = ag_batch_msg(p, m);
         uint32_t key[8], iv[3];
         load_words(p.keys + m * (uint64_t)(4 * NK), NK, key);
         load_words(p.iv + 12 * m, 3, iv);
         uint32_t tg[4];
-        ag_perkey_message<NK, DEC>(key, iv[0], iv[1], iv[2], d, te, sb, rows, subc, tg);
+        ag_perkey_message<NK, DEC, WIDE>(key, iv[0], iv[1], iv[2], d, te, sb, rows, subc, tg);
         uint8_t* tp = p.tag + 16 * m;
         if (DEC) {
             uint32_t x[4];
@@ -348,17 +349,17 @@ cudaError_t ag_launch_batch_perkey_tile(const TileParams& p, int nr, int decrypt
 template <int NK>
 static cudaError_t launch_perkey_t(const BatchParams& p, int decrypt, int ncta, cudaStream_t st)
 {
-    cudaError_t e;
-    if (decrypt) {
-        e = cudaFuncSetAttribute(k_batch_perkey<NK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
+    auto go = [&](auto kernel) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
         if (e != cudaSuccess) return e;
-        k_batch_perkey<NK, true><<<ncta, PK_NT, PK_SMEM, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(k_batch_perkey<NK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_SMEM);
-        if (e != cudaSuccess) return e;
-        k_batch_perkey<NK, false><<<ncta, PK_NT, PK_SMEM, st>>>(p);
-    }
-    return cudaGetLastError();
+        kernel<<<ncta, PK_NT, PK_SMEM, st>>>(p);
+        return cudaGetLastError();
+    };
+    // realigned wide access when a message may sit at an odd address: batches packed by offsets, or records whose
+    // buffers or pitch are not 16-byte aligned
+    const bool wide = p.in_off || p.aad_off || ((((uintptr_t)p.in | (uintptr_t)p.out) | p.stride) & 15) != 0;
+    if (wide) return decrypt ? go(k_batch_perkey<NK, true, true>) : go(k_batch_perkey<NK, false, true>);
+    return decrypt ? go(k_batch_perkey<NK, true, false>) : go(k_batch_perkey<NK, false, false>);
 }
 
 cudaError_t ag_launch_batch_perkey(const BatchParams& p, int nr, int decrypt, int max_cta, cudaStream_t st)

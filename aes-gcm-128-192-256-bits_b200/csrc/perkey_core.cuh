@@ -250,7 +250,10 @@ AG_HD gf128 gf_mul_table4(const gf128& x, ROWS&& rows)
 // ---- one whole message ------------------------------------------------------------
 // key: NK little-endian words of the raw key.  Returns the computed tag words (LE) and
 // writes the payload.  Unified order AAD | CT | length block (gcm_ghash.vhd:259-272,257).
-template <int NK, bool DEC, class TE, class SB, class ROWS, class SUBC>
+// WIDE: the message may sit at an odd address (batches packed by offsets): whole blocks are then read as realigned
+// 16-byte granules and written through a carried granule, as in the single-lane layout of the shared-key batches
+// (gcm_core.cuh: AgWideWindow, AgLoadCarry, AgStoreCarry) instead of byte by byte.
+template <int NK, bool DEC, bool WIDE = false, class TE, class SB, class ROWS, class SUBC>
 AG_HD void ag_perkey_message(const uint32_t* key, uint32_t iv0, uint32_t iv1, uint32_t iv2, const MsgDesc& d, TE&& te,
                              SB&& sb, ROWS&& rows, SUBC&& subc, uint32_t tag[4])
 {
@@ -262,11 +265,21 @@ AG_HD void ag_perkey_message(const uint32_t* key, uint32_t iv0, uint32_t iv1, ui
     perkey_ctr_block<NK>(st, 1u, te, subc, e);  // E_K(J0), J0 = IV || 00000001 (aes_icb.vhd:34,99)
 
     gf128 y = gf_zero();
-    const uint64_t a = (d.aad_len + 15) >> 4, n = (d.len + 15) >> 4;
+    const uint64_t a = (d.aad_len + 15) >> 4, n = (d.len + 15) >> 4;   // both < 2^32 (checked / documented at the API)
+    const AgWideWindow win_aad = WIDE ? AgWideWindow::make(d.aad, d.aad ? d.aad_len : 0) : AgWideWindow{0, 0};
+    const AgWideWindow win_in = WIDE ? AgWideWindow::make(d.in, d.len) : AgWideWindow{0, 0};
+    AgLoadCarry lc_aad, lc_in;
+    lc_aad.j = lc_in.j = 0xFFFFFFFFu;
+    lc_aad.g = lc_in.g = make_uint4(0, 0, 0, 0);
+#if defined(__CUDA_ARCH__)
+    AgStoreCarry carry;
+    carry.init();
+    const bool wide_st = WIDE && (((uintptr_t)d.out & 15) != 0);
+#endif
     for (uint64_t i = 0; i < a; ++i) {
         const uint64_t left = d.aad_len - 16 * i;
         uint32_t s[4];
-        ag_load_block(d.aad + 16 * i, left < 16 ? (uint32_t)left : 16u, s);
+        ag_load_block_win<WIDE>(d.aad, (uint32_t)i, left < 16 ? (uint32_t)left : 16u, s, win_aad, lc_aad);
         y = gf_xor(y, gf_from_le_words(s[0], s[1], s[2], s[3]));
         y = gf_mul_table4(y, rows);
     }
@@ -274,10 +287,19 @@ AG_HD void ag_perkey_message(const uint32_t* key, uint32_t iv0, uint32_t iv1, ui
         const uint64_t left = d.len - 16 * j;
         const uint32_t nv = left < 16 ? (uint32_t)left : 16u;
         uint32_t x[4], ks[4];
-        ag_load_block(d.in + 16 * j, nv, x);
+        ag_load_block_win<WIDE>(d.in, (uint32_t)j, nv, x, win_in, lc_in);
         perkey_ctr_block<NK>(st, 2u + (uint32_t)j, te, subc, ks);
         uint32_t o[4] = {x[0] ^ ks[0], x[1] ^ ks[1], x[2] ^ ks[2], x[3] ^ ks[3]};
+#if defined(__CUDA_ARCH__)
+        if (WIDE && wide_st && nv == 16) {
+            carry.put(d.out + 16 * j, o);
+        } else {
+            if (WIDE) carry.flush();
+            ag_store_block(d.out + 16 * j, nv, o);
+        }
+#else
         ag_store_block(d.out + 16 * j, nv, o);
+#endif
         if (DEC) {
             y = gf_xor(y, gf_from_le_words(x[0], x[1], x[2], x[3]));
         } else {
@@ -286,6 +308,9 @@ AG_HD void ag_perkey_message(const uint32_t* key, uint32_t iv0, uint32_t iv1, ui
         }
         y = gf_mul_table4(y, rows);
     }
+#if defined(__CUDA_ARCH__)
+    if (WIDE) carry.flush();
+#endif
     const uint64_t ab = d.aad_len * 8, cb = d.len * 8;
     y.w[0] ^= (uint32_t)(ab >> 32);
     y.w[1] ^= (uint32_t)ab;

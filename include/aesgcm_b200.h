@@ -260,7 +260,10 @@ int agcm_batch_crypt_uniform_j0(agcm_ctx* ctx, int decrypt, int lanes, const uin
  * the aes_kexp schedule on the fly, one stage per round (config/config_aes_kexp.py:
  * 113-159), derives its own H and E_K(J0), and absorbs GHASH with the serial
  * recurrence of src/gcm_ghash.vhd:269-272.  Does not use or change the context key.
- * Other arguments as agcm_batch_crypt / agcm_batch_crypt_uniform. */
+ * Other arguments as agcm_batch_crypt / agcm_batch_crypt_uniform.
+ * Messages of different lengths are taken in length order (device sort, from 1024 messages); the kernel works ONE
+ * lane per message, so this call is for short messages (packets): a message of tens of KiB under its own key is
+ * better served by agcm_set_key + the stream calls. */
 int agcm_batch_crypt_perkey(agcm_ctx* ctx, int mode, int decrypt, const uint8_t* d_keys, const uint8_t* d_iv12,
                             const uint8_t* d_aad, const uint64_t* d_aad_off, const uint8_t* d_in, const uint64_t* d_in_off,
                             uint8_t* d_out, uint8_t* d_tag, uint8_t* d_ok, size_t n_msgs, void* stream);

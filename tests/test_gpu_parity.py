@@ -942,6 +942,52 @@ def test_batch_host_api_roundtrip(engine, oracle):
         assert ref[:-16] == out[i * length:(i + 1) * length].tobytes() and ref[-16:] == tags[16 * i:16 * i + 16].tobytes(), i
 
 
+def test_perkey_ragged_length_sorted(engine, oracle, torch_mod):
+    """A key per message AND a length per message (the reference's regression runs: every test has its own random key,
+    IV, AAD and payload sizes, tb/gcm_testbench.py:25-39): from 1024 messages on the per-key kernel takes the messages
+    in length order (perm[] from the device sort).  Encrypt vs the oracle, decrypt with corrupted tags, every key size;
+    the unsorted order (AGCM_NO_LEN_SORT) gives the same bytes."""
+    torch = torch_mod
+    rng = np.random.default_rng(4242)
+    for kb, nm in ((32, 3000), (16, 1024), (24, 1500)):
+        lens = rng.choice([0, 1, 16, 64, 100, 576, 1500, 4000], nm)
+        alens = rng.integers(0, 70, nm)
+        in_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+        aad_off = np.concatenate([[0], np.cumsum(alens)]).astype(np.uint64)
+        msg = rng.integers(0, 256, int(in_off[-1]), dtype=np.uint8)
+        aad = rng.integers(0, 256, int(aad_off[-1]), dtype=np.uint8)
+        ivs = rng.integers(0, 256, 12 * nm, dtype=np.uint8)
+        keys = rng.integers(0, 256, kb * nm, dtype=np.uint8)
+        w_ct, w_tags = oracle.gcm_batch(keys, kb, False, ivs, aad, aad_off, msg, in_off, decrypt=False, threads=8)
+        d_io, d_ao = torch.from_numpy(in_off.view(np.int64)).cuda(), torch.from_numpy(aad_off.view(np.int64)).cuda()
+        d_keys, d_iv, d_aad, d_msg = _dev(torch, keys), _dev(torch, ivs), _dev(torch, aad), _dev(torch, msg)
+        for nosort in (False, True):
+            if nosort:
+                os.environ["AGCM_NO_LEN_SORT"] = "1"
+            try:
+                d_ct = torch.zeros(msg.size + 16, dtype=torch.uint8, device="cuda")
+                d_tags = torch.zeros(16 * nm, dtype=torch.uint8, device="cuda")
+                n0 = engine.launch_count
+                engine.batch_crypt_perkey_device(kb * 8, 0, d_keys, d_iv, d_aad, d_ao, d_msg, d_io, d_ct, d_tags)
+                torch.cuda.synchronize()
+                assert engine.launch_count - n0 == (1 if nosort else 4)      # 3 sort launches + the kernel
+            finally:
+                os.environ.pop("AGCM_NO_LEN_SORT", None)
+            assert (d_ct.cpu().numpy()[:msg.size] == w_ct).all(), (kb, nosort)
+            assert (d_ct.cpu().numpy()[msg.size:] == 0).all()
+            assert (d_tags.cpu().numpy() == w_tags).all(), (kb, nosort)
+        tags_in = w_tags.copy()
+        bad = np.arange(3, nm, 97)
+        tags_in[16 * bad] ^= 1
+        d_back = torch.zeros(msg.size, dtype=torch.uint8, device="cuda")
+        d_ok = torch.full((nm,), 7, dtype=torch.uint8, device="cuda")
+        engine.batch_crypt_perkey_device(kb * 8, 1, d_keys, d_iv, d_aad, d_ao, d_ct[:msg.size], d_io, d_back, _dev(torch, tags_in), d_ok)
+        torch.cuda.synchronize()
+        assert (d_back.cpu().numpy() == msg).all()
+        ok = d_ok.cpu().numpy()
+        assert (ok[bad] == 0).all() and int(ok.sum()) == nm - bad.size
+
+
 def test_config4_perkey_decrypt_verify(engine, oracle, torch_mod):
     """BASELINE config 4 semantics at reduced count: AES-256 decrypt+verify, a DISTINCT key per
     message expanded on the device, 64 B AAD, payload swept over {64, 256, 1500, 4096} B, some tags

@@ -49,4 +49,24 @@ for kb in (16, 32):
             print(json.dumps({"aes": kb * 8, "mix": name + " in %d B slots" % pitch, "mean_len": round(float(lens.mean()), 1), "ms": round(ms, 4),
                               "payload_GBps": round(total / ms / 1e6, 1), "Mmsg_per_s": round(n / ms / 1e3, 1)}), flush=True)
             del d_in, d_out
+# a key per message as well (agcm_batch_crypt_perkey, offsets): the per-key kernel in length order
+if not os.environ.get("RAGGED_SLOTS_ONLY"):
+    for name, lens in mixes.items():
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        total = int(off[-1])
+        d_in = torch.randint(0, 256, (total,), dtype=torch.uint8, device="cuda"); d_out = torch.empty_like(d_in)
+        d_off = torch.from_numpy(off).cuda()
+        d_keys = torch.randint(0, 256, (32 * n,), dtype=torch.uint8, device="cuda")
+        d_iv = torch.randint(0, 256, (12 * n,), dtype=torch.uint8, device="cuda"); d_tags = torch.zeros(16 * n, dtype=torch.uint8, device="cuda")
+        fn = lambda: eng.batch_crypt_perkey_device(256, 0, d_keys, d_iv, None, None, d_in, d_off, d_out, d_tags)
+        for _ in range(2): fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5): fn()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(json.dumps({"aes": 256, "mix": name + ", a key per message", "mean_len": round(float(lens.mean()), 1), "ms": round(ms, 4),
+                          "payload_GBps": round(total / ms / 1e6, 1), "Mmsg_per_s": round(n / ms / 1e3, 1)}), flush=True)
+        del d_in, d_out
 eng.close()
