@@ -1450,6 +1450,9 @@ static int perkey_common(agcm_ctx* c, int mode, int decrypt, BatchParams& p, siz
         // the 32 messages of a warp are equally long; thread g then works on perm[g], perm[g + grid], ...
         int rc = len_sort(c, p, n_msgs, (cudaStream_t)stream);
         if (rc) return rc;
+        if (!c->d_tile_ticket) AG_CUDA(c, cudaMalloc(&c->d_tile_ticket, 4 * sizeof(uint32_t)));
+        AG_CUDA(c, cudaMemsetAsync(c->d_tile_ticket, 0, sizeof(uint32_t), (cudaStream_t)stream));
+        p.ticket = c->d_tile_ticket;   // groups of 32 messages, longest first, to whichever warp is free
     }
     AG_CUDA(c, ag_launch_batch_perkey(p, nr, decrypt, c->ncta, (cudaStream_t)stream));
     c->launches++;

@@ -147,7 +147,20 @@ __global__ void __launch_bounds__(PK_NT, 1) k_batch_perkey(const __grid_constant
     Rows4Smem rows{s_al + (tid >> 3) * 2048u + (tid & 7) * 16u};
     SubCacheSmem subc{s_al + PK_NT * 256u + tid * 4u};
 
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + tid; g < p.n_msgs; g += (uint64_t)gridDim.x * blockDim.x) {
+    // Static stride, or (p.ticket: offset batches in length order) the next 32 messages of the order to whichever warp
+    // is free: a warp that drew long messages must not also own a fixed share of all the later ones.
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + tid;
+    for (;; g += (uint64_t)gridDim.x * blockDim.x) {
+        if (p.ticket) {
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(p.ticket, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if ((uint64_t)t * 32 >= p.n_msgs) break;
+            g = (uint64_t)t * 32 + lane;
+            if (g >= p.n_msgs) continue;   // the last group may be short (the warp's next draw ends the loop)
+        } else if (g >= p.n_msgs) {
+            break;
+        }
         const uint64_t m = p.perm ? p.perm[g] : g;   // length order for offset batches: a warp's 32 messages are equally long
         const MsgDesc d = ag_batch_msg(p, m);
         uint32_t key[8], iv[3];
