@@ -34,6 +34,14 @@ for s in $STEPS; do
     hybrid)
       nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I include -o /tmp/hybrid_probe tools/hybrid_probe.cu -L aes-gcm-128-192-256-bits_b200 -laesgcm_b200 -Xlinker -rpath=$PWD/aes-gcm-128-192-256-bits_b200 > $OUT/${TAG}_hybrid.log 2>&1
       timeout 300 /tmp/hybrid_probe >> $OUT/${TAG}_hybrid.log 2>&1; echo "hybrid rc=$?"; cat $OUT/${TAG}_hybrid.log ;;
+    ragged)
+      timeout 600 python tools/bench_ragged.py > $OUT/${TAG}_ragged.jsonl 2>&1; echo "ragged rc=$?"; cat $OUT/${TAG}_ragged.jsonl
+      AGCM_NO_LEN_SORT=1 timeout 600 python tools/bench_ragged.py > $OUT/${TAG}_ragged_nosort.jsonl 2>&1
+      AGCM_NO_LEN_CLASSES=1 timeout 600 python tools/bench_ragged.py > $OUT/${TAG}_ragged_noclasses.jsonl 2>&1
+      RAGGED_SLOTS_ONLY=1 AGCM_SLOTS_LANES=2048 timeout 600 python tools/bench_ragged.py > $OUT/${TAG}_ragged_gather.jsonl 2>&1 ;;
+    e2esizes)
+      timeout 600 python tools/bench_e2e.py 32:0 32:1024 32:2048 16:1024 64:1024 > $OUT/${TAG}_e2e_sizes.jsonl 2>&1; echo "e2esizes rc=$?"; cat $OUT/${TAG}_e2e_sizes.jsonl
+      for k in none tiny d2d kstream indep; do timeout 120 python tools/pipeline_timeline.py 512 16 $k q; done > $OUT/${TAG}_timeline.txt 2>&1; cat $OUT/${TAG}_timeline.txt ;;
     sweep5)
       timeout 1500 python tools/sweep_config5.py --out $OUT/${TAG}_config5.json > $OUT/${TAG}_config5.log 2>&1; echo "sweep5 rc=$?"; tail -75 $OUT/${TAG}_config5.log ;;
     variants)
