@@ -131,7 +131,15 @@ __device__ void finish_warp(const FinishArgs& p, gf128 s)
     const uint32_t lane = threadIdx.x & 31;
     const KeyDev* kd = p.key;
     const uint64_t n = (p.ct_len + 15) >> 4;
-    if (p.aad && p.aad_len) {  // uniform
+    // the constants of the serial chain below, requested up front (each is a global-memory round trip otherwise)
+    const gf128 hkey = kd->H;
+    uint32_t exp_tag[4] = {0, 0, 0, 0};
+    if (lane == 0 && p.tag_expected && p.ok) ag_load_block(p.tag_expected, 16, exp_tag);
+    gf128 hn_pre = gf_zero();
+    const bool have_aad = p.aad && p.aad_len;
+    if (have_aad && p.hn) { hn_pre.w[0] = __ldcg(p.hn + 0); hn_pre.w[1] = __ldcg(p.hn + 1); hn_pre.w[2] = __ldcg(p.hn + 2); hn_pre.w[3] = __ldcg(p.hn + 3); }
+    const gf128 w_lane = have_aad ? kd->hpow_thread[32 - lane] : gf_zero();
+    if (have_aad) {  // uniform
         // short AAD (host routes long AAD through k_stream<GHASH_ONLY>): the warp
         // runs the same front-padded strided Horner with G = 32 and generic products.
         const uint64_t a = (p.aad_len + 15) >> 4;
@@ -149,20 +157,15 @@ __device__ void finish_warp(const FinishArgs& p, gf128 s)
                 qa = gf_xor(qa, gf_from_le_words(x[0], x[1], x[2], x[3]));
             }
         }
-        qa = gf_mul(qa, kd->hpow_thread[32 - lane]);
+        qa = gf_mul(qa, w_lane);
         qa = warp_xor(qa);                     // QA = sum A_i H^(a-i)
-        gf128 hn;
-        if (p.hn) {
-            hn.w[0] = __ldcg(p.hn + 0); hn.w[1] = __ldcg(p.hn + 1); hn.w[2] = __ldcg(p.hn + 2); hn.w[3] = __ldcg(p.hn + 3);
-        } else {
-            hn = warp_gf_pow(kd, n);
-        }
+        const gf128 hn = p.hn ? hn_pre : warp_gf_pow(kd, n);
         if (lane == 0) s = gf_xor(s, gf_mul(qa, hn));
     }
     if (lane == 0) {
         const uint64_t ab = p.aad_len * 8, cb = p.ct_len * 8;
         s.w[0] ^= (uint32_t)(ab >> 32); s.w[1] ^= (uint32_t)ab; s.w[2] ^= (uint32_t)(cb >> 32); s.w[3] ^= (uint32_t)cb;
-        s = gf_mul(s, kd->H);
+        s = gf_mul(s, hkey);
         uint32_t e[4];
         if (p.smem_tables) {
             TeSmem te{ag_smem, 0};
@@ -175,9 +178,7 @@ __device__ void finish_warp(const FinishArgs& p, gf128 s)
                          ag_bswap32(s.w[3]) ^ e[3]};
         ag_store_block(p.tag_calc, 16, t);
         if (p.tag_expected && p.ok) {
-            uint32_t x[4];
-            ag_load_block(p.tag_expected, 16, x);
-            const uint32_t diff = (x[0] ^ t[0]) | (x[1] ^ t[1]) | (x[2] ^ t[2]) | (x[3] ^ t[3]);
+            const uint32_t diff = (exp_tag[0] ^ t[0]) | (exp_tag[1] ^ t[1]) | (exp_tag[2] ^ t[2]) | (exp_tag[3] ^ t[3]);
             *p.ok = diff ? 0 : 1;
         }
     }
@@ -299,6 +300,8 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_con
 
     // lane weight H^(Gt-g) = (H^NT)^(ncta-1-cta) * H^(NT-tid); lanes that absorbed nothing (short
     // messages leave most of the grid idle) skip the bit-serial product
+    gf128 w_cta = gf_zero();
+    if (tid == 0) w_cta = p.key->hpow_cta[gridDim.x - 1 - blockIdx.x];   // in flight during the per-thread product
     if (__any_sync(0xffffffffu, (y.w[0] | y.w[1] | y.w[2] | y.w[3]) != 0)) y = gf_mul(y, p.key->hpow_thread[nt - tid]);
     y = warp_xor(y);
     gf128* red = reinterpret_cast<gf128*>(ag_smem + SM_MISC);
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(AG_STREAM_NT_MAX, 1) k_stream(const __grid_con
         gf128 v = (tid < (nt >> 5)) ? red[tid] : gf_zero();
         v = warp_xor(v);
         if (tid == 0) {
-            v = gf_mul(v, p.key->hpow_cta[gridDim.x - 1 - blockIdx.x]);
+            v = gf_mul(v, w_cta);
             uint32_t* dst = p.partials + 4 * blockIdx.x;
             dst[0] = v.w[0]; dst[1] = v.w[1]; dst[2] = v.w[2]; dst[3] = v.w[3];
         }
