@@ -44,18 +44,31 @@ __global__ void __launch_bounds__(256) k_key_setup(KeyDev* kd, const __grid_cons
     const uint32_t tid = threadIdx.x;
     __shared__ gf128 s_pow2[64];
     __shared__ uint32_t s_rk[60];
+    __shared__ uint32_t s_te0[256];                      // the serial parts below look up shared memory, not L2
+    __shared__ gf128 s_hthr[AG_STREAM_NT_MAX + 1];       // H^k, k <= NT: built here, written out once
+    __shared__ gf128 s_hcta[AG_MAX_CTA + 1];             // (H^NT)^k, k <= ncta
+    s_te0[tid] = __ldg(te0 + tid);                       // blockDim.x == 256
+    __syncthreads();
+    struct TeShared {
+        const uint32_t* t;
+        __device__ __forceinline__ uint32_t operator()(int tab, uint32_t w, int k) const
+        {
+            const uint32_t v = t[(w >> (8 * k)) & 0xff];
+            return tab ? ag_rotl32(v, 8 * tab) : v;
+        }
+    };
     if (in.pre_expanded) {
         if (tid < 4 * (in.nr + 1)) s_rk[tid] = in.w[tid];
     } else if (tid == 0) {
         uint8_t key[32];
         for (uint32_t j = 0; j < in.key_bytes; ++j) key[j] = (uint8_t)(in.w[j >> 2] >> (8 * (j & 3)));
-        auto sb = [&](uint32_t b) { return (__ldg(te0 + (b & 0xff)) >> 8) & 0xff; };
+        auto sb = [&](uint32_t b) { return (s_te0[b & 0xff] >> 8) & 0xff; };
         aes_key_expand_words(key, (int)in.key_bytes, sb, s_rk);
     }
     __syncthreads();
     if (tid < 60) kd->rk[tid] = tid < 4 * (in.nr + 1) ? s_rk[tid] : 0u;
     if (tid == 0) {
-        TeGlobal te{te0};
+        TeShared te{s_te0};
         uint32_t h[4];
         aes_encrypt_words(s_rk, (int)in.nr, 0, 0, 0, 0, te, h);  // H = E_K(0^128), gcm_gctr.vhd:141-144
         gf128 p = gf_from_le_words(h[0], h[1], h[2], h[3]);
@@ -65,42 +78,44 @@ __global__ void __launch_bounds__(256) k_key_setup(KeyDev* kd, const __grid_cons
         kd->ncta = ncta;
         for (int k = 0; k < 64; ++k) {
             s_pow2[k] = p;
-            kd->pow2[k] = p;
             p = gf_sqr(p);
         }
-        kd->hpow_thread[0] = gf_one();
-        kd->hpow_thread[1] = s_pow2[0];
-        kd->hpow_cta[0] = gf_one();
+        s_hthr[0] = gf_one();
+        s_hthr[1] = s_pow2[0];
+        s_hcta[0] = gf_one();
     }
     __syncthreads();
+    if (tid < 64) kd->pow2[tid] = s_pow2[tid];
     // H^k for k = 2..nt_stream by doubling: H^(2^s + j) = H^j * H^(2^s), j = 1..2^s
     for (uint32_t s = 0; (1u << s) < nt_stream; ++s) {
         const uint32_t half = 1u << s;
         for (uint32_t j = tid; j < half; j += blockDim.x) {
             const uint32_t dst = half + 1 + j;
-            if (dst <= nt_stream) kd->hpow_thread[dst] = gf_mul(kd->hpow_thread[1 + j], s_pow2[s]);
+            if (dst <= nt_stream) s_hthr[dst] = gf_mul(s_hthr[1 + j], s_pow2[s]);
         }
         __syncthreads();
     }
     // (H^NT)^k for k = 1..ncta, same doubling with base powers pow2[log2(NT) + s]
     uint32_t lg = 0;
     while ((1u << lg) < nt_stream) ++lg;
-    if (tid == 0) kd->hpow_cta[1] = s_pow2[lg];
+    if (tid == 0) s_hcta[1] = s_pow2[lg];
     __syncthreads();
     for (uint32_t s = 0; (1u << s) < ncta; ++s) {
         const uint32_t half = 1u << s;
         for (uint32_t j = tid; j < half; j += blockDim.x) {
             const uint32_t dst = half + 1 + j;
-            if (dst <= ncta) kd->hpow_cta[dst] = gf_mul(kd->hpow_cta[1 + j], s_pow2[lg + s]);
+            if (dst <= ncta) s_hcta[dst] = gf_mul(s_hcta[1 + j], s_pow2[lg + s]);
         }
         __syncthreads();
     }
+    for (uint32_t k = tid; k <= nt_stream; k += blockDim.x) kd->hpow_thread[k] = s_hthr[k];
+    for (uint32_t k = tid; k <= ncta; k += blockDim.x) kd->hpow_cta[k] = s_hcta[k];
     // Shoup tables, row b per thread (blockDim.x == 256)
     for (int j = 0; j < 8; ++j) {
         gf128 c;
         if (j < 6) c = s_pow2[j];
         else if (j == 6) c = s_pow2[lg];
-        else c = kd->hpow_cta[ncta];
+        else c = s_hcta[ncta];
         gf128 basis[8];
         basis[0] = c;
 #pragma unroll
